@@ -1,0 +1,485 @@
+"""ctypes binding of the C-ABI in include/cora_b200.h.
+
+This is the binding the tests and bench.py use; it holds no arithmetic.  There is no
+CPU fallback: if the shared library is missing, or no CUDA device is present, the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcora_b200.so")
+
+PRECON_NONE, PRECON_JACOBI, PRECON_BLOCK_CHOLESKY, PRECON_REG_CHOLESKY = 0, 1, 2, 3
+TNT_STATUS = ["Gradient", "PreconditionedGradient", "RelativeDecrease", "Stepsize", "TrustRegion",
+              "IterationLimit", "ElapsedTime", "UserFunction"]
+EINVAL, ERUNTIME, ECUDA, ENOTIMPL = 1, 2, 3, 4
+
+
+class CoraB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+class InvalidArgument(CoraB200Error, ValueError):
+    """std::invalid_argument / MatrixShapeException of the reference."""
+
+
+class NotImplementedInReference(CoraB200Error, NotImplementedError):
+    pass
+
+
+class TntParams(C.Structure):
+    _fields_ = [("Delta0", C.c_double), ("eta1", C.c_double), ("eta2", C.c_double),
+                ("alpha1", C.c_double), ("alpha2", C.c_double),
+                ("max_TPCG_iterations", C.c_int32), ("max_iterations", C.c_int32),
+                ("kappa_fgr", C.c_double), ("theta", C.c_double),
+                ("preconditioned_gradient_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("relative_decrease_tolerance", C.c_double), ("stepsize_tolerance", C.c_double),
+                ("Delta_tolerance", C.c_double), ("max_computation_time", C.c_double),
+                ("verbose", C.c_int32), ("reserved", C.c_int32)]
+
+
+_PD = C.POINTER(C.c_double)
+
+
+class TntResultC(C.Structure):
+    _fields_ = [("f", C.c_double), ("gradfx_norm", C.c_double), ("preconditioned_gradfx_norm", C.c_double),
+                ("elapsed_time", C.c_double), ("device_time", C.c_double),
+                ("status", C.c_int32), ("num_outer", C.c_int32), ("total_inner", C.c_int64),
+                ("kernel_launches", C.c_int64), ("trace_capacity", C.c_int32), ("reserved", C.c_int32),
+                ("objective_values", _PD), ("gradient_norms", _PD), ("preconditioned_gradient_norms", _PD),
+                ("trust_region_radius", _PD), ("time", _PD), ("update_step_norms", _PD),
+                ("update_step_M_norms", _PD), ("gain_ratios", _PD),
+                ("inner_iterations", C.POINTER(C.c_int32))]
+
+
+class StageC(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("status", C.c_int32), ("num_outer", C.c_int32), ("certified", C.c_int32),
+                ("cg_iterations", C.c_int64), ("f", C.c_double), ("gradfx_norm", C.c_double),
+                ("theta", C.c_double), ("eta", C.c_double), ("tnt_seconds", C.c_double),
+                ("cert_seconds", C.c_double)]
+
+
+class SolveResultC(C.Structure):
+    _fields_ = [("f", C.c_double), ("lifted_f", C.c_double), ("final_rank", C.c_int32),
+                ("lifted_rank", C.c_int32), ("certified", C.c_int32), ("num_stages", C.c_int32),
+                ("total_cg_iterations", C.c_int64), ("seconds", C.c_double),
+                ("stage_capacity", C.c_int32), ("reserved", C.c_int32), ("stages", C.POINTER(StageC))]
+
+
+@dataclass
+class TntResult:
+    """Mirror of Optimization::Riemannian::TNTResult (TNT.h:168-194)."""
+    x: Optional[np.ndarray] = None
+    f: float = 0.0
+    gradfx_norm: float = 0.0
+    preconditioned_grad_f_x_norm: float = 0.0
+    status: str = "IterationLimit"
+    elapsed_time: float = 0.0
+    device_time: float = 0.0
+    kernel_launches: int = 0
+    objective_values: List[float] = field(default_factory=list)
+    gradient_norms: List[float] = field(default_factory=list)
+    preconditioned_gradient_norms: List[float] = field(default_factory=list)
+    trust_region_radius: List[float] = field(default_factory=list)
+    time: List[float] = field(default_factory=list)
+    inner_iterations: List[int] = field(default_factory=list)
+    update_step_norms: List[float] = field(default_factory=list)
+    update_step_M_norms: List[float] = field(default_factory=list)
+    gain_ratios: List[float] = field(default_factory=list)
+
+
+@dataclass
+class CertResults:
+    """Mirror of CORA::CertResults (include/CORA/CORA_types.h:58-64)."""
+    is_certified: bool
+    theta: float
+    x: np.ndarray
+    all_eigvecs: np.ndarray
+    num_iters: int
+
+
+_lib = None
+
+# every symbol include/cora_b200.h declares (checked by the CPU test-suite)
+SYMBOLS = [
+    "cora_b200_last_error", "cora_b200_version", "cora_b200_device_count", "cora_b200_create",
+    "cora_b200_destroy", "cora_b200_size", "cora_b200_set_preconditioner", "cora_b200_get_reg_lambda",
+    "cora_b200_set_reg_lambda", "cora_b200_data_matrix_product", "cora_b200_objective", "cora_b200_egrad",
+    "cora_b200_rgrad", "cora_b200_hessvec", "cora_b200_tangent_proj", "cora_b200_precondition",
+    "cora_b200_retract", "cora_b200_project", "cora_b200_lambda_blocks", "cora_b200_certificate_product",
+    "cora_b200_tnt_default_params", "cora_b200_tnt", "cora_b200_set_iterate", "cora_b200_get_iterate",
+    "cora_b200_tnt_resident", "cora_b200_spmm_resident", "cora_b200_certify", "cora_b200_saddle_escape",
+    "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
+    "cora_b200_assemble",
+]
+
+
+def load():
+    """Load libcora_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CoraB200Error(ECUDA, "libcora_b200.so is not built (%s): run `python cora_b200/build.py`; "
+                            "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.cora_b200_last_error.restype = C.c_char_p
+    for s in SYMBOLS:
+        getattr(lib, s)
+    _lib = lib
+    return lib
+
+
+def _check(code):
+    if code == 0:
+        return
+    msg = load().cora_b200_last_error().decode()
+    if code == EINVAL:
+        raise InvalidArgument(code, msg)
+    if code == ENOTIMPL:
+        raise NotImplementedInReference(code, msg)
+    raise CoraB200Error(code, msg)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(load().cora_b200_device_count(C.byref(n)))
+    return n.value
+
+
+def default_tnt_params(**kw) -> TntParams:
+    p = TntParams()
+    _check(load().cora_b200_tnt_default_params(C.byref(p)))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _f64(a, shape=None):
+    """Column-major float64 view/copy (the buffer of an Eigen::MatrixXd)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    a = np.asfortranarray(a)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise InvalidArgument(EINVAL, "expected matrix of shape %s but got %s" % (tuple(shape), tuple(a.shape)))
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(_PD)
+
+
+def layout_roundtrip(d, n, m, nt, Q):
+    """Test hook: CSR -> internal layout -> CSR on the host (no GPU)."""
+    import scipy.sparse as sp
+    Q = sp.csr_matrix(Q)
+    rp = np.ascontiguousarray(Q.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(Q.indices, dtype=np.int32)
+    va = np.ascontiguousarray(Q.data, dtype=np.float64)
+    nnz = int(Q.nnz)
+    orp = np.zeros(Q.shape[0] + 1, dtype=np.int32)
+    oci = np.zeros(max(nnz, 1), dtype=np.int32)
+    ova = np.zeros(max(nnz, 1), dtype=np.float64)
+    stats = np.zeros(8, dtype=np.int64)
+    i32 = C.POINTER(C.c_int32)
+    _check(load().cora_b200_layout_roundtrip(
+        C.c_int(d), C.c_int(n), C.c_int(m), C.c_int(nt), rp.ctypes.data_as(i32), ci.ctypes.data_as(i32),
+        _p(va), C.c_int64(nnz), orp.ctypes.data_as(i32), oci.ctypes.data_as(i32), _p(ova),
+        stats.ctypes.data_as(C.POINTER(C.c_int64))))
+    k = int(stats[7])
+    out = sp.csr_matrix((ova[:k], oci[:k], orp), shape=Q.shape)
+    names = ["num_tiles", "max_slots", "nnz_block", "nnz_spill", "nnz_hub", "num_hub_groups",
+             "block_values_stored", "nnz_out"]
+    return out, dict(zip(names, (int(x) for x in stats)))
+
+
+def assemble(d, n, l, arrays):
+    """Data matrix Q (scipy CSR, reference row order) from flattened measurement stacks."""
+    import scipy.sparse as sp
+    lib = load()
+    i64, f64 = np.int64, np.float64
+    A = {k: np.ascontiguousarray(arrays[k], dtype=(i64 if k in ("rp_i", "rp_j", "rot_i", "rot_j", "rg_a", "rg_b") else f64))
+         for k in ("rp_i", "rp_j", "rp_t", "rp_tau", "rot_i", "rot_j", "rot_R", "rot_kappa", "rg_a", "rg_b", "rg_r", "rg_w")}
+    E, Ep, m = len(A["rp_tau"]), len(A["rot_kappa"]), len(A["rg_w"])
+    pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    nnz = C.c_int64(0)
+    args = [C.c_int(d), C.c_int(n), C.c_int(l), C.c_int64(E), pi(A["rp_i"]), pi(A["rp_j"]), _p(A["rp_t"]),
+            _p(A["rp_tau"]), C.c_int64(Ep), pi(A["rot_i"]), pi(A["rot_j"]), _p(A["rot_R"]), _p(A["rot_kappa"]),
+            C.c_int64(m), pi(A["rg_a"]), pi(A["rg_b"]), _p(A["rg_r"]), _p(A["rg_w"]), C.byref(nnz)]
+    _check(lib.cora_b200_assemble(*args, None, None, None))
+    N = d * n + m + n + l
+    rp = np.zeros(N + 1, dtype=np.int32)
+    ci = np.zeros(max(nnz.value, 1), dtype=np.int32)
+    va = np.zeros(max(nnz.value, 1), dtype=np.float64)
+    i32 = C.POINTER(C.c_int32)
+    _check(lib.cora_b200_assemble(*args, rp.ctypes.data_as(i32), ci.ctypes.data_as(i32), _p(va)))
+    return sp.csr_matrix((va[: nnz.value], ci[: nnz.value], rp), shape=(N, N))
+
+
+class Handle:
+    """One problem on one GPU: the device side of CORA::Problem after updateProblemData()."""
+
+    def __init__(self, d, n_poses, n_ranges, n_trans, Q, preconditioner=PRECON_JACOBI, device=0,
+                 stream=None, reg_chol_max_cond=0.0):
+        import scipy.sparse as sp
+        lib = load()
+        Q = sp.csr_matrix(Q)
+        Q.sort_indices()
+        N = d * n_poses + n_ranges + n_trans
+        if Q.shape != (N, N):
+            raise InvalidArgument(EINVAL, "data matrix has shape %s, expected (%d, %d)" % (Q.shape, N, N))
+        self.d, self.n, self.m, self.nt, self.N = int(d), int(n_poses), int(n_ranges), int(n_trans), int(N)
+        self.nnz = int(Q.nnz)
+        rp = np.ascontiguousarray(Q.indptr, dtype=np.int32)
+        ci = np.ascontiguousarray(Q.indices, dtype=np.int32)
+        va = np.ascontiguousarray(Q.data, dtype=np.float64)
+        self._h = C.c_void_p()
+        i32 = C.POINTER(C.c_int32)
+        _check(lib.cora_b200_create(C.byref(self._h), C.c_int(device), C.c_void_p(stream or 0), C.c_int(d),
+                                    C.c_int(n_poses), C.c_int(n_ranges), C.c_int(n_trans),
+                                    rp.ctypes.data_as(i32), ci.ctypes.data_as(i32), _p(va), C.c_int64(self.nnz),
+                                    C.c_int(preconditioner), C.c_double(reg_chol_max_cond)))
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.cora_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- configuration ------------------------------------------------------
+    def set_preconditioner(self, preconditioner, reg_chol_max_cond=0.0):
+        _check(self._lib.cora_b200_set_preconditioner(self._h, C.c_int(preconditioner),
+                                                      C.c_double(reg_chol_max_cond)))
+
+    @property
+    def reg_lambda(self):
+        v = C.c_double()
+        _check(self._lib.cora_b200_get_reg_lambda(self._h, C.byref(v)))
+        return v.value
+
+    @reg_lambda.setter
+    def reg_lambda(self, lam):
+        _check(self._lib.cora_b200_set_reg_lambda(self._h, C.c_double(lam)))
+
+    # -- tier 1 ---------------------------------------------------------------
+    def _mat(self, A, r=None):
+        A = _f64(A)
+        if A.shape[0] != self.N or (r is not None and A.shape[1] != r):
+            raise InvalidArgument(EINVAL, "expected matrix of shape (%d, %s) but got (%d, %d)"
+                                  % (self.N, r if r is not None else "r", A.shape[0], A.shape[1]))
+        return A
+
+    def data_matrix_product(self, Y):
+        Y = self._mat(Y)
+        out = np.empty_like(Y, order="F")
+        _check(self._lib.cora_b200_data_matrix_product(self._h, Y.shape[1], _p(Y), _p(out)))
+        return out
+
+    def evaluate_objective(self, Y):
+        Y = self._mat(Y)
+        f = C.c_double()
+        _check(self._lib.cora_b200_objective(self._h, Y.shape[1], _p(Y), C.byref(f)))
+        return f.value
+
+    def euclidean_gradient(self, Y):
+        Y = self._mat(Y)
+        out = np.empty_like(Y, order="F")
+        _check(self._lib.cora_b200_egrad(self._h, Y.shape[1], _p(Y), _p(out)))
+        return out
+
+    def riemannian_gradient(self, Y, egrad=None):
+        Y = self._mat(Y)
+        G = self._mat(egrad, Y.shape[1]) if egrad is not None else None
+        out = np.empty_like(Y, order="F")
+        _check(self._lib.cora_b200_rgrad(self._h, Y.shape[1], _p(Y), _p(G) if G is not None else None, _p(out)))
+        return out
+
+    def hessvec(self, Y, egrad, Ydot):
+        Y = self._mat(Y)
+        r = Y.shape[1]
+        G = self._mat(egrad, r) if egrad is not None else None
+        D = self._mat(Ydot, r)
+        out = np.empty_like(Y, order="F")
+        _check(self._lib.cora_b200_hessvec(self._h, r, _p(Y), _p(G) if G is not None else None, _p(D), _p(out)))
+        return out
+
+    def tangent_space_projection(self, Y, V):
+        Y = self._mat(Y)
+        V = self._mat(V, Y.shape[1])
+        out = np.empty_like(Y, order="F")
+        _check(self._lib.cora_b200_tangent_proj(self._h, Y.shape[1], _p(Y), _p(V), _p(out)))
+        return out
+
+    def precondition(self, V):
+        V = self._mat(V)
+        out = np.empty_like(V, order="F")
+        _check(self._lib.cora_b200_precondition(self._h, V.shape[1], _p(V), _p(out)))
+        return out
+
+    def retract(self, Y, V):
+        Y = self._mat(Y)
+        V = self._mat(V, Y.shape[1])
+        out = np.empty_like(Y, order="F")
+        _check(self._lib.cora_b200_retract(self._h, Y.shape[1], _p(Y), _p(V), _p(out)))
+        return out
+
+    def project_to_manifold(self, A):
+        A = self._mat(A)
+        out = np.empty_like(A, order="F")
+        _check(self._lib.cora_b200_project(self._h, A.shape[1], _p(A), _p(out)))
+        return out
+
+    def compute_lambda_blocks(self, Y):
+        Y = self._mat(Y)
+        st = np.zeros((self.d, self.d * self.n), order="F")
+        ob = np.zeros(max(self.m, 1))
+        _check(self._lib.cora_b200_lambda_blocks(self._h, Y.shape[1], _p(Y), _p(st), _p(ob)))
+        return st, ob[: self.m]
+
+    def certificate_product(self, Y, x):
+        Y = self._mat(Y)
+        x = self._mat(x)
+        out = np.empty_like(x, order="F")
+        _check(self._lib.cora_b200_certificate_product(self._h, Y.shape[1], _p(Y), x.shape[1], _p(x), _p(out)))
+        return out
+
+    # -- tier 2 ---------------------------------------------------------------
+    @staticmethod
+    def _alloc_result(cap):
+        res = TntResultC()
+        keep = {}
+        res.trace_capacity = cap
+        for name in ("objective_values", "gradient_norms", "preconditioned_gradient_norms",
+                     "trust_region_radius", "time", "update_step_norms", "update_step_M_norms", "gain_ratios"):
+            keep[name] = np.zeros(cap)
+            setattr(res, name, _p(keep[name]))
+        keep["inner_iterations"] = np.zeros(cap, dtype=np.int32)
+        res.inner_iterations = keep["inner_iterations"].ctypes.data_as(C.POINTER(C.c_int32))
+        return res, keep
+
+    @staticmethod
+    def _unpack_result(res, keep, x=None):
+        k = res.num_outer
+        out = TntResult(x=x, f=res.f, gradfx_norm=res.gradfx_norm,
+                        preconditioned_grad_f_x_norm=res.preconditioned_gradfx_norm,
+                        status=TNT_STATUS[res.status], elapsed_time=res.elapsed_time,
+                        device_time=res.device_time, kernel_launches=res.kernel_launches)
+        for name in ("objective_values", "gradient_norms", "preconditioned_gradient_norms",
+                     "trust_region_radius", "time"):
+            setattr(out, name, keep[name][: k + 1].tolist())
+        for name in ("update_step_norms", "update_step_M_norms", "gain_ratios", "inner_iterations"):
+            setattr(out, name, keep[name][:k].tolist())
+        return out
+
+    def tnt(self, X0, params: Optional[TntParams] = None) -> TntResult:
+        X0 = self._mat(X0)
+        params = params or default_tnt_params()
+        res, keep = self._alloc_result(params.max_iterations + 2)
+        out = np.empty_like(X0, order="F")
+        _check(self._lib.cora_b200_tnt(self._h, X0.shape[1], _p(X0), C.byref(params), _p(out), C.byref(res)))
+        return self._unpack_result(res, keep, out)
+
+    def set_iterate(self, X):
+        X = self._mat(X)
+        _check(self._lib.cora_b200_set_iterate(self._h, X.shape[1], _p(X)))
+
+    def set_iterate_ptr(self, r, host_ptr):
+        """X given as a raw host pointer (e.g. a pinned torch tensor, column-major N x r)."""
+        _check(self._lib.cora_b200_set_iterate(self._h, C.c_int(r), C.cast(host_ptr, _PD)))
+
+    def get_iterate(self, r):
+        out = np.empty((self.N, r), order="F")
+        _check(self._lib.cora_b200_get_iterate(self._h, r, _p(out)))
+        return out
+
+    def get_iterate_ptr(self, r, host_ptr):
+        _check(self._lib.cora_b200_get_iterate(self._h, C.c_int(r), C.cast(host_ptr, _PD)))
+
+    def tnt_resident(self, params: Optional[TntParams] = None) -> TntResult:
+        params = params or default_tnt_params()
+        res, keep = self._alloc_result(params.max_iterations + 2)
+        _check(self._lib.cora_b200_tnt_resident(self._h, C.byref(params), C.byref(res)))
+        return self._unpack_result(res, keep)
+
+    def spmm_resident(self, reps):
+        ms = C.c_float()
+        _check(self._lib.cora_b200_spmm_resident(self._h, C.c_int(reps), C.byref(ms)))
+        return ms.value
+
+    def certify_solution(self, Y, eta, nx, bootstrap=None, max_iters=500) -> CertResults:
+        Y = self._mat(Y)
+        r = Y.shape[1]
+        B = _f64(bootstrap) if bootstrap is not None and np.size(bootstrap) else None
+        cap = max(nx, r + 2)
+        ev = np.zeros((self.N, cap), order="F")
+        x = np.zeros(self.N)
+        cert, ncols = C.c_int(), C.c_int()
+        theta, iters = C.c_double(), C.c_int64()
+        _check(self._lib.cora_b200_certify(self._h, r, _p(Y), C.c_double(eta), C.c_int(nx),
+                                           _p(B) if B is not None else None,
+                                           C.c_int(B.shape[1] if B is not None else 0), C.c_int(max_iters),
+                                           C.byref(cert), C.byref(theta), _p(x), _p(ev), C.c_int(cap),
+                                           C.byref(ncols), C.byref(iters)))
+        return CertResults(bool(cert.value), theta.value, x, ev[:, : ncols.value].copy(), iters.value)
+
+    def saddle_escape(self, Y, theta, v, gradient_tolerance=1e-4, preconditioned_gradient_tolerance=1e-4):
+        Y = self._mat(Y)
+        v = np.ascontiguousarray(v, dtype=np.float64).ravel()
+        if v.shape[0] != self.N:
+            raise InvalidArgument(EINVAL, "v must have N entries")
+        out = np.empty((self.N, Y.shape[1] + 1), order="F")
+        _check(self._lib.cora_b200_saddle_escape(self._h, Y.shape[1] + 1, _p(Y), C.c_double(theta), _p(v),
+                                                 C.c_double(gradient_tolerance),
+                                                 C.c_double(preconditioned_gradient_tolerance), _p(out)))
+        return out
+
+    def project_solution(self, Y):
+        Y = self._mat(Y)
+        out = np.empty((self.N, self.d), order="F")
+        _check(self._lib.cora_b200_project_solution(self._h, Y.shape[1], _p(Y), _p(out)))
+        return out
+
+    def solve(self, X0, max_rank=20, params: Optional[TntParams] = None, verbose=False):
+        X0 = self._mat(X0)
+        params = params or default_tnt_params()
+        cap = 2 * (max_rank + 2)
+        stages = (StageC * cap)()
+        res = SolveResultC()
+        res.stage_capacity = cap
+        res.stages = C.cast(stages, C.POINTER(StageC))
+        out = np.empty((self.N, self.d), order="F")
+        _check(self._lib.cora_b200_solve(self._h, X0.shape[1], _p(X0), C.c_int(max_rank), C.byref(params),
+                                         C.c_int(int(verbose)), _p(out), C.byref(res)))
+        st = []
+        for i in range(min(res.num_stages, cap)):
+            s = stages[i]
+            st.append(dict(rank=s.rank, status=TNT_STATUS[s.status], outer=s.num_outer,
+                           certified=bool(s.certified), cg=s.cg_iterations, f=s.f, grad=s.gradfx_norm,
+                           theta=s.theta, eta=s.eta, tnt_seconds=s.tnt_seconds, cert_seconds=s.cert_seconds))
+        return dict(x=out, f=res.f, lifted_f=res.lifted_f, final_rank=res.final_rank,
+                    lifted_rank=res.lifted_rank, certified=bool(res.certified),
+                    total_cg_iterations=res.total_cg_iterations, seconds=res.seconds, stages=st)

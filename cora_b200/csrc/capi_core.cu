@@ -1,0 +1,417 @@
+// capi_core.cu -- lifecycle + tier-1 (operator level) entry points of the C-ABI.
+#include <mutex>
+
+#include "assemble.hpp"
+#include "chain_chol.cuh"
+#include "ops.cuh"
+#include "solver.cuh"
+
+namespace cora_b200 {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &m) { g_last_error = m; }
+}  // namespace cora_b200
+
+using namespace cora_b200;
+
+#define API_BEGIN try {
+#define API_END                                                  \
+  }                                                              \
+  catch (const cora_b200::Error &e) {                            \
+    set_last_error(e.what());                                    \
+    return e.code;                                               \
+  }                                                              \
+  catch (const std::invalid_argument &e) {                       \
+    set_last_error(e.what());                                    \
+    return CORA_B200_EINVAL;                                     \
+  }                                                              \
+  catch (const std::exception &e) {                              \
+    set_last_error(e.what());                                    \
+    return CORA_B200_ERUNTIME;                                   \
+  }                                                              \
+  return CORA_B200_OK;
+
+static void require(bool ok, const char *msg) {
+  if (!ok) throw Error(CORA_B200_EINVAL, msg);
+}
+
+extern "C" const char *cora_b200_last_error(void) { return g_last_error.c_str(); }
+extern "C" int cora_b200_version(void) { return 100; }
+
+extern "C" int cora_b200_device_count(int *count) {
+  API_BEGIN
+  require(count != nullptr, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  API_END
+}
+
+namespace cora_b200 {
+
+static void fill_dev_layout(H *h) {
+  const HostLayout &L = h->HL;
+  DevLayout &D = h->DL;
+  D.d = L.d; D.D1 = L.D1; D.n = L.n; D.m = L.m; D.l = L.l;
+  D.N = (int)L.N; D.TR = L.TR; D.TP = L.TP; D.numTiles = L.numTiles;
+  D.nPoseRows = (int)L.nPoseRows; D.G = (int)L.G;
+  D.maxSlots = (int)std::max<int64_t>(1, L.max_slots);
+  D.numLong = (int)L.long_grp.size();
+  D.tile_slots = h->d_tile_slots.p; D.tile_boff = h->d_tile_boff.p; D.tile_coff = h->d_tile_coff.p;
+  D.bval = h->d_bval.p; D.bcol = h->d_bcol.p; D.sdiag = h->d_sdiag.p;
+  D.grp_ptr = h->d_grp_ptr.p; D.rem_pk = h->d_rem_pk.p; D.rem_val = h->d_rem_val.p;
+  D.tile_long_ptr = h->d_tile_long_ptr.p; D.long_grp = h->d_long_grp.p; D.long_ptr = h->d_long_ptr.p;
+  D.long_pk = h->d_long_pk.p; D.long_val = h->d_long_val.p;
+  D.dinv = h->d_dinv.p; D.int2ref = h->d_int2ref.p;
+}
+
+}  // namespace cora_b200
+
+extern "C" int cora_b200_create(cora_b200_t **out, int device, void *stream, int d, int n_poses,
+                                int n_ranges, int n_trans, const int32_t *rowptr, const int32_t *col,
+                                const double *val, int64_t nnz, int preconditioner,
+                                double reg_chol_max_cond) {
+  H *h = nullptr;
+  try {
+    require(out != nullptr && rowptr != nullptr && (nnz == 0 || (col != nullptr && val != nullptr)),
+            "NULL argument to cora_b200_create");
+    require(preconditioner >= CORA_B200_PRECON_NONE && preconditioner <= CORA_B200_PRECON_REG_CHOLESKY,
+            "unknown preconditioner");
+    if (preconditioner == CORA_B200_PRECON_BLOCK_CHOLESKY)
+      throw Error(CORA_B200_ENOTIMPL,
+                  "Preconditioner::BlockCholesky is broken in the reference (src/CORA_problem.cpp:515-539) "
+                  "and not implemented");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      throw Error(CORA_B200_ECUDA, "no CUDA device available: cora_b200 has no CPU fallback");
+    }
+    require(device >= 0 && device < ndev, "invalid CUDA device index");
+    CUDA_CHECK(cudaSetDevice(device));
+    h = new H();
+    h->device = device;
+    if (stream) {
+      h->stream = (cudaStream_t)stream;
+    } else {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+      h->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    int TR = 192;
+    if (const char *e = getenv("CORA_B200_TILE_ROWS")) TR = atoi(e);
+    if (const char *e = getenv("CORA_B200_CG_CHUNK")) h->cg_chunk = std::max(1, atoi(e));
+    build_layout(h->HL, d, n_poses, n_ranges, n_trans, rowptr, col, val, nnz, TR);
+    HostLayout &L = h->HL;
+    cudaStream_t s = h->stream;
+    h->d_tile_slots.upload(L.tile_slots, s);
+    { std::vector<long long> t(L.tile_boff.begin(), L.tile_boff.end()); h->d_tile_boff.upload(t, s);
+      std::vector<long long> c(L.tile_coff.begin(), L.tile_coff.end()); h->d_tile_coff.upload(c, s);
+      CUDA_CHECK(cudaStreamSynchronize(s)); }
+    h->d_bval.upload(L.bval, s); h->d_bcol.upload(L.bcol, s); h->d_sdiag.upload(L.sdiag, s);
+    h->d_grp_ptr.upload(L.grp_ptr, s); h->d_rem_pk.upload(L.rem_pk, s); h->d_rem_val.upload(L.rem_val, s);
+    h->d_tile_long_ptr.upload(L.tile_long_ptr, s); h->d_long_grp.upload(L.long_grp, s);
+    h->d_long_ptr.upload(L.long_ptr, s); h->d_long_pk.upload(L.long_pk, s); h->d_long_val.upload(L.long_val, s);
+    h->d_int2ref.upload(L.int2ref, s);
+    h->d_diag.upload(L.diag, s);
+    { std::vector<double> inv(L.diag.size());
+      for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1.0 / L.diag[i];  // src/CORA_problem.cpp:616-618
+      h->d_dinv.upload(inv, s);
+      CUDA_CHECK(cudaStreamSynchronize(s)); }
+    h->d_partials.alloc((size_t)std::max(L.numTiles, h->sm_count * 8) * kNPart);
+    h->d_scal.alloc(SC_COUNT);
+    h->d_counter.alloc(4);
+    h->d_ctrl.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(h->d_counter.p, 0, 4 * sizeof(unsigned), s));
+    CUDA_CHECK(cudaMemsetAsync(h->d_scal.p, 0, SC_COUNT * sizeof(double), s));
+    CUDA_CHECK(cudaMemsetAsync(h->d_ctrl.p, 0, sizeof(CgCtrl), s));
+    CUDA_CHECK(cudaMallocHost((void **)&h->h_scal, SC_COUNT * sizeof(double)));
+    CUDA_CHECK(cudaMallocHost((void **)&h->h_ctrl, 2 * sizeof(CgCtrl)));
+    CUDA_CHECK(cudaEventCreate(&h->ev0));
+    CUDA_CHECK(cudaEventCreate(&h->ev1));
+    CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_chunk[0], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_chunk[1], cudaEventDisableTiming));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    fill_dev_layout(h);
+    h->precond = preconditioner;
+    h->reg_max_cond = reg_chol_max_cond > 0 ? reg_chol_max_cond : 1e6;
+    // the big host copies of the values are no longer needed; the chain factorisation
+    // reads them from the device
+    update_preconditioner(h);
+    *out = h;
+  } catch (const cora_b200::Error &e) {
+    set_last_error(e.what());
+    if (h) cora_b200_destroy(h);
+    return e.code;
+  } catch (const std::invalid_argument &e) {
+    set_last_error(e.what());
+    if (h) cora_b200_destroy(h);
+    return CORA_B200_EINVAL;
+  } catch (const std::exception &e) {
+    set_last_error(e.what());
+    if (h) cora_b200_destroy(h);
+    return CORA_B200_ERUNTIME;
+  }
+  return CORA_B200_OK;
+}
+
+extern "C" int cora_b200_destroy(cora_b200_t *h) {
+  if (!h) return CORA_B200_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  destroy_chain_chol(h->chol);
+  if (h->h_scal) cudaFreeHost(h->h_scal);
+  if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CORA_B200_OK;
+}
+
+extern "C" int cora_b200_size(const cora_b200_t *h, int64_t *N) {
+  API_BEGIN
+  require(h && N, "NULL argument");
+  *N = h->HL.N;
+  API_END
+}
+
+extern "C" int cora_b200_set_preconditioner(cora_b200_t *h, int preconditioner, double reg_chol_max_cond) {
+  API_BEGIN
+  require(h != nullptr, "NULL handle");
+  require(preconditioner >= CORA_B200_PRECON_NONE && preconditioner <= CORA_B200_PRECON_REG_CHOLESKY,
+          "unknown preconditioner");
+  if (preconditioner == CORA_B200_PRECON_BLOCK_CHOLESKY)
+    throw Error(CORA_B200_ENOTIMPL, "Preconditioner::BlockCholesky not implemented");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  h->precond = preconditioner;
+  if (reg_chol_max_cond > 0) h->reg_max_cond = reg_chol_max_cond;
+  update_preconditioner(h);
+  API_END
+}
+
+extern "C" int cora_b200_get_reg_lambda(const cora_b200_t *h, double *lambda) {
+  API_BEGIN
+  require(h && lambda, "NULL argument");
+  *lambda = h->lambda_reg;
+  API_END
+}
+
+extern "C" int cora_b200_set_reg_lambda(cora_b200_t *h, double lambda) {
+  API_BEGIN
+  require(h != nullptr, "NULL handle");
+  require(lambda > 0, "lambda must be positive");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  h->lambda_reg = lambda;
+  h->lambda_user = true;
+  update_preconditioner(h);
+  API_END
+}
+
+// --------------------------------------------------------------------- tier 1 ---
+namespace {
+struct Tier1 {
+  H *h;
+  int r;
+  Tier1(cora_b200_t *h_, int r_, bool geom = true) : h(h_), r(r_) {
+    require(h != nullptr, "NULL handle");
+    if (geom) check_geom_rank(r);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    ensure_workspace(h, r);
+    h->resident_r = 0;  // tier-1 calls clobber the resident iterate
+  }
+  double *v(int i) { return h->ws[i].p; }
+  long long nE() const { return (long long)h->DL.N * r; }
+};
+}  // namespace
+
+extern "C" int cora_b200_data_matrix_product(cora_b200_t *h, int r, const double *Y, double *out) {
+  API_BEGIN
+  require(Y && out, "NULL argument");
+  Tier1 T(h, r, false);
+  import_matrix(h, Y, r, T.v(V_X), r);
+  launch_qprod(h, QM_SPMM, T.v(V_X), nullptr, nullptr, T.v(V_G), nullptr, r, POST_STORE, SC_TMP, nullptr);
+  export_matrix(h, T.v(V_G), r, out);
+  API_END
+}
+
+extern "C" int cora_b200_objective(cora_b200_t *h, int r, const double *Y, double *f) {
+  API_BEGIN
+  require(Y && f, "NULL argument");
+  Tier1 T(h, r);
+  import_matrix(h, Y, r, T.v(V_X), r);
+  launch_qprod(h, QM_GRAD, T.v(V_X), T.v(V_X), nullptr, T.v(V_GRAD), T.v(V_G), r, POST_STORE, SC_XG, nullptr);
+  read_scal(h);
+  *f = 0.5 * h->h_scal[SC_XG];
+  API_END
+}
+
+extern "C" int cora_b200_egrad(cora_b200_t *h, int r, const double *Y, double *G) {
+  return cora_b200_data_matrix_product(h, r, Y, G);
+}
+
+extern "C" int cora_b200_rgrad(cora_b200_t *h, int r, const double *Y, const double *G, double *out) {
+  API_BEGIN
+  require(Y && out, "NULL argument");
+  Tier1 T(h, r);
+  import_matrix(h, Y, r, T.v(V_X), r);
+  if (G) {
+    import_matrix(h, G, r, T.v(V_G), r);
+    launch_tangent(h, T.v(V_X), T.v(V_G), T.v(V_GRAD), r);
+  } else {
+    launch_qprod(h, QM_GRAD, T.v(V_X), T.v(V_X), nullptr, T.v(V_GRAD), T.v(V_G), r, POST_STORE, SC_XG, nullptr);
+  }
+  export_matrix(h, T.v(V_GRAD), r, out);
+  API_END
+}
+
+extern "C" int cora_b200_hessvec(cora_b200_t *h, int r, const double *Y, const double *G,
+                                 const double *Ydot, double *out) {
+  API_BEGIN
+  require(Y && Ydot && out, "NULL argument");
+  Tier1 T(h, r);
+  import_matrix(h, Y, r, T.v(V_X), r);
+  if (G) import_matrix(h, G, r, T.v(V_G), r);
+  else launch_qprod(h, QM_SPMM, T.v(V_X), nullptr, nullptr, T.v(V_G), nullptr, r, POST_STORE, SC_TMP, nullptr);
+  import_matrix(h, Ydot, r, T.v(V_P), r);
+  launch_qprod(h, QM_HESS, T.v(V_P), T.v(V_X), T.v(V_G), T.v(V_HP), nullptr, r, POST_STORE, SC_HHH, nullptr);
+  export_matrix(h, T.v(V_HP), r, out);
+  API_END
+}
+
+extern "C" int cora_b200_tangent_proj(cora_b200_t *h, int r, const double *Y, const double *V, double *out) {
+  API_BEGIN
+  require(Y && V && out, "NULL argument");
+  Tier1 T(h, r);
+  import_matrix(h, Y, r, T.v(V_X), r);
+  import_matrix(h, V, r, T.v(V_T0), r);
+  launch_tangent(h, T.v(V_X), T.v(V_T0), T.v(V_T1), r);
+  export_matrix(h, T.v(V_T1), r, out);
+  API_END
+}
+
+extern "C" int cora_b200_precondition(cora_b200_t *h, int r, const double *V, double *out) {
+  API_BEGIN
+  require(V && out, "NULL argument");
+  Tier1 T(h, r, false);
+  import_matrix(h, V, r, T.v(V_T0), r);
+  apply_preconditioner(h, T.v(V_T0), T.v(V_Z), r, nullptr);
+  export_matrix(h, T.v(V_Z), r, out);
+  API_END
+}
+
+extern "C" int cora_b200_retract(cora_b200_t *h, int r, const double *Y, const double *V, double *out) {
+  API_BEGIN
+  require(Y && V && out, "NULL argument");
+  Tier1 T(h, r);
+  import_matrix(h, Y, r, T.v(V_X), r);
+  import_matrix(h, V, r, T.v(V_T0), r);
+  launch_retract(h, T.v(V_X), T.v(V_T0), 1.0, nullptr, T.v(V_XP), r, -1);
+  export_matrix(h, T.v(V_XP), r, out);
+  API_END
+}
+
+extern "C" int cora_b200_project(cora_b200_t *h, int r, const double *A, double *out) {
+  API_BEGIN
+  require(A && out, "NULL argument");
+  Tier1 T(h, r);
+  import_matrix(h, A, r, T.v(V_X), r);
+  launch_retract(h, T.v(V_X), nullptr, 0.0, nullptr, T.v(V_XP), r, -1);
+  export_matrix(h, T.v(V_XP), r, out);
+  API_END
+}
+
+extern "C" int cora_b200_lambda_blocks(cora_b200_t *h, int r, const double *Y, double *lam_st, double *lam_ob) {
+  API_BEGIN
+  require(Y && lam_st && lam_ob, "NULL argument");
+  Tier1 T(h, r);
+  import_matrix(h, Y, r, T.v(V_X), r);
+  compute_lambda(h, T.v(V_X), r);
+  const size_t ns = (size_t)h->DL.n * h->DL.d * h->DL.d;
+  if (ns) CUDA_CHECK(cudaMemcpyAsync(lam_st, h->d_lam_st.p, ns * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (h->DL.m) CUDA_CHECK(cudaMemcpyAsync(lam_ob, h->d_lam_ob.p, (size_t)h->DL.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+extern "C" int cora_b200_certificate_product(cora_b200_t *h, int r, const double *Y, int k, const double *x,
+                                             double *out) {
+  API_BEGIN
+  require(Y && x && out && k > 0, "bad argument");
+  Tier1 T(h, std::max(r, k), false);
+  check_geom_rank(r);
+  import_matrix(h, Y, r, T.v(V_X), r);
+  compute_lambda(h, T.v(V_X), r);
+  DevLayout LS = build_certificate_layout(h, 0.0);
+  import_matrix(h, x, k, T.v(V_T0), k);
+  launch_qprod(h, QM_SPMM, T.v(V_T0), nullptr, nullptr, T.v(V_T1), nullptr, k, POST_STORE, SC_TMP, nullptr, &LS);
+  export_matrix(h, T.v(V_T1), k, out);
+  API_END
+}
+
+extern "C" int cora_b200_layout_roundtrip(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
+                                          const int32_t *col, const double *val, int64_t nnz,
+                                          int32_t *out_rowptr, int32_t *out_col, double *out_val,
+                                          int64_t *stats) {
+  API_BEGIN
+  require(rowptr && out_rowptr && stats, "NULL argument");
+  HostLayout L;
+  int TR = 192;
+  if (const char *e = getenv("CORA_B200_TILE_ROWS")) TR = atoi(e);
+  build_layout(L, d, n_poses, n_ranges, n_trans, rowptr, col, val, nnz, TR);
+  std::vector<int32_t> rp, ci;
+  std::vector<double> v;
+  layout_to_csr(L, rp, ci, v);
+  if ((int64_t)ci.size() > nnz) throw Error(CORA_B200_ERUNTIME, "layout round trip produced more entries than the input");
+  std::memcpy(out_rowptr, rp.data(), rp.size() * sizeof(int32_t));
+  if (!ci.empty()) {
+    std::memcpy(out_col, ci.data(), ci.size() * sizeof(int32_t));
+    std::memcpy(out_val, v.data(), v.size() * sizeof(double));
+  }
+  stats[0] = L.numTiles; stats[1] = L.max_slots; stats[2] = L.nnz_block; stats[3] = L.nnz_rem;
+  stats[4] = L.nnz_long; stats[5] = (int64_t)L.long_grp.size(); stats[6] = (int64_t)L.bval.size();
+  stats[7] = (int64_t)ci.size();
+  API_END
+}
+
+// ------------------------------------------------------------------ assembly ----
+namespace {
+std::vector<int32_t> g_asm_rowptr, g_asm_col;
+std::vector<double> g_asm_val;
+std::mutex g_asm_mutex;
+}  // namespace
+
+extern "C" int cora_b200_assemble(int d, int n_poses, int n_landmarks, int64_t E, const int64_t *rp_i,
+                                  const int64_t *rp_j, const double *rp_t, const double *rp_tau, int64_t Ep,
+                                  const int64_t *rot_i, const int64_t *rot_j, const double *rot_R,
+                                  const double *rot_kappa, int64_t m, const int64_t *rg_a, const int64_t *rg_b,
+                                  const double *rg_r, const double *rg_w, int64_t *nnz, int32_t *rowptr,
+                                  int32_t *col, double *val) {
+  API_BEGIN
+  require(nnz != nullptr, "NULL nnz");
+  std::lock_guard<std::mutex> lock(g_asm_mutex);
+  if (rowptr == nullptr) {  // phase 1: assemble, report nnz, keep the result for phase 2
+    Measurements M{d, n_poses, n_landmarks, E, rp_i, rp_j, rp_t, rp_tau, Ep, rot_i, rot_j, rot_R, rot_kappa,
+                   m, rg_a, rg_b, rg_r, rg_w};
+    assemble_data_matrix(M, g_asm_rowptr, g_asm_col, g_asm_val);
+    *nnz = (int64_t)g_asm_col.size();
+  } else {  // phase 2: copy out
+    require(*nnz == (int64_t)g_asm_col.size() && !g_asm_rowptr.empty(), "call with rowptr == NULL first");
+    std::memcpy(rowptr, g_asm_rowptr.data(), g_asm_rowptr.size() * sizeof(int32_t));
+    if (*nnz) {
+      require(col && val, "NULL output");
+      std::memcpy(col, g_asm_col.data(), g_asm_col.size() * sizeof(int32_t));
+      std::memcpy(val, g_asm_val.data(), g_asm_val.size() * sizeof(double));
+    }
+    std::vector<int32_t>().swap(g_asm_rowptr);
+    std::vector<int32_t>().swap(g_asm_col);
+    std::vector<double>().swap(g_asm_val);
+  }
+  API_END
+}

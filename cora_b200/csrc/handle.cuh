@@ -1,0 +1,93 @@
+// handle.cuh -- the device-side problem handle and its launch helpers.
+#pragma once
+#include <chrono>
+#include <cstring>
+
+#include "internal.cuh"
+
+namespace cora_b200 {
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    free();
+    n = count;
+    if (count) CUDA_CHECK(cudaMalloc((void **)&p, count * sizeof(T)));
+  }
+  void upload(const std::vector<T> &v, cudaStream_t s) {
+    alloc(v.size() ? v.size() : 1);
+    if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { free(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+};
+
+// names of the N x r work vectors
+enum Vec {
+  V_X = 0,   // current iterate
+  V_G,       // Euclidean gradient Q X
+  V_GRAD,    // Riemannian gradient
+  V_PG,      // preconditioned gradient / STPCG v
+  V_S,       // STPCG step
+  V_R,       // STPCG residual
+  V_P,       // STPCG direction
+  V_HP,      // Hess p
+  V_XP,      // proposed iterate
+  V_GP,      // Q X+
+  V_GRADP,   // grad at X+
+  V_Z,       // external preconditioner output / scratch
+  V_T0,      // scratch (tier-1 staging)
+  V_T1,
+  V_COUNT
+};
+
+struct ChainChol;  // chain_chol.cuh
+
+}  // namespace cora_b200
+
+struct cora_b200_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  cora_b200::HostLayout HL;  // structure (values freed after upload)
+  cora_b200::DevLayout DL{};
+  // device copies of the layout
+  cora_b200::DevBuf<int> d_tile_slots, d_bcol, d_grp_ptr, d_tile_long_ptr, d_long_grp, d_long_ptr, d_int2ref;
+  cora_b200::DevBuf<long long> d_tile_boff, d_tile_coff;
+  cora_b200::DevBuf<unsigned> d_rem_pk, d_long_pk;
+  cora_b200::DevBuf<double> d_bval, d_sdiag, d_rem_val, d_long_val, d_dinv, d_diag;
+  // certificate values S + eta I on the same structure
+  cora_b200::DevBuf<double> d_bvalS, d_sdiagS, d_lam_st, d_lam_ob;
+  // workspace
+  int ws_r = 0;
+  cora_b200::DevBuf<double> ws[cora_b200::V_COUNT];
+  cora_b200::DevBuf<double> d_stage;    // reference-layout staging, N x ws_r
+  cora_b200::DevBuf<double> d_longbuf;  // numLong x D1 x ws_r
+  cora_b200::DevBuf<double> d_partials;
+  cora_b200::DevBuf<double> d_scal;
+  cora_b200::DevBuf<unsigned> d_counter;
+  cora_b200::DevBuf<cora_b200::CgCtrl> d_ctrl;
+  double *h_scal = nullptr;             // pinned
+  cora_b200::CgCtrl *h_ctrl = nullptr;  // pinned
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr};
+  // preconditioner
+  int precond = CORA_B200_PRECON_JACOBI;
+  double reg_max_cond = 1e6;
+  double lambda_reg = -1.0;
+  bool lambda_user = false;
+  cora_b200::ChainChol *chol = nullptr;  // RegularizedCholesky factor of (Q + lambda I)[:-1,:-1]
+  // resident iterate rank
+  int resident_r = 0;
+  int64_t launches = 0;
+  int cg_chunk = 8;
+};

@@ -1,0 +1,309 @@
+// solver.cuh -- device-resident STPCG and the TNT outer loop.
+//
+//   STPCG  libs/Optimization/include/Optimization/LinearAlgebra/IterativeSolvers.h:166-426
+//   TNT    libs/Optimization/include/Optimization/Riemannian/TNT.h:242-689
+//   closures (f, QM, metric, retract, precon): src/CORA.cpp:52-122
+//
+// One CG iteration is three launches (k_qprod<HESS>, k_cg_update, k_cg_pupdate); all
+// scalars of the recurrences live in CgCtrl on the device and are advanced by the last
+// CTA of each reduction, so the host only polls a "done" flag once per chunk of
+// iterations (with one chunk of look-ahead so the GPU never idles).
+#pragma once
+#include <cmath>
+
+#include "chain_chol.cuh"
+#include "ops.cuh"
+
+namespace cora_b200 {
+
+// Z = M^-1 V  (Problem::precondition, src/CORA_problem.cpp:869-903), no projection.
+inline void apply_preconditioner(H *h, const double *V, double *Z, int r, const CgCtrl *ctrl) {
+  const long long nE = (long long)h->DL.N * r;
+  if (h->precond == CORA_B200_PRECON_JACOBI) {
+    k_jacobi<<<flat_grid(h, nE), kThreads, 0, h->stream>>>(h->DL.dinv, V, Z, r, nE);
+    check_launch(h);
+  } else if (h->precond == CORA_B200_PRECON_REG_CHOLESKY) {
+    if (!h->chol) throw Error(CORA_B200_ERUNTIME, "RegularizedCholesky factor missing");
+    chain_solve(h, h->chol, V, Z, r, ctrl);
+  } else {
+    throw Error(CORA_B200_EINVAL, "The desired preconditioner is not implemented");  // :892-894
+  }
+}
+
+// V = proj_Y(M^-1 R) with <R,V>, <V,V> -> scal[slot..slot+1]   (src/CORA.cpp:89-92)
+inline void precondition_project(H *h, const double *Y, double *R, double *Vout, int r, int slot) {
+  UArgs A{};
+  A.Y = Y; A.R = R; A.V = Vout; A.r = r; A.do_axpy = 0; A.do_proj = 1; A.post = POST_STORE; A.slot = slot;
+  A.gated = 0; A.ctrl = nullptr;
+  if (h->precond == CORA_B200_PRECON_JACOBI) {
+    A.zsrc = 0;
+  } else {
+    apply_preconditioner(h, R, h->ws[V_Z].p, r, nullptr);
+    A.zsrc = 2;
+    A.Z = h->ws[V_Z].p;
+  }
+  launch_update(h, A);
+}
+
+inline void update_preconditioner(H *h) {
+  destroy_chain_chol(h->chol);
+  h->chol = nullptr;
+  if (h->precond == CORA_B200_PRECON_REG_CHOLESKY) {
+    if (!h->lambda_user) h->lambda_reg = estimate_spectral_norm(h) / (h->reg_max_cond - 1.0);  // :556-591
+    bool pd = false;
+    h->chol = build_chain_chol(h, h->d_bval.p, h->d_sdiag.p, h->lambda_reg, /*pin_last=*/true, &pd);
+    if (!pd) throw Error(CORA_B200_ERUNTIME, "RegularizedCholesky: Q + lambda I is not positive definite");
+  }
+}
+
+inline void compute_lambda(H *h, const double *X, int r) {
+  launch_qprod(h, QM_SPMM, X, nullptr, nullptr, h->ws[V_G].p, nullptr, r, POST_STORE, SC_TMP, nullptr);
+  const size_t ns = (size_t)h->DL.n * h->DL.d * h->DL.d;
+  if (h->d_lam_st.n < std::max<size_t>(ns, 1)) h->d_lam_st.alloc(std::max<size_t>(ns, 1));
+  if (h->d_lam_ob.n < (size_t)std::max(h->DL.m, 1)) h->d_lam_ob.alloc((size_t)std::max(h->DL.m, 1));
+  const int tot = h->DL.n + h->DL.m;
+  if (tot > 0) {
+    DISPATCH_D(h, k_lambda<DD><<<(tot + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(
+                      h->DL, X, h->ws[V_G].p, h->d_lam_st.p, h->d_lam_ob.p, r));
+    check_launch(h);
+  }
+}
+
+// Values of S + eta I on Q's structure (needs compute_lambda first).
+inline DevLayout build_certificate_layout(H *h, double eta) {
+  const size_t nb = (size_t)h->HL.tile_boff[h->HL.numTiles];
+  const size_t ns = (size_t)h->DL.l + h->DL.m;
+  if (h->d_bvalS.n < std::max<size_t>(nb, 1)) h->d_bvalS.alloc(std::max<size_t>(nb, 1));
+  if (h->d_sdiagS.n < std::max<size_t>(ns, 1)) h->d_sdiagS.alloc(std::max<size_t>(ns, 1));
+  if (nb) CUDA_CHECK(cudaMemcpyAsync(h->d_bvalS.p, h->d_bval.p, nb * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  const int tot = h->DL.n + h->DL.l + h->DL.m;
+  if (tot > 0) {
+    DISPATCH_D(h, k_patch_certificate<DD><<<(tot + kThreads - 1) / kThreads, kThreads, 0, h->stream>>>(
+                      h->DL, h->d_lam_st.p, h->d_lam_ob.p, eta, h->d_bvalS.p, h->d_sdiagS.p));
+    check_launch(h);
+  }
+  DevLayout LS = h->DL;
+  LS.bval = h->d_bvalS.p;
+  LS.sdiag = h->d_sdiagS.p;
+  return LS;
+}
+
+// ------------------------------------------------------------------- STPCG -----
+struct StpcgOut {
+  double hM = 0.0;
+  int iterations = 0;
+  int exit_reason = 0;
+};
+
+inline void enqueue_cg_iteration(H *h, int r) {
+  double *X = h->ws[V_X].p, *G = h->ws[V_G].p, *P = h->ws[V_P].p, *HP = h->ws[V_HP].p;
+  CgCtrl *ctrl = h->d_ctrl.p;
+  launch_qprod(h, QM_HESS, P, X, G, HP, nullptr, r, POST_CG_HESS, 0, ctrl);
+  UArgs A{};
+  A.Y = X; A.P = P; A.HP = HP; A.S = h->ws[V_S].p; A.R = h->ws[V_R].p; A.V = h->ws[V_PG].p;
+  A.ctrl = ctrl; A.r = r; A.gated = 1; A.post = POST_CG_UPDATE;
+  if (h->precond == CORA_B200_PRECON_JACOBI) {
+    A.do_axpy = 1; A.zsrc = 0; A.do_proj = 1;
+    launch_update(h, A);
+  } else {
+    A.do_axpy = 1; A.do_proj = 0;
+    launch_update(h, A);
+    apply_preconditioner(h, h->ws[V_R].p, h->ws[V_Z].p, r, ctrl);
+    A.do_axpy = 0; A.zsrc = 2; A.Z = h->ws[V_Z].p; A.do_proj = 1;
+    launch_update(h, A);
+  }
+  const long long nE = (long long)h->DL.N * r;
+  k_cg_pupdate<<<flat_grid(h, nE), kThreads, 0, h->stream>>>(ctrl, h->ws[V_PG].p, P, nE);
+  check_launch(h);
+}
+
+// Solve for the step S at the current iterate (V_X, V_G, V_GRAD, V_PG = P(grad)).
+inline StpcgOut run_stpcg(H *h, int r, double Delta, const cora_b200_tnt_params &p, int rv_slot) {
+  if (!(Delta > 0)) throw Error(CORA_B200_EINVAL, "Trust-region radius (Delta) must be a positive real value");
+  const long long nE = (long long)h->DL.N * r;
+  const int max_it = p.max_TPCG_iterations;
+  k_cg_init<<<flat_grid(h, nE), kThreads, 0, h->stream>>>(h->d_ctrl.p, h->d_scal.p, rv_slot, Delta, max_it,
+                                                         p.kappa_fgr, p.theta, 1e-8, h->ws[V_GRAD].p,
+                                                         h->ws[V_PG].p, h->ws[V_S].p, h->ws[V_R].p,
+                                                         h->ws[V_P].p, nE);
+  check_launch(h);
+  int launched = 0, nchunks = 0;
+  auto enqueue_chunk = [&]() {
+    for (int i = 0; i < h->cg_chunk && launched < max_it; ++i, ++launched) enqueue_cg_iteration(h, r);
+    const int b = nchunks & 1;
+    CUDA_CHECK(cudaMemcpyAsync(&h->h_ctrl[b], h->d_ctrl.p, sizeof(CgCtrl), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaEventRecord(h->ev_chunk[b], h->stream));
+    ++nchunks;
+  };
+  enqueue_chunk();
+  int k = 0;
+  CgCtrl fin;
+  for (;;) {
+    if (nchunks == k + 1 && launched < max_it) enqueue_chunk();  // one chunk of look-ahead
+    CUDA_CHECK(cudaEventSynchronize(h->ev_chunk[k & 1]));
+    fin = h->h_ctrl[k & 1];
+    if (fin.state != 0) break;
+    ++k;
+    if (k >= nchunks) {
+      if (launched >= max_it) throw Error(CORA_B200_ERUNTIME, "STPCG did not terminate (internal error)");
+      enqueue_chunk();
+    }
+  }
+  if (nchunks > k + 1) CUDA_CHECK(cudaEventSynchronize(h->ev_chunk[(k + 1) & 1]));  // drain look-ahead
+  StpcgOut out;
+  out.iterations = fin.it;
+  out.hM = fin.hM;
+  out.exit_reason = fin.exit_reason;
+  if (fin.exit_reason == CG_EXIT_KERNEL) {
+    // IterativeSolvers.h:305-338, finished from the host: p lies in ker(H)
+    launch_dot2(h, h->ws[V_P].p, h->ws[V_R].p, nullptr, nullptr, nE, SC_TMP);
+    read_scal(h);
+    double sMp = fin.sMp, sgn = 1.0;
+    if (h->h_scal[SC_TMP] < 0) { sgn = -1.0; sMp = -sMp; }
+    const double sigma = (-sMp + std::sqrt(sMp * sMp + fin.pM2 * (fin.Delta2 - fin.sM2))) / fin.pM2;
+    launch_axpby(h, 1.0, h->ws[V_S].p, sigma * sgn, h->ws[V_P].p, h->ws[V_S].p, nE);
+    out.hM = fin.Delta;
+  }
+  return out;
+}
+
+// --------------------------------------------------------------------- TNT -----
+struct TraceWriter {
+  cora_b200_tnt_result *res;
+  int n_state = 0, n_iter = 0;
+  void state(double t, double f, double g, double pg, double Delta) {
+    if (n_state < res->trace_capacity) {
+      if (res->time) res->time[n_state] = t;
+      if (res->objective_values) res->objective_values[n_state] = f;
+      if (res->gradient_norms) res->gradient_norms[n_state] = g;
+      if (res->preconditioned_gradient_norms) res->preconditioned_gradient_norms[n_state] = pg;
+      if (res->trust_region_radius) res->trust_region_radius[n_state] = Delta;
+    }
+    ++n_state;
+  }
+  void iter(int inner, double hn, double hM, double rho) {
+    if (n_iter < res->trace_capacity) {
+      if (res->inner_iterations) res->inner_iterations[n_iter] = inner;
+      if (res->update_step_norms) res->update_step_norms[n_iter] = hn;
+      if (res->update_step_M_norms) res->update_step_M_norms[n_iter] = hM;
+      if (res->gain_ratios) res->gain_ratios[n_iter] = rho;
+    }
+    ++n_iter;
+  }
+};
+
+inline void swap_vec(H *h, int a, int b) {
+  std::swap(h->ws[a].p, h->ws[b].p);
+  std::swap(h->ws[a].n, h->ws[b].n);
+}
+
+inline void tnt_resident(H *h, int r, const cora_b200_tnt_params &p, cora_b200_tnt_result *res) {
+  check_geom_rank(r);
+  if (h->precond != CORA_B200_PRECON_JACOBI && h->precond != CORA_B200_PRECON_REG_CHOLESKY)
+    throw Error(CORA_B200_EINVAL, "The desired preconditioner is not implemented");
+  ensure_workspace(h, r);
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  auto elapsed = [&]() { return std::chrono::duration<double>(clk::now() - t0).count(); };
+  const int64_t launches0 = h->launches;
+  CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  TraceWriter tw{res};
+  const double sqrt_eps = std::sqrt(2.220446049250313e-16);
+  auto v = [&](int i) { return h->ws[i].p; };
+
+  // TNT.h:372-392: f(x), QM(x), gradient norms
+  launch_qprod(h, QM_GRAD, v(V_X), v(V_X), nullptr, v(V_GRAD), v(V_G), r, POST_STORE, SC_XG, nullptr);
+  int rv_slot = SC_RV, rv_slot_prop = SC_RV2;
+  precondition_project(h, v(V_X), v(V_GRAD), v(V_PG), r, rv_slot);
+  read_scal(h);
+  double fx = 0.5 * h->h_scal[SC_XG];
+  double gnorm = std::sqrt(h->h_scal[SC_GG]);
+  double pgnorm = std::sqrt(h->h_scal[rv_slot + 1]);
+  double Delta = p.Delta0;
+  int status = CORA_B200_TNT_ITERATION_LIMIT;
+  int64_t total_inner = 0;
+  int iteration = 0;
+  for (; iteration < p.max_iterations; ++iteration) {
+    const double el = elapsed();
+    if (p.max_computation_time > 0 && el > p.max_computation_time) {  // TNT.h:447-452
+      status = CORA_B200_TNT_ELAPSED_TIME;
+      break;
+    }
+    tw.state(el, fx, gnorm, pgnorm, Delta);
+    if (p.verbose)
+      std::printf("Iter: %4d, time: %.3e, f: %.8e, |g|: %.3e, |M^{-1}g|: %.3e", iteration, el, fx, gnorm, pgnorm);
+    if (gnorm < p.gradient_tolerance) { status = CORA_B200_TNT_GRADIENT; break; }  // :474-481
+    if (pgnorm < p.preconditioned_gradient_tolerance) { status = CORA_B200_TNT_PRECONDITIONED_GRADIENT; break; }
+
+    const StpcgOut cg = run_stpcg(h, r, Delta, p, rv_slot);  // :489-492
+    total_inner += cg.iterations;
+    // proposed point, its objective / gradient, model decrease (TNT.h:503-512); the
+    // preconditioned gradient at the proposal is computed speculatively so that one
+    // host synchronisation per outer iteration suffices
+    launch_retract(h, v(V_X), v(V_S), 1.0, v(V_GRAD), v(V_XP), r, SC_HH);
+    launch_qprod(h, QM_GRAD, v(V_XP), v(V_XP), nullptr, v(V_GRADP), v(V_GP), r, POST_STORE, SC_XG2, nullptr);
+    launch_qprod(h, QM_HESS, v(V_S), v(V_X), v(V_G), v(V_HP), nullptr, r, POST_STORE, SC_HHH, nullptr);
+    precondition_project(h, v(V_XP), v(V_GRADP), v(V_T0), r, rv_slot_prop);
+    read_scal(h);
+    const double hnorm = std::sqrt(h->h_scal[SC_HH]);
+    const double fxp = 0.5 * h->h_scal[SC_XG2];
+    const double dm = -h->h_scal[SC_GH] - 0.5 * h->h_scal[SC_HHH];
+    const double df = fx - fxp;
+    const double rel = df / (sqrt_eps + std::fabs(fx));
+    const double rho = df / dm;
+    const bool accepted = !std::isnan(rho) && rho > p.eta1;  // :532
+    tw.iter(cg.iterations, hnorm, cg.hM, rho);
+    if (p.verbose)
+      std::printf(", Delta: %.3e, inner iters: %3d, |h|: %.3e, |h|_M: %.3e, df: %.6e, rho: %.3e. %s\n", Delta,
+                  cg.iterations, hnorm, cg.hM, df, rho, accepted ? "Step accepted" : "Step REJECTED!");
+    if (accepted) {
+      swap_vec(h, V_X, V_XP);
+      fx = fxp;
+      if (rel < p.relative_decrease_tolerance) {  // :561-564 (gradient of the old point is reported)
+        status = CORA_B200_TNT_RELATIVE_DECREASE;
+        ++iteration;
+        break;
+      }
+      if (hnorm < p.stepsize_tolerance) {  // :567-570
+        status = CORA_B200_TNT_STEPSIZE;
+        ++iteration;
+        break;
+      }
+      swap_vec(h, V_G, V_GP);  // QM(x) :573
+      swap_vec(h, V_GRAD, V_GRADP);
+      swap_vec(h, V_PG, V_T0);
+      std::swap(rv_slot, rv_slot_prop);
+      gnorm = std::sqrt(h->h_scal[SC_GG2]);
+      pgnorm = std::sqrt(h->h_scal[rv_slot + 1]);
+    }
+    if (!std::isnan(rho) && rho >= p.eta2) {  // :590-603
+      Delta = std::max(p.alpha2 * cg.hM, Delta);
+    } else if (std::isnan(rho) || rho < p.eta1) {
+      Delta = p.alpha1 * cg.hM;
+      if (Delta < p.Delta_tolerance) {
+        status = CORA_B200_TNT_TRUST_REGION;
+        ++iteration;
+        break;
+      }
+    }
+  }
+  CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  CUDA_CHECK(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  const double el = elapsed();
+  tw.state(el, fx, gnorm, pgnorm, Delta);
+  if (p.verbose) std::printf("\n");
+  res->f = fx;
+  res->gradfx_norm = gnorm;
+  res->preconditioned_gradfx_norm = pgnorm;
+  res->elapsed_time = el;
+  res->device_time = ms * 1e-3;
+  res->status = status;
+  res->num_outer = tw.n_iter;
+  res->total_inner = total_inner;
+  res->kernel_launches = h->launches - launches0;
+  h->resident_r = r;
+}
+
+}  // namespace cora_b200

@@ -1,0 +1,269 @@
+/* cora_b200.h -- C-ABI of the B200-native CORA staircase inner loop.
+ *
+ * The reference (MarineRoboticsGroup/cora @ 015dc43) has no FFI seam: its solver
+ * reaches the hot path only through the Riemannian methods of CORA::Problem and
+ * through solveCORA().  This header is the seam a maintainer would bind instead;
+ * every entry point names the reference interface it replaces (paths relative to
+ * the reference root).  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions (all pointers are HOST memory unless the name ends in _dev):
+ *   dense matrices  column-major double, leading dimension = rows -- exactly the
+ *                   buffer of an Eigen::MatrixXd (include/CORA/CORA_types.h:47-48)
+ *   data matrix     CSR int32 rowptr[N+1], int32 col[nnz], double val[nnz] -- the
+ *                   compressed Eigen::SparseMatrix<double,RowMajor>
+ *                   (include/CORA/CORA_types.h:70); both triangles stored
+ *   row order       [d rows per pose | one row per range factor | n pose
+ *                   translations | l landmark translations]
+ *                   (src/CORA_problem.cpp:964-1021)
+ *   status          every function returns 0 on success, a CORA_B200_E* code
+ *                   otherwise; cora_b200_last_error() returns the message the C++
+ *                   shim rethrows as the matching reference exception.
+ *   threading       one handle <-> one CUDA device + one stream; handles are
+ *                   independent.  A handle is not re-entrant (the reference
+ *                   Problem is not either: include/CORA/CORA_problem.h:270-280).
+ */
+#ifndef CORA_B200_H_
+#define CORA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CORA_B200_OK 0
+#define CORA_B200_EINVAL 1   /* std::invalid_argument / MatrixShapeException   */
+#define CORA_B200_ERUNTIME 2 /* std::runtime_error                              */
+#define CORA_B200_ECUDA 3    /* CUDA failure or no CUDA device: never a CPU fallback */
+#define CORA_B200_ENOTIMPL 4 /* NotImplementedException (CORA_types.h:15-19)    */
+
+/* enum class Preconditioner (include/CORA/CORA_types.h:76-77) */
+#define CORA_B200_PRECON_NONE 0
+#define CORA_B200_PRECON_JACOBI 1
+#define CORA_B200_PRECON_BLOCK_CHOLESKY 2 /* broken in the reference; ENOTIMPL */
+#define CORA_B200_PRECON_REG_CHOLESKY 3
+
+/* enum class TNTStatus (libs/Optimization/.../Riemannian/TNT.h:134-164) */
+#define CORA_B200_TNT_GRADIENT 0
+#define CORA_B200_TNT_PRECONDITIONED_GRADIENT 1
+#define CORA_B200_TNT_RELATIVE_DECREASE 2
+#define CORA_B200_TNT_STEPSIZE 3
+#define CORA_B200_TNT_TRUST_REGION 4
+#define CORA_B200_TNT_ITERATION_LIMIT 5
+#define CORA_B200_TNT_ELAPSED_TIME 6
+#define CORA_B200_TNT_USER_FUNCTION 7
+
+typedef struct cora_b200_handle cora_b200_t;
+
+const char *cora_b200_last_error(void);
+int cora_b200_version(void);
+/* number of visible CUDA devices (0 on a CPU-only host; not an error) */
+int cora_b200_device_count(int *count);
+
+/* ---- lifecycle: what Problem::updateProblemData() does once per problem -------
+ * (src/CORA_problem.cpp:500-510: fillDataMatrix :625-712 has produced the CSR;
+ * updatePreconditioner :512-623 is done inside create).  The handle copies Q, so
+ * the caller may free its buffers.  `stream` is a cudaStream_t (NULL: the handle
+ * creates its own non-blocking stream).  reg_chol_max_cond: the reference's
+ * $CORA_REG_CHOLESKY_MAX_COND (:582), <= 0 selects its default 1e6. */
+int cora_b200_create(cora_b200_t **h, int device, void *stream, int d, int n_poses,
+                     int n_ranges, int n_trans, const int32_t *rowptr,
+                     const int32_t *col, const double *val, int64_t nnz,
+                     int preconditioner, double reg_chol_max_cond);
+int cora_b200_destroy(cora_b200_t *h);
+int cora_b200_size(const cora_b200_t *h, int64_t *N);
+/* Problem::setPreconditioner (include/CORA/CORA_problem.h:335-337) + updatePreconditioner */
+int cora_b200_set_preconditioner(cora_b200_t *h, int preconditioner, double reg_chol_max_cond);
+/* lambda of RegularizedCholesky actually used (src/CORA_problem.cpp:591) */
+int cora_b200_get_reg_lambda(const cora_b200_t *h, double *lambda);
+/* override lambda (parity runs pass the oracle's converged ||Q||_2/(c-1)) */
+int cora_b200_set_reg_lambda(cora_b200_t *h, double lambda);
+
+/* ---- tier 1: operator level (include/CORA/CORA_problem.h:340-350) ------------
+ * Y, G, Ydot, V, A, out are N x r.  One upload + kernels + one download each; the
+ * performance path is tier 2. */
+/* Problem::dataMatrixProduct, src/CORA_problem.cpp:742-757 (Explicit) */
+int cora_b200_data_matrix_product(cora_b200_t *h, int r, const double *Y, double *out);
+/* Problem::evaluateObjective, :759-762 */
+int cora_b200_objective(cora_b200_t *h, int r, const double *Y, double *f);
+/* Problem::Euclidean_gradient, :764-770 */
+int cora_b200_egrad(cora_b200_t *h, int r, const double *Y, double *G);
+/* Problem::Riemannian_gradient(Y, NablaF_Y), :772-780; G may be NULL (recomputed) */
+int cora_b200_rgrad(cora_b200_t *h, int r, const double *Y, const double *G, double *out);
+/* Problem::Riemannian_Hessian_vector_product, :822-867 */
+int cora_b200_hessvec(cora_b200_t *h, int r, const double *Y, const double *G,
+                      const double *Ydot, double *out);
+/* Problem::tangent_space_projection, :782-820 */
+int cora_b200_tangent_proj(cora_b200_t *h, int r, const double *Y, const double *V,
+                           double *out);
+/* Problem::precondition, :869-903 (no tangent projection; src/CORA.cpp:89-92 adds it) */
+int cora_b200_precondition(cora_b200_t *h, int r, const double *V, double *out);
+/* Problem::retract, :936-938 */
+int cora_b200_retract(cora_b200_t *h, int r, const double *Y, const double *V, double *out);
+/* Problem::projectToManifold, :905-934 */
+int cora_b200_project(cora_b200_t *h, int r, const double *A, double *out);
+/* Problem::compute_Lambda_blocks, :1105-1131: lam_st is d x (d*n) column-major (the
+ * reference's d x dn block row), lam_ob has n_ranges entries */
+int cora_b200_lambda_blocks(cora_b200_t *h, int r, const double *Y, double *lam_st,
+                            double *lam_ob);
+/* S*x for S = get_certificate_matrix(Y) (:1162-1166) without forming S: x, out N x k */
+int cora_b200_certificate_product(cora_b200_t *h, int r, const double *Y, int k,
+                                  const double *x, double *out);
+
+/* ---- tier 2: solver level ----------------------------------------------------- */
+
+/* Optimization::Riemannian::TNTParams (TNT.h:76-130) with solveCORA's values as
+ * the defaults cora_b200_tnt_default_params() fills (src/CORA.cpp:95-109). */
+typedef struct cora_b200_tnt_params {
+  double Delta0;                            /* 5      */
+  double eta1;                              /* 0.05   */
+  double eta2;                              /* 0.9    */
+  double alpha1;                            /* 0.25   */
+  double alpha2;                            /* 3.0    */
+  int32_t max_TPCG_iterations;              /* 80     */
+  int32_t max_iterations;                   /* 250    */
+  double kappa_fgr;                         /* 0.1    */
+  double theta;                             /* 0.8    */
+  double preconditioned_gradient_tolerance; /* 1e-6   */
+  double gradient_tolerance;                /* 1e-6   */
+  double relative_decrease_tolerance;       /* 1e-6   */
+  double stepsize_tolerance;                /* 1e-6   */
+  double Delta_tolerance;                   /* 1e-5   */
+  double max_computation_time;              /* 20 s (src/CORA.cpp:106); <=0: no cap */
+  int32_t verbose;                          /* show_iterates */
+  int32_t reserved;
+} cora_b200_tnt_params;
+
+/* TNTResult (TNT.h:168-194 + Riemannian/Concepts.h:136-148 + Base/Concepts.h:64-88).
+ * Trace arrays are caller-allocated with `trace_capacity` entries each (NULL: not
+ * recorded); per-iteration traces receive num_outer entries, the "state" traces
+ * (objective_values, gradient_norms, preconditioned_gradient_norms,
+ * trust_region_radius, time) num_outer + 1 as in the reference. */
+typedef struct cora_b200_tnt_result {
+  double f;
+  double gradfx_norm;
+  double preconditioned_gradfx_norm;
+  double elapsed_time;   /* host wall-clock, seconds                         */
+  double device_time;    /* CUDA-event time of the whole call on the stream  */
+  int32_t status;        /* CORA_B200_TNT_*                                  */
+  int32_t num_outer;     /* trust-region iterations performed                */
+  int64_t total_inner;   /* sum of inner_iterations (CG iterations)          */
+  int64_t kernel_launches;
+  int32_t trace_capacity;
+  int32_t reserved;
+  double *objective_values;
+  double *gradient_norms;
+  double *preconditioned_gradient_norms;
+  double *trust_region_radius;
+  double *time;
+  double *update_step_norms;
+  double *update_step_M_norms;
+  double *gain_ratios;
+  int32_t *inner_iterations;
+} cora_b200_tnt_result;
+
+int cora_b200_tnt_default_params(cora_b200_tnt_params *p);
+
+/* Optimization::Riemannian::TNT (TNT.h:242-689) with the closures of
+ * src/CORA.cpp:52-122 (f, QM, metric, retract, precon), the STPCG loop
+ * (IterativeSolvers.h:166-426) device resident.  X0 must be on the manifold (the
+ * caller has applied projectToManifold, src/CORA.cpp:128). */
+int cora_b200_tnt(cora_b200_t *h, int r, const double *X0, const cora_b200_tnt_params *p,
+                  double *X_out, cora_b200_tnt_result *res);
+
+/* Device-resident variants used by bench.py's `value` leg and by the staircase:
+ * the iterate stays in HBM between calls. */
+int cora_b200_set_iterate(cora_b200_t *h, int r, const double *X);   /* H2D + layout */
+int cora_b200_get_iterate(cora_b200_t *h, int r, double *X);         /* D2H + layout */
+int cora_b200_tnt_resident(cora_b200_t *h, const cora_b200_tnt_params *p,
+                           cora_b200_tnt_result *res);
+/* timed data-matrix products on the resident iterate: reps launches of Q*X, returns
+ * the CUDA-event milliseconds for all of them (roofline leg of bench.py) */
+int cora_b200_spmm_resident(cora_b200_t *h, int reps, float *ms_total);
+
+/* Problem::certify_solution (src/CORA_problem.cpp:1030-1103) + fast_verification
+ * (src/CORA_utils.cpp:17-186).  x has N entries; all_eigvecs (may be NULL) is
+ * N x all_eigvecs_cols_capacity, *all_eigvecs_cols receives the columns written. */
+int cora_b200_certify(cora_b200_t *h, int r, const double *Y, double eta, int nx,
+                      const double *bootstrap, int bootstrap_cols, int max_iters,
+                      int *is_certified, double *theta, double *x, double *all_eigvecs,
+                      int all_eigvecs_cols_capacity, int *all_eigvecs_cols,
+                      int64_t *num_iters);
+
+/* saddleEscape (src/CORA.cpp:245-350): Y is N x (r_new-1), v has N entries, Y_out
+ * is N x r_new. */
+int cora_b200_saddle_escape(cora_b200_t *h, int r_new, const double *Y, double theta,
+                            const double *v, double gradient_tolerance,
+                            double preconditioned_gradient_tolerance, double *Y_out);
+
+/* projectSolution (src/CORA.cpp:352-441): N x r -> N x d */
+int cora_b200_project_solution(cora_b200_t *h, int r, const double *Y, double *Y_out);
+
+/* One stage record of the staircase (one TNT + one certification). */
+typedef struct cora_b200_stage {
+  int32_t rank;
+  int32_t status;
+  int32_t num_outer;
+  int32_t certified;
+  int64_t cg_iterations;
+  double f;
+  double gradfx_norm;
+  double theta;
+  double eta;
+  double tnt_seconds;
+  double cert_seconds;
+} cora_b200_stage;
+
+typedef struct cora_b200_solve_result {
+  double f;             /* final (rank-d refined) cost                         */
+  double lifted_f;      /* cost at the certified lifted rank                   */
+  int32_t final_rank;   /* = d after rounding                                  */
+  int32_t lifted_rank;
+  int32_t certified;    /* certificate at the lifted rank                      */
+  int32_t num_stages;
+  int64_t total_cg_iterations;
+  double seconds;       /* solve-to-certificate wall-clock                     */
+  int32_t stage_capacity;
+  int32_t reserved;
+  cora_b200_stage *stages; /* caller-allocated, stage_capacity entries or NULL */
+} cora_b200_solve_result;
+
+/* solveCORA (src/CORA.cpp:26-243): staircase from rank r0 up to max_rank, rounding
+ * and refinement.  X0 is N x r0; X_out is N x d. */
+int cora_b200_solve(cora_b200_t *h, int r0, const double *X0, int max_rank,
+                    const cora_b200_tnt_params *p, int verbose, double *X_out,
+                    cora_b200_solve_result *res);
+
+/* ---- multi-GPU helper: every rank passes its own result; on return
+ * winner_rank is the arg-min of f over certified ranks (over all ranks when none
+ * is certified) and X_inout (N x r_max, column-major, zero padded) holds the
+ * winner's iterate on every rank.  `nccl_comm` is an ncclComm_t. */
+int cora_b200_gather_best(void *nccl_comm, cora_b200_t *h, int world_size, int my_rank,
+                          int r_max, double f, int certified, double *X_inout,
+                          int *winner_rank, double *winner_f);
+
+/* ---- host-side assembly of the data matrix: Problem::fillDataMatrix and friends
+ * (src/CORA_problem.cpp:115-377, 625-712) from the flattened measurement stacks, in
+ * O(#factors log #factors) (the reference's add*Measurement is O(M^2)).
+ * Translation indices address [n poses | l landmarks]; rot_R is row-major d x d per
+ * factor.  Two-phase: call with rowptr == NULL to assemble and obtain *nnz, then again
+ * with buffers (rowptr N+1, col/val *nnz entries) to copy the CSR out.  CPU only. */
+int cora_b200_assemble(int d, int n_poses, int n_landmarks, int64_t E, const int64_t *rp_i,
+                       const int64_t *rp_j, const double *rp_t, const double *rp_tau, int64_t Ep,
+                       const int64_t *rot_i, const int64_t *rot_j, const double *rot_R,
+                       const double *rot_kappa, int64_t m, const int64_t *rg_a, const int64_t *rg_b,
+                       const double *rg_r, const double *rg_w, int64_t *nnz, int32_t *rowptr,
+                       int32_t *col, double *val);
+
+/* ---- test hooks (no compute): the internal device layout, rebuilt into CSR on
+ * the host so the CPU test-suite can check the permutation / block-ELL / spill
+ * split without a GPU.  Buffers are caller-allocated (nnz entries). */
+int cora_b200_layout_roundtrip(int d, int n_poses, int n_ranges, int n_trans,
+                               const int32_t *rowptr, const int32_t *col, const double *val,
+                               int64_t nnz, int32_t *out_rowptr, int32_t *out_col,
+                               double *out_val, int64_t *stats /* 8 entries */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORA_B200_H_ */
