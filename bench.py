@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- CG iterations/s of the CORA staircase inner loop on the 100k-pose SE(3) RA-SLAM
+problem (BASELINE.json configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A step = one bounded slice of the truncated-Newton solve: `--outer` trust-region iterations
+(each one STPCG solve of at most 80 CG iterations + retraction + model/gradient evaluation)
+continuing from the iterate the previous step left.  value = CG iterations of all ranks /
+device time of the K timed steps (max over ranks), iterate resident in HBM.  e2e = the same
+through cora_b200_tnt() with HOST (pinned) buffers: H2D of the iterate, the solve slice, D2H of
+the result, every step.  Every rank solves its own random restart of the same problem (weak
+scaling; no data-path collective -- the winning restart is gathered once at the end).
+
+--impl reference times the CPU restatement of the reference (oracle/) on the host cores on a
+bounded sample of the same workload; /root/reference cannot be built (no Eigen/SuiteSparse).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n=100_000, l=10, m=20_000, d=3, rank=5, seed=42)
+METRIC = "cg_iterations_per_second"
+UNIT = "CG it/s"
+
+
+def algorithmic_bytes(nnz, N, r):
+    """CSR-fp64-int32-equivalent traffic, independent of the storage format."""
+    V = 8 * N * r
+    q = 12 * nnz + 4 * (N + 1)
+    return dict(spmm=q + 2 * V, hessvec=q + 4 * V, cg_iter=q + 15 * V + 8 * N)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                               r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_problem():
+    from cora_b200 import capi, synthetic
+    w = WORKLOAD
+    arrays, _ = synthetic.make_arrays(w["n"], w["l"], w["m"], d=w["d"], seed=w["seed"])
+    Q = capi.assemble(w["d"], w["n"], w["l"], arrays)
+    m = len(arrays["rg_w"])
+    return arrays, Q, m
+
+
+def initial_guess(N, r, seed):
+    """project(U[-1,1]^{N x r}) is applied on the device; this is the raw sample (PCG64)."""
+    return np.asfortranarray(np.random.default_rng(seed).uniform(-1, 1, size=(N, r)))
+
+
+def config_dict(args, N, nnz, m):
+    w = WORKLOAD
+    return {"workload": "synthetic 100k-pose SE(3) + 20k range factors (BASELINE configs[2]), rank %d" % w["rank"],
+            "n_poses": w["n"], "n_landmarks": w["l"], "n_ranges": int(m), "N": int(N), "nnz": int(nnz),
+            "rank": w["rank"], "preconditioner": "Jacobi", "outer_iterations_per_step": args.outer,
+            "max_TPCG_iterations": 80, "restarts": "one random restart per GPU (seed = rank)",
+            "l2": "working set of one CG iteration (Q 52 MB + 10 vectors x 16.8 MB) exceeds the 126 MB L2; "
+                  "no explicit flush"}
+
+
+# ------------------------------------------------------------------ reference arm ---
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cora_oracle as co
+    arrays, Q, m = build_problem()
+    w = WORKLOAD
+    p = co.Problem.from_arrays(w["d"], w["n"], w["l"], arrays, rank=w["rank"], preconditioner=co.JACOBI)
+    p.Q = Q.tocsr()
+    p._update_preconditioner()
+    p.up_to_date = True
+    N = p.N
+    x = p.project_to_manifold(initial_guess(N, w["rank"], 0))
+    # bounded sample: one outer iteration with at most `ref_cg` CG iterations per step
+    prm = co.cora_tnt_params(max_iterations=1, max_TPCG_iterations=args.ref_cg)
+    # the CPU sample starts where CG iterations are counted: grow the trust region first
+    # (from a random point the first STPCG calls end on the boundary at iteration 0)
+    pre = co.problem_tnt(p, x, co.cora_tnt_params(max_iterations=args.ref_pre, max_TPCG_iterations=args.ref_cg))
+    x, prm.Delta0 = pre.x, pre.trust_region_radius[-1]
+    its, t_steps = 0, []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = co.problem_tnt(p, x, prm)
+        dt = time.perf_counter() - t0
+        x = res.x
+        prm.Delta0 = res.trust_region_radius[-1]
+        if s >= args.warmup:
+            its += int(sum(res.inner_iterations))
+            t_steps.append(dt)
+    T = sum(t_steps)
+    val = its / T
+    sample = "%d steps x (1 TNT outer iteration, <= %d CG iterations) of the same problem, NumPy/SciPy restatement" % (
+        args.steps, args.ref_cg)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args, N, Q.nnz, m),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------ our arm ---
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cora_b200 import build as _build, capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.barrier()
+    arrays, Q, m = build_problem()
+    w = WORKLOAD
+    d, n, l, r = w["d"], w["n"], w["l"], w["rank"]
+    N = d * n + m + n + l
+    stream = torch.cuda.current_stream().cuda_stream
+    h = capi.Handle(d, n, m, n + l, Q, preconditioner=capi.PRECON_JACOBI, device=local, stream=stream)
+    ab = algorithmic_bytes(Q.nnz, N, r)
+    prm = capi.default_tnt_params(max_iterations=args.outer, max_computation_time=0.0)
+
+    x0 = h.project_to_manifold(initial_guess(N, r, rank))
+    pin_in = torch.empty((r, N), dtype=torch.float64).pin_memory()   # column-major N x r
+    pin_out = torch.empty((r, N), dtype=torch.float64).pin_memory()
+    pin_in.numpy()[:] = x0.T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, nsteps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        its = launches = 0
+        for _ in range(nsteps):
+            a, b = step_fn()
+            its += a
+            launches += b
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) * 1e-3, its, launches
+
+    # ---- value leg: iterate resident in HBM ----
+    h.set_iterate(x0)
+
+    def step_resident():
+        res = h.tnt_resident(prm)
+        prm.Delta0 = res.trust_region_radius[-1]   # the solve continues: keep the trust region
+        return int(sum(res.inner_iterations)), res.kernel_launches
+
+    timed(step_resident, args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    h.profile_hessvec(0)
+    T, its, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+
+    # ---- dominant kernel, timed live with CUDA events around each launch in the CG loop ----
+    h.profile_hessvec(4096)
+    timed(step_resident, max(1, min(args.steps, 3)))
+    ms = h.profile_read()
+    h.profile_hessvec(0)
+    ms = ms[ms > 0.25 * np.median(ms)] if len(ms) else ms   # drop gated no-op launches
+    t_hess = float(np.mean(ms)) * 1e-3 if len(ms) else float("nan")
+
+    # ---- e2e leg: host buffers in, host buffers out, every step ----
+    lib = capi.load()
+    import ctypes as C
+    resC, keep = capi.Handle._alloc_result(prm.max_iterations + 2)
+
+    def step_e2e():
+        code = lib.cora_b200_tnt(h._h, C.c_int(r), C.cast(pin_in.data_ptr(), capi._PD), C.byref(prm),
+                                 C.cast(pin_out.data_ptr(), capi._PD), C.byref(resC))
+        capi._check(code)
+        pin_in.copy_(pin_out)   # the next slice continues from this result (host side)
+        prm.Delta0 = keep["trust_region_radius"][resC.num_outer]
+        return int(resC.total_inner), int(resC.kernel_launches)
+
+    prm.Delta0 = 5.0
+    timed(step_e2e, args.warmup)
+    Te, its_e, _ = timed(step_e2e, args.steps)
+
+    # ---- aggregate over ranks ----
+    vals = torch.tensor([T, Te, float(its), float(its_e), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        T, Te = float(mx[0]), float(mx[1])
+        its, its_e, launches = float(sm[2]), float(sm[3]), float(sm[4])
+    value = its / T
+    e2e = its_e / Te
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        ach = ab["hessvec"] / t_hess / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(args, N, Q.nnz, m),
+                "cg_iterations_timed": int(its), "us_per_cg_iteration": 1e6 * T * world / max(1.0, its),
+                "clocks": clocks,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * N * r),
+                        "d2h_bytes_per_step": int(8 * N * r)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "k_qprod<3> (fused Hessian-vector product)",
+                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["hessvec"],
+                             "avg_launch_us": 1e6 * t_hess, "launches_timed": int(len(ms)),
+                             "traffic": None,
+                             "cg_iteration": {"algorithmic_bytes": ab["cg_iter"],
+                                              "achieved": ab["cg_iter"] * its / world / T / 1e9,
+                                              "frac": ab["cg_iter"] * its / world / T / 1e9 / peak}}}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(arrays, Q, m, args)
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(arrays, Q, m, args):
+    """The oracle (a CPU restatement of the reference, `kind: port`) on a bounded sample."""
+    from oracle import cora_oracle as co
+    w = WORKLOAD
+    p = co.Problem.from_arrays(w["d"], w["n"], w["l"], arrays, rank=w["rank"], preconditioner=co.JACOBI)
+    p.Q = Q.tocsr()
+    p._update_preconditioner()
+    p.up_to_date = True
+    x = p.project_to_manifold(initial_guess(p.N, w["rank"], 0))
+    pre = co.problem_tnt(p, x, co.cora_tnt_params(max_iterations=args.ref_pre, max_TPCG_iterations=args.ref_cg))
+    prm = co.cora_tnt_params(max_iterations=2, max_TPCG_iterations=args.ref_cg, Delta0=pre.trust_region_radius[-1])
+    t0 = time.perf_counter()
+    res = co.problem_tnt(p, pre.x, prm)
+    dt = time.perf_counter() - t0
+    its = int(sum(res.inner_iterations))
+    return {"value": its / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "2 TNT outer iterations (<= %d CG iterations each) of the same problem, same x0, after 14 untimed outer iterations, "
+                      "NumPy/SciPy restatement, %d CG iterations in %.1f s" % (args.ref_cg, its, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--outer", type=int, default=6, help="TNT outer iterations per step")
+    ap.add_argument("--ref-cg", type=int, default=20, help="CG cap per outer iteration of the CPU sample")
+    ap.add_argument("--ref-pre", type=int, default=14, help="untimed outer iterations before the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -119,7 +119,8 @@ SYMBOLS = [
     "cora_b200_tnt_default_params", "cora_b200_tnt", "cora_b200_set_iterate", "cora_b200_get_iterate",
     "cora_b200_tnt_resident", "cora_b200_spmm_resident", "cora_b200_certify", "cora_b200_saddle_escape",
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
-    "cora_b200_assemble",
+    "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
+    "cora_b200_profile_read", "cora_b200_debug_chain_host",
 ]
 
 
@@ -203,6 +204,29 @@ def layout_roundtrip(d, n, m, nt, Q):
     names = ["num_tiles", "max_slots", "nnz_block", "nnz_spill", "nnz_hub", "num_hub_groups",
              "block_values_stored", "nnz_out"]
     return out, dict(zip(names, (int(x) for x in stats)))
+
+
+def debug_chain_host(d, n, m, nt, Q, shift, pin_last=True, V=None):
+    """Test hook: host execution of the chain Cholesky.  Returns (pos_def, M^-1 V or None)."""
+    import scipy.sparse as sp
+    Q = sp.csr_matrix(Q)
+    rp = np.ascontiguousarray(Q.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(Q.indices, dtype=np.int32)
+    va = np.ascontiguousarray(Q.data, dtype=np.float64)
+    i32 = C.POINTER(C.c_int32)
+    pd = C.c_int(0)
+    out = None
+    r = 0
+    if V is not None:
+        V = _f64(V)
+        r = V.shape[1]
+        out = np.zeros_like(V, order="F")
+    _check(load().cora_b200_debug_chain_host(C.c_int(d), C.c_int(n), C.c_int(m), C.c_int(nt),
+                                             rp.ctypes.data_as(i32), ci.ctypes.data_as(i32), _p(va),
+                                             C.c_int64(Q.nnz), C.c_double(shift), C.c_int(int(pin_last)),
+                                             C.c_int(r), _p(V) if V is not None else None,
+                                             _p(out) if out is not None else None, C.byref(pd)))
+    return bool(pd.value), out
 
 
 def assemble(d, n, l, arrays):
@@ -424,6 +448,22 @@ class Handle:
         res, keep = self._alloc_result(params.max_iterations + 2)
         _check(self._lib.cora_b200_tnt_resident(self._h, C.byref(params), C.byref(res)))
         return self._unpack_result(res, keep)
+
+    def snapshot_iterate(self):
+        _check(self._lib.cora_b200_snapshot_iterate(self._h))
+
+    def restore_iterate(self):
+        _check(self._lib.cora_b200_restore_iterate(self._h))
+
+    def profile_hessvec(self, max_samples):
+        _check(self._lib.cora_b200_profile_hessvec(self._h, C.c_int(max_samples)))
+
+    def profile_read(self, capacity=65536):
+        ms = np.zeros(capacity, dtype=np.float32)
+        n = C.c_int(0)
+        _check(self._lib.cora_b200_profile_read(self._h, C.c_int(capacity),
+                                                ms.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n)))
+        return ms[: n.value].astype(np.float64)
 
     def spmm_resident(self, reps):
         ms = C.c_float()

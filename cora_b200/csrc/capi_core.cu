@@ -5,6 +5,7 @@
 #include "chain_chol.cuh"
 #include "ops.cuh"
 #include "solver.cuh"
+#include "lanczos.cuh"
 
 namespace cora_b200 {
 static thread_local std::string g_last_error;
@@ -170,6 +171,7 @@ extern "C" int cora_b200_destroy(cora_b200_t *h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 2; ++i)
     if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return CORA_B200_OK;
@@ -412,6 +414,34 @@ extern "C" int cora_b200_assemble(int d, int n_poses, int n_landmarks, int64_t E
     std::vector<int32_t>().swap(g_asm_rowptr);
     std::vector<int32_t>().swap(g_asm_col);
     std::vector<double>().swap(g_asm_val);
+  }
+  API_END
+}
+
+// Test hook (CPU only): the chain factorisation + solve executed on the host through the SAME
+// per-chunk functions the device kernels call, so the CPU suite can pin the algorithm against the
+// oracle's sparse LU without a GPU.  V, out: N x r column-major in the reference row order.
+extern "C" int cora_b200_debug_chain_host(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
+                                          const int32_t *col, const double *val, int64_t nnz, double shift,
+                                          int pin_last, int r, const double *V, double *out, int *pos_def) {
+  API_BEGIN
+  require(rowptr && pos_def, "NULL argument");
+  HostLayout L;
+  build_layout(L, d, n_poses, n_ranges, n_trans, rowptr, col, val, nnz, 192);
+  ChainFactorHost F;
+  const bool solve = (V != nullptr && out != nullptr && r > 0);
+  if (L.D1 == 3) chain_factor_host<3>(F, L, L.bval.data(), L.sdiag.data(), shift, pin_last != 0, solve);
+  else chain_factor_host<4>(F, L, L.bval.data(), L.sdiag.data(), shift, pin_last != 0, solve);
+  *pos_def = F.pos_def ? 1 : 0;
+  if (solve && F.pos_def) {
+    const size_t N = (size_t)L.N;
+    std::vector<double> Vi(N * r), Zi(N * r);
+    for (size_t i = 0; i < N; ++i)
+      for (int c = 0; c < r; ++c) Vi[i * r + c] = V[(size_t)c * N + L.int2ref[i]];
+    if (L.D1 == 3) chain_apply_host<3>(F, L, Vi.data(), Zi.data(), r);
+    else chain_apply_host<4>(F, L, Vi.data(), Zi.data(), r);
+    for (size_t i = 0; i < N; ++i)
+      for (int c = 0; c < r; ++c) out[(size_t)c * N + L.int2ref[i]] = Zi[i * r + c];
   }
   API_END
 }

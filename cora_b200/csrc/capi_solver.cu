@@ -105,6 +105,58 @@ extern "C" int cora_b200_spmm_resident(cora_b200_t *h, int reps, float *ms_total
   API_END
 }
 
+extern "C" int cora_b200_snapshot_iterate(cora_b200_t *h) {
+  API_BEGIN
+  require(h != nullptr, "NULL handle");
+  require(h->resident_r > 0, "no resident iterate");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->DL.N * h->resident_r;
+  if (h->d_snap.n < n) h->d_snap.alloc(n);
+  CUDA_CHECK(cudaMemcpyAsync(h->d_snap.p, h->ws[V_X].p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->snap_r = h->resident_r;
+  API_END
+}
+
+extern "C" int cora_b200_restore_iterate(cora_b200_t *h) {
+  API_BEGIN
+  require(h != nullptr, "NULL handle");
+  require(h->snap_r > 0, "no snapshot");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  ensure_workspace(h, h->snap_r);
+  const size_t n = (size_t)h->DL.N * h->snap_r;
+  CUDA_CHECK(cudaMemcpyAsync(h->ws[V_X].p, h->d_snap.p, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->resident_r = h->snap_r;
+  API_END
+}
+
+extern "C" int cora_b200_profile_hessvec(cora_b200_t *h, int max_samples) {
+  API_BEGIN
+  require(h != nullptr, "NULL handle");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->prof_n = 0;
+  h->prof_on = max_samples > 0;
+  while ((int)h->prof_ev.size() < 2 * max_samples) {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    h->prof_ev.push_back(e);
+  }
+  API_END
+}
+
+extern "C" int cora_b200_profile_read(cora_b200_t *h, int capacity, float *ms, int *count) {
+  API_BEGIN
+  require(h && ms && count, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  int n = 0;
+  for (size_t i = 0; i + 1 < h->prof_n && n < capacity; i += 2, ++n)
+    CUDA_CHECK(cudaEventElapsedTime(&ms[n], h->prof_ev[i], h->prof_ev[i + 1]));
+  *count = n;
+  h->prof_n = 0;
+  API_END
+}
+
 extern "C" int cora_b200_certify(cora_b200_t *h, int r, const double *Y, double eta, int nx,
                                  const double *bootstrap, int bootstrap_cols, int max_iters, int *is_certified,
                                  double *theta, double *x, double *all_eigvecs, int all_eigvecs_cols_capacity,

@@ -45,6 +45,7 @@ enum Vec {
   V_GP,      // Q X+
   V_GRADP,   // grad at X+
   V_Z,       // external preconditioner output / scratch
+  V_V,       // STPCG preconditioned residual v (V_PG must survive a rejected step)
   V_T0,      // scratch (tier-1 staging)
   V_T1,
   V_COUNT
@@ -90,4 +91,10 @@ struct cora_b200_handle {
   int resident_r = 0;
   int64_t launches = 0;
   int cg_chunk = 8;
+  // optional per-launch timing of the dominant kernel (k_qprod<HESS> inside STPCG)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_n = 0;
+  cora_b200::DevBuf<double> d_snap;  // snapshot of the resident iterate
+  int snap_r = 0;
 };

@@ -292,6 +292,68 @@ __device__ __forceinline__ void jacobi_eig(double (&A)[D][D], double (&V)[D][D])
   }
 }
 
+// Accurate path for ill-conditioned blocks: one-sided (Hestenes) Jacobi on the d rows of w.
+// Rotations from the left make the rows mutually orthogonal, U^T w = Sigma V^T; the polar factor
+// is U V^T = U * (rows of U^T w normalised).  Relative accuracy eps*cond(w) instead of the
+// eps*cond(w)^2 of the Gram-matrix route.
+template <int D>
+__device__ __noinline__ void stiefel_polar_hestenes(double *w, int r, int RS) {
+  double U[D][D];
+#pragma unroll
+  for (int a = 0; a < D; ++a)
+#pragma unroll
+    for (int b = 0; b < D; ++b) U[a][b] = (a == b) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    bool rotated = false;
+#pragma unroll
+    for (int p = 0; p < D; ++p)
+#pragma unroll
+      for (int q = p + 1; q < D; ++q) {
+        double app = 0.0, aqq = 0.0, apq = 0.0;
+        for (int c = 0; c < r; ++c) {
+          const double x = w[p * RS + c], y = w[q * RS + c];
+          app = fma(x, x, app); aqq = fma(y, y, aqq); apq = fma(x, y, apq);
+        }
+        if (fabs(apq) <= 1e-16 * sqrt(app * aqq) || apq == 0.0) continue;
+        rotated = true;
+        const double th = (aqq - app) / (2.0 * apq);
+        const double tt = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+        const double cs = 1.0 / sqrt(tt * tt + 1.0), sn = tt * cs;
+        for (int c = 0; c < r; ++c) {
+          const double x = w[p * RS + c], y = w[q * RS + c];
+          w[p * RS + c] = cs * x - sn * y;
+          w[q * RS + c] = sn * x + cs * y;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {  // U <- U J  (so that w_orig = U * w)
+          const double ukp = U[k][p], ukq = U[k][q];
+          U[k][p] = cs * ukp - sn * ukq;
+          U[k][q] = sn * ukp + cs * ukq;
+        }
+      }
+    if (!rotated) break;
+  }
+  double inv[D];
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    double s = 0.0;
+    for (int c = 0; c < r; ++c) s = fma(w[a * RS + c], w[a * RS + c], s);
+    inv[a] = 1.0 / sqrt(fmax(s, 1e-300));
+  }
+  for (int c = 0; c < r; ++c) {
+    double v[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) v[a] = w[a * RS + c] * inv[a];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) s = fma(U[a][k], v[k], s);
+      w[a * RS + c] = s;
+    }
+  }
+}
+
 // Polar factor of the d x r block w (rows RS apart), in place:
 // w <- (w w^T)^{-1/2} w, the row form of StiefelProduct.cpp:26-34 (thin SVD -> U V^T).
 template <int D>
@@ -315,6 +377,15 @@ __device__ __forceinline__ void stiefel_polar(double *w, int r, int RS) {
 #pragma unroll
     for (int b = 0; b < D; ++b) A[a][b] = Gm[a][b];
   jacobi_eig<D>(A, V);
+  {
+    double lmin = A[0][0], lmax = A[0][0];
+#pragma unroll
+    for (int a = 1; a < D; ++a) { lmin = fmin(lmin, A[a][a]); lmax = fmax(lmax, A[a][a]); }
+    if (lmin < 1e-6 * lmax) {  // ill-conditioned block (random initial guesses only)
+      stiefel_polar_hestenes<D>(w, r, RS);
+      return;
+    }
+  }
   double is[D];
 #pragma unroll
   for (int a = 0; a < D; ++a) is[a] = 1.0 / sqrt(fmax(A[a][a], 1e-300));
@@ -363,6 +434,38 @@ __device__ __forceinline__ void stiefel_polar(double *w, int r, int RS) {
 #pragma unroll
       for (int b = 0; b < D; ++b) M[a][b] = 0.5 * (Mn[a][b] + Mn[b][a]);
   }
+  for (int c = 0; c < r; ++c) {
+    double wc[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) wc[a] = w[a * RS + c];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < D; ++b) s = fma(M[a][b], wc[b], s);
+      w[a * RS + c] = s;
+    }
+  }
+  // final Newton-Schulz step on the block itself, w <- (1.5 I - 0.5 w w^T) w: the Gram-matrix
+  // route above is accurate to eps*cond(G); this restores orthonormality to rounding level
+  // for ill-conditioned blocks (random initial guesses)
+#pragma unroll
+  for (int a = 0; a < D; ++a)
+#pragma unroll
+    for (int b = 0; b < D; ++b) Gm[a][b] = 0.0;
+  for (int c = 0; c < r; ++c) {
+    double wc[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) wc[a] = w[a * RS + c];
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int b = 0; b < D; ++b) Gm[a][b] = fma(wc[a], wc[b], Gm[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < D; ++a)
+#pragma unroll
+    for (int b = 0; b < D; ++b) M[a][b] = ((a == b) ? 1.5 : 0.0) - 0.25 * (Gm[a][b] + Gm[b][a]);
   for (int c = 0; c < r; ++c) {
     double wc[D];
 #pragma unroll

@@ -95,8 +95,11 @@ inline void launch_qprod(H *h, int mode, const double *X, const double *Y, const
   A.longbuf = h->d_longbuf.p;
   A.partials = h->d_partials.p; A.counter = h->d_counter.p; A.scal = h->d_scal.p;
   A.ctrl = ctrl; A.r = r; A.mode = mode; A.post = post; A.slot = slot;
+  const bool prof = h->prof_on && mode == QM_HESS && ctrl != nullptr && h->prof_n + 2 <= h->prof_ev.size();
+  if (prof) CUDA_CHECK(cudaEventRecord(h->prof_ev[h->prof_n++], h->stream));
   DISPATCH_D(h, k_qprod<DD><<<L.numTiles, kThreads, smem_q<DD>(h, r, mode), h->stream>>>(L, A));
   check_launch(h);
+  if (prof) CUDA_CHECK(cudaEventRecord(h->prof_ev[h->prof_n++], h->stream));
 }
 
 inline void launch_update(H *h, const UArgs &A0) {

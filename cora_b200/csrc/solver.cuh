@@ -100,7 +100,7 @@ inline void enqueue_cg_iteration(H *h, int r) {
   CgCtrl *ctrl = h->d_ctrl.p;
   launch_qprod(h, QM_HESS, P, X, G, HP, nullptr, r, POST_CG_HESS, 0, ctrl);
   UArgs A{};
-  A.Y = X; A.P = P; A.HP = HP; A.S = h->ws[V_S].p; A.R = h->ws[V_R].p; A.V = h->ws[V_PG].p;
+  A.Y = X; A.P = P; A.HP = HP; A.S = h->ws[V_S].p; A.R = h->ws[V_R].p; A.V = h->ws[V_V].p;
   A.ctrl = ctrl; A.r = r; A.gated = 1; A.post = POST_CG_UPDATE;
   if (h->precond == CORA_B200_PRECON_JACOBI) {
     A.do_axpy = 1; A.zsrc = 0; A.do_proj = 1;
@@ -113,7 +113,7 @@ inline void enqueue_cg_iteration(H *h, int r) {
     launch_update(h, A);
   }
   const long long nE = (long long)h->DL.N * r;
-  k_cg_pupdate<<<flat_grid(h, nE), kThreads, 0, h->stream>>>(ctrl, h->ws[V_PG].p, P, nE);
+  k_cg_pupdate<<<flat_grid(h, nE), kThreads, 0, h->stream>>>(ctrl, h->ws[V_V].p, P, nE);
   check_launch(h);
 }
 

@@ -177,6 +177,14 @@ int cora_b200_set_iterate(cora_b200_t *h, int r, const double *X);   /* H2D + la
 int cora_b200_get_iterate(cora_b200_t *h, int r, double *X);         /* D2H + layout */
 int cora_b200_tnt_resident(cora_b200_t *h, const cora_b200_tnt_params *p,
                            cora_b200_tnt_result *res);
+/* keep / restore a device copy of the resident iterate (bench.py restarts a solve without
+ * touching the host) */
+int cora_b200_snapshot_iterate(cora_b200_t *h);
+int cora_b200_restore_iterate(cora_b200_t *h);
+/* per-launch CUDA-event timing of the dominant kernel (the fused Hessian-vector product
+ * inside STPCG): enable with max_samples > 0, read back the milliseconds of each launch */
+int cora_b200_profile_hessvec(cora_b200_t *h, int max_samples);
+int cora_b200_profile_read(cora_b200_t *h, int capacity, float *ms, int *count);
 /* timed data-matrix products on the resident iterate: reps launches of Q*X, returns
  * the CUDA-event milliseconds for all of them (roofline leg of bench.py) */
 int cora_b200_spmm_resident(cora_b200_t *h, int reps, float *ms_total);
@@ -262,6 +270,13 @@ int cora_b200_layout_roundtrip(int d, int n_poses, int n_ranges, int n_trans,
                                const int32_t *rowptr, const int32_t *col, const double *val,
                                int64_t nnz, int32_t *out_rowptr, int32_t *out_col,
                                double *out_val, int64_t *stats /* 8 entries */);
+
+/* Test hook (CPU only, no GPU): chain factorisation of (Q + shift I) [last row pinned when
+ * pin_last] and M^-1 V executed on the host through the same per-chunk routines the device
+ * kernels call.  V/out may be NULL (factor only); *pos_def receives the PD verdict. */
+int cora_b200_debug_chain_host(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
+                               const int32_t *col, const double *val, int64_t nnz, double shift,
+                               int pin_last, int r, const double *V, double *out, int *pos_def);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,139 @@
+"""Certification, saddle escape, rounding and the staircase through the C-ABI.
+
+The reference's decision procedure (Cholesky PSD test of S + eta I, eigen-search only on failure,
+early exit x'Sx < -eta/2) is mirrored; the eigen-search itself is PARITY UNPINNED in the reference
+(SYM-ILDL-preconditioned LOBPCG, third-party), so the tests compare decisions, the validity of the
+returned direction, and lambda_min against dense eigenvalues."""
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, load_dataset, load_fixture, make_handle
+from oracle import cora_oracle as co
+from synth import make_synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(**kw):
+    from cora_b200 import capi
+    base = dict(max_computation_time=0.0)
+    base.update(kw)
+    return capi.default_tnt_params(**base)
+
+
+def test_ground_truth_is_certified(lib):  # tests/test_certification.cpp:81-101
+    g, p = load_fixture("small_ra_slam_problem")
+    p.preconditioner = co.JACOBI
+    p.update_problem_data()
+    with make_handle(p) as h:
+        res = h.certify_solution(g["X_gt"], 1e-6, 10)
+        assert res.is_certified and res.theta == 0.0 and not res.x.any()
+
+
+@pytest.mark.parametrize("name", ["small_ra_slam_problem"])
+def test_random_point_not_certified(lib, name):  # tests/test_certification.cpp:103-125
+    g, p = load_fixture(name)
+    p.preconditioner = co.JACOBI
+    p.update_problem_data()
+    X = g["X_rand_dim2"]
+    S = g["S_rand"]
+    lam_min = float(np.linalg.eigvalsh(S)[0])   # -51.836068938594046
+    with make_handle(p) as h:
+        res = h.certify_solution(X, 1e-6, 10)
+    assert not res.is_certified
+    x = res.x
+    assert abs(np.linalg.norm(x) - 1.0) < 1e-10
+    assert abs(float(x @ (S @ x)) - res.theta) < 1e-8 * abs(lam_min)   # theta = x'Sx
+    assert res.theta < -1e-6 / 2
+    assert lam_min - 1e-9 <= res.theta <= 0.9 * lam_min               # close to the minimum eigenvalue
+
+
+def test_certify_synthetic_decisions(lib):
+    """Noise-free chain: the ground truth is the global optimum -> certified; a rank-deficient
+    critical point reached at rank d from a bad start is typically not."""
+    p = make_synthetic(n=600, l=4, m=250, d=3, seed=21)
+    p.update_problem_data()
+    from cora_b200 import synthetic
+    with make_handle(p) as h:
+        # a TNT solution from random start at rank d, then compare the decision with the dense answer
+        p.rank = 3
+        x0 = p.random_initial_guess(np.random.default_rng(1))
+        sol = h.tnt(x0, _params(max_iterations=60))
+        eta = min(max(sol.f * 5e-6, 1e-7), 1e-1)
+        res = h.certify_solution(sol.x, eta, 10)
+        S = p.certificate_matrix(sol.x).toarray()
+        w = np.linalg.eigvalsh(S)
+        assert res.is_certified == bool(w[0] + eta > 0)
+        if not res.is_certified:
+            x = res.x
+            th = float(x @ (S @ x))
+            assert abs(th - res.theta) <= 1e-7 * max(1.0, abs(w[0]))
+            assert res.theta < -eta / 2 and res.theta >= w[0] - 1e-8 * abs(w[0])
+
+
+def test_saddle_escape_matches_oracle(lib):
+    g, p = load_fixture("small_ra_slam_problem")
+    p.preconditioner = co.JACOBI
+    p.update_problem_data()
+    p.rank = 2
+    x0 = p.random_initial_guess(np.random.default_rng(0))
+    res = co.problem_tnt(p, x0, co.cora_tnt_params())
+    S = p.certificate_matrix(res.x).toarray()
+    w, V = np.linalg.eigh(S)
+    assert w[0] < -1e-3
+    theta, v = float(w[0]), V[:, 0]
+    p.increment_rank()
+    ref = co.saddle_escape(p, res.x, theta, v, 1e-4, 1e-4)
+    with make_handle(p) as h:
+        got = h.saddle_escape(res.x, theta, v, 1e-4, 1e-4)
+    np.testing.assert_allclose(got, ref, atol=1e-9)
+    assert p.evaluate_objective(got) < res.f
+
+
+def test_project_solution_matches_oracle(lib):
+    p = load_dataset("single_drone", preconditioner=co.JACOBI)
+    p.update_problem_data()
+    p.rank = 5
+    Y = p.random_initial_guess(np.random.default_rng(3))
+    ref = co.project_solution(p, Y)
+    with make_handle(p) as h:
+        got = h.project_solution(Y)
+    d, n, m = p.d, p.n, p.m
+    # the truncated SVD fixes Yd only up to signs of singular vectors: compare O(d)-invariants
+    np.testing.assert_allclose(got @ got.T @ np.ones(p.N), ref @ ref.T @ np.ones(p.N), rtol=1e-8, atol=1e-8)
+    B = got[: d * n].reshape(n, d, d)
+    assert np.abs(np.einsum("nij,nkj->nik", B, B) - np.eye(d)).max() < 1e-12
+    assert np.abs(np.linalg.det(B) - 1.0).max() < 1e-10
+    assert np.abs(np.linalg.norm(got[d * n: d * n + m], axis=1) - 1).max() < 1e-13
+    assert abs(p.evaluate_objective(got) - p.evaluate_objective(ref)) <= 1e-8 * abs(p.evaluate_objective(ref))
+
+
+def test_staircase_small_problem(lib):  # f* = 0 certified at rank 3
+    g, p = load_fixture("small_ra_slam_problem")
+    p.preconditioner = co.JACOBI
+    p.update_problem_data()
+    p.rank = 2
+    x0 = np.random.default_rng(0).uniform(-1, 1, size=(p.N, 2))
+    with make_handle(p) as h:
+        out = h.solve(x0, max_rank=6, params=_params())
+    assert out["certified"]
+    assert abs(out["lifted_f"]) < 1e-8 and abs(out["f"]) < 1e-8
+    assert out["final_rank"] == 2 and out["x"].shape == (p.N, 2)
+    assert out["total_cg_iterations"] > 0
+
+
+@pytest.mark.parametrize("name,r0,f_lift,f_ref", [("plaza2", 3, 724.0, 734.328), ("single_drone", 5, 7.2333, 7.6976)])
+def test_staircase_datasets_known_answers(lib, name, r0, f_lift, f_ref):
+    """End-to-end known answers (Plaza2's 734.328 is the one cost figure the
+    reference records, run_utils/parse_data.py:40).  With the reference's stopping rules the lifted
+    cost is reproducible to ~1e-4 relative between correct implementations."""
+    from cora_b200 import capi
+    p = load_dataset(name, preconditioner=co.REG_CHOLESKY)
+    p.update_problem_data()
+    x0 = np.random.default_rng(0).uniform(-1, 1, size=(p.N, r0))
+    with make_handle(p, preconditioner=capi.PRECON_REG_CHOLESKY) as h:
+        out = h.solve(x0, max_rank=10, params=_params())
+    assert out["certified"], out["stages"]
+    assert abs(out["lifted_f"] - f_lift) <= 2e-3 * f_lift, out["stages"]
+    assert abs(out["f"] - f_ref) <= 1e-4 * f_ref, out["stages"]
+    assert out["final_rank"] == p.d
