@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(kThreads) k_round_solution(const DevLayout L, 
         for (int k = 0; k < D; ++k) s = fma(V[a][k] * sc[k], V[b][k], s);
         T[a][b] = s;
       }
+    double R[D][D];
 #pragma unroll
     for (int a = 0; a < D; ++a)
 #pragma unroll
@@ -190,6 +191,25 @@ __global__ void __launch_bounds__(kThreads) k_round_solution(const DevLayout L, 
         double s = 0.0;
 #pragma unroll
         for (int k = 0; k < D; ++k) s = fma(T[a][k], M[k][b], s);
+        R[a][b] = s;
+      }
+    // one Newton-Schulz step restores orthonormality to rounding level for ill-conditioned blocks
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int b = 0; b < D; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s = fma(R[a][k], R[b][k], s);
+        G[a][b] = ((a == b) ? 1.5 : 0.0) - 0.5 * s;
+      }
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int b = 0; b < D; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s = fma(G[a][k], R[k][b], s);
         m[a * D + b] = s;
       }
     if (reflect) m[D * D + D - 1] = -m[D * D + D - 1];  // translation row of the pose

@@ -102,7 +102,7 @@ def test_project_solution_matches_oracle(lib):
     # the truncated SVD fixes Yd only up to signs of singular vectors: compare O(d)-invariants
     np.testing.assert_allclose(got @ got.T @ np.ones(p.N), ref @ ref.T @ np.ones(p.N), rtol=1e-8, atol=1e-8)
     B = got[: d * n].reshape(n, d, d)
-    assert np.abs(np.einsum("nij,nkj->nik", B, B) - np.eye(d)).max() < 1e-12
+    assert np.abs(np.einsum("nij,nkj->nik", B, B) - np.eye(d)).max() < 1e-13
     assert np.abs(np.linalg.det(B) - 1.0).max() < 1e-10
     assert np.abs(np.linalg.norm(got[d * n: d * n + m], axis=1) - 1).max() < 1e-13
     assert abs(p.evaluate_objective(got) - p.evaluate_objective(ref)) <= 1e-8 * abs(p.evaluate_objective(ref))
