@@ -95,17 +95,20 @@ def build_problem():
     return arrays, Q, m
 
 
-def initial_guess(N, r, seed):
-    """project(U[-1,1]^{N x r}) is applied on the device; this is the raw sample (PCG64)."""
-    return np.asfortranarray(np.random.default_rng(seed).uniform(-1, 1, size=(N, r)))
+def initial_guess(arrays, seed):
+    """Odometry initialisation (examples/paper_experiments.cpp:426-534): chained odometry, random
+    landmarks, a random SO(r) right factor -- `seed` selects the restart."""
+    from cora_b200 import synthetic
+    w = WORKLOAD
+    return synthetic.odometry_initialization(w["d"], w["n"], w["l"], arrays, w["rank"], seed=seed)
 
 
 def config_dict(args, N, nnz, m):
     w = WORKLOAD
     return {"workload": "synthetic 100k-pose SE(3) + 20k range factors (BASELINE configs[2]), rank %d" % w["rank"],
             "n_poses": w["n"], "n_landmarks": w["l"], "n_ranges": int(m), "N": int(N), "nnz": int(nnz),
-            "rank": w["rank"], "preconditioner": "Jacobi", "outer_iterations_per_step": args.outer,
-            "max_TPCG_iterations": 80, "restarts": "one random restart per GPU (seed = rank)",
+            "rank": w["rank"], "preconditioner": "Jacobi", "outer_iterations_per_step": args.outer, "untimed_startup_outer_iterations": args.pre_outer,
+            "max_TPCG_iterations": 80, "init": "odometry chain + random landmarks + random SO(r) factor (paper_experiments.cpp:426-534)", "restarts": "one restart per GPU (seed = rank)",
             "l2": "working set of one CG iteration (Q 52 MB + 10 vectors x 16.8 MB) exceeds the 126 MB L2; "
                   "no explicit flush"}
 
@@ -123,7 +126,7 @@ def run_reference(args):
     p._update_preconditioner()
     p.up_to_date = True
     N = p.N
-    x = p.project_to_manifold(initial_guess(N, w["rank"], 0))
+    x = p.project_to_manifold(initial_guess(arrays, 0))
     # bounded sample: one outer iteration with at most `ref_cg` CG iterations per step
     prm = co.cora_tnt_params(max_iterations=1, max_TPCG_iterations=args.ref_cg)
     # the CPU sample starts where CG iterations are counted: grow the trust region first
@@ -178,7 +181,7 @@ def run_ours(args):
     ab = algorithmic_bytes(Q.nnz, N, r)
     prm = capi.default_tnt_params(max_iterations=args.outer, max_computation_time=0.0)
 
-    x0 = h.project_to_manifold(initial_guess(N, r, rank))
+    x0 = h.project_to_manifold(initial_guess(arrays, rank))
     pin_in = torch.empty((r, N), dtype=torch.float64).pin_memory()   # column-major N x r
     pin_out = torch.empty((r, N), dtype=torch.float64).pin_memory()
     pin_in.numpy()[:] = x0.T
@@ -201,12 +204,24 @@ def run_ours(args):
         barrier()
         return e0.elapsed_time(e1) * 1e-3, its, launches
 
-    # ---- value leg: iterate resident in HBM ----
+    # ---- untimed: leave the start-up phase (STPCG ends on the trust-region boundary after 0-3
+    # iterations until the radius has grown) so that the timed steps are CG iterations ----
     h.set_iterate(x0)
+    pre = h.tnt_resident(capi.default_tnt_params(max_iterations=args.pre_outer, max_computation_time=0.0))
+    delta_warm = pre.trust_region_radius[-1]
+    h.snapshot_iterate()
+    pin_warm = torch.empty((r, N), dtype=torch.float64).pin_memory()
+    h.get_iterate_ptr(r, pin_warm.data_ptr())
+
+    # ---- value leg: iterate resident in HBM ----
+    prm.Delta0 = delta_warm
 
     def step_resident():
         res = h.tnt_resident(prm)
         prm.Delta0 = res.trust_region_radius[-1]   # the solve continues: keep the trust region
+        if res.status != "IterationLimit":        # converged inside the bench: start the slice again
+            h.restore_iterate()
+            prm.Delta0 = delta_warm
         return int(sum(res.inner_iterations)), res.kernel_launches
 
     timed(step_resident, args.warmup)
@@ -218,7 +233,7 @@ def run_ours(args):
 
     # ---- dominant kernel, timed live with CUDA events around each launch in the CG loop ----
     h.profile_hessvec(4096)
-    timed(step_resident, max(1, min(args.steps, 3)))
+    timed(step_resident, max(1, min(args.steps, 2)))
     ms = h.profile_read()
     h.profile_hessvec(0)
     ms = ms[ms > 0.25 * np.median(ms)] if len(ms) else ms   # drop gated no-op launches
@@ -228,16 +243,21 @@ def run_ours(args):
     lib = capi.load()
     import ctypes as C
     resC, keep = capi.Handle._alloc_result(prm.max_iterations + 2)
+    pin_in.copy_(pin_warm)
 
     def step_e2e():
         code = lib.cora_b200_tnt(h._h, C.c_int(r), C.cast(pin_in.data_ptr(), capi._PD), C.byref(prm),
                                  C.cast(pin_out.data_ptr(), capi._PD), C.byref(resC))
         capi._check(code)
-        pin_in.copy_(pin_out)   # the next slice continues from this result (host side)
-        prm.Delta0 = keep["trust_region_radius"][resC.num_outer]
+        if resC.status == capi.TNT_STATUS.index("IterationLimit"):
+            pin_in.copy_(pin_out)   # the next slice continues from this result (host side)
+            prm.Delta0 = keep["trust_region_radius"][resC.num_outer]
+        else:
+            pin_in.copy_(pin_warm)
+            prm.Delta0 = delta_warm
         return int(resC.total_inner), int(resC.kernel_launches)
 
-    prm.Delta0 = 5.0
+    prm.Delta0 = delta_warm
     timed(step_e2e, args.warmup)
     Te, its_e, _ = timed(step_e2e, args.steps)
 
@@ -292,7 +312,7 @@ def cpu_baseline(arrays, Q, m, args):
     p.Q = Q.tocsr()
     p._update_preconditioner()
     p.up_to_date = True
-    x = p.project_to_manifold(initial_guess(p.N, w["rank"], 0))
+    x = p.project_to_manifold(initial_guess(arrays, 0))
     pre = co.problem_tnt(p, x, co.cora_tnt_params(max_iterations=args.ref_pre, max_TPCG_iterations=args.ref_cg))
     prm = co.cora_tnt_params(max_iterations=2, max_TPCG_iterations=args.ref_cg, Delta0=pre.trust_region_radius[-1])
     t0 = time.perf_counter()
@@ -310,7 +330,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--outer", type=int, default=6, help="TNT outer iterations per step")
+    ap.add_argument("--outer", type=int, default=5, help="TNT outer iterations per step")
+    ap.add_argument("--pre-outer", type=int, default=40,
+                    help="untimed TNT outer iterations before the first step (trust-region start-up)")
     ap.add_argument("--ref-cg", type=int, default=20, help="CG cap per outer iteration of the CPU sample")
     ap.add_argument("--ref-pre", type=int, default=14, help="untimed outer iterations before the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

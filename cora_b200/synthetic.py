@@ -100,3 +100,37 @@ def ground_truth_matrix(d, n, l, arrays, gt):
         X[d * n: d * n + m] = diff / np.linalg.norm(diff, axis=1)[:, None]
     X[d * n + m:] = T
     return X
+
+
+def odometry_initialization(d, n, l, arrays, rank, seed=0):
+    """x0 (N x rank, reference row order) by composing the odometry chain, as the reference's paper
+    experiments initialise (examples/paper_experiments.cpp:426-534): pose i gets R_i^T / t_i of the
+    chained odometry, landmarks 10*U[-1,1]^d, range rows the normalised translation differences
+    (second minus first id), everything embedded in rank columns and rotated by a random SO(rank)
+    element so that it is generically dense.  Single chain A0 -> A1 -> ...."""
+    rng = np.random.default_rng(seed)
+    m = len(arrays["rg_w"])
+    N = d * n + m + n + l
+    ii, jj = np.asarray(arrays["rot_i"]), np.asarray(arrays["rot_j"])
+    Rm, tm = np.asarray(arrays["rot_R"]), np.asarray(arrays["rp_t"])
+    R = np.empty((n, d, d)); t = np.empty((n, d))
+    R[0] = np.eye(d); t[0] = 0.0
+    nxt = {int(a): k for k, (a, b) in enumerate(zip(ii, jj)) if b == a + 1}
+    for i in range(n - 1):
+        k = nxt[i]
+        t[i + 1] = t[i] + R[i] @ tm[k]
+        R[i + 1] = R[i] @ Rm[k]
+    X = np.zeros((N, rank))
+    X[: d * n, :d] = np.transpose(R, (0, 2, 1)).reshape(d * n, d)
+    T = np.concatenate([t, 10.0 * rng.uniform(-1, 1, size=(l, d))]) if l else t
+    X[d * n + m:, :d] = T
+    if m:
+        diff = T[arrays["rg_b"]] - T[arrays["rg_a"]]
+        nrm = np.linalg.norm(diff, axis=1)
+        bad = nrm < 1e-5
+        diff[bad] = rng.uniform(-1, 1, size=(int(bad.sum()), d))
+        X[d * n: d * n + m, :d] = diff / np.linalg.norm(diff, axis=1)[:, None]
+    Qr, _ = np.linalg.qr(rng.uniform(-1, 1, size=(rank, rank)))
+    if np.linalg.det(Qr) < 0:
+        Qr[:, -1] *= -1
+    return np.asfortranarray(X @ Qr)
