@@ -67,6 +67,11 @@ static void fill_dev_layout(H *h) {
   D.tile_long_ptr = h->d_tile_long_ptr.p; D.long_grp = h->d_long_grp.p; D.long_ptr = h->d_long_ptr.p;
   D.long_pk = h->d_long_pk.p; D.long_val = h->d_long_val.p;
   D.dinv = h->d_dinv.p; D.int2ref = h->d_int2ref.p;
+  D.numChunks = (int)L.chunk_beg.size();
+  D.chunk_beg = h->d_chunk_beg.p; D.chunk_end = h->d_chunk_end.p; D.long_chunk_ptr = h->d_long_chunk_ptr.p;
+  D.TRP = L.TRP; D.maxTileSpill = (int)L.max_tile_spill;
+  D.tile_sp_off = h->d_tile_sp_off.p; D.tile_sp_cnt = h->d_tile_sp_cnt.p; D.sp_gptr = h->d_sp_gptr.p;
+  D.sp_pk = h->d_sp_pk.p; D.sp_val = h->d_sp_val.p;
 }
 
 }  // namespace cora_b200
@@ -118,6 +123,13 @@ extern "C" int cora_b200_create(cora_b200_t **out, int device, void *stream, int
     h->d_tile_long_ptr.upload(L.tile_long_ptr, s); h->d_long_grp.upload(L.long_grp, s);
     h->d_long_ptr.upload(L.long_ptr, s); h->d_long_pk.upload(L.long_pk, s); h->d_long_val.upload(L.long_val, s);
     h->d_int2ref.upload(L.int2ref, s);
+    h->d_chunk_beg.upload(L.chunk_beg, s); h->d_chunk_end.upload(L.chunk_end, s);
+    h->d_long_chunk_ptr.upload(L.long_chunk_ptr, s);
+    { std::vector<long long> o(L.tile_sp_off.begin(), L.tile_sp_off.end()); h->d_tile_sp_off.upload(o, s);
+      CUDA_CHECK(cudaStreamSynchronize(s)); }
+    h->d_tile_sp_cnt.upload(L.tile_sp_cnt, s); h->d_sp_gptr.upload(L.sp_gptr, s);
+    h->d_sp_pk.upload(L.sp_pk, s); h->d_sp_val.upload(L.sp_val, s);
+    if (const char *e = getenv("CORA_B200_TNT_PATH")) h->use_persistent = std::string(e) != "launch";
     h->d_diag.upload(L.diag, s);
     { std::vector<double> inv(L.diag.size());
       for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1.0 / L.diag[i];  // src/CORA_problem.cpp:616-618
@@ -167,6 +179,7 @@ extern "C" int cora_b200_destroy(cora_b200_t *h) {
   destroy_chain_chol(h->chol);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  if (h->h_tntdev) cudaFreeHost(h->h_tntdev);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 2; ++i)

@@ -64,6 +64,10 @@ struct cora_b200_handle {
   cora_b200::DevLayout DL{};
   // device copies of the layout
   cora_b200::DevBuf<int> d_tile_slots, d_bcol, d_grp_ptr, d_tile_long_ptr, d_long_grp, d_long_ptr, d_int2ref;
+  cora_b200::DevBuf<int> d_chunk_beg, d_chunk_end, d_long_chunk_ptr, d_tile_sp_cnt, d_sp_gptr;
+  cora_b200::DevBuf<long long> d_tile_sp_off;
+  cora_b200::DevBuf<unsigned> d_sp_pk;
+  cora_b200::DevBuf<double> d_sp_val;
   cora_b200::DevBuf<long long> d_tile_boff, d_tile_coff;
   cora_b200::DevBuf<unsigned> d_rem_pk, d_long_pk;
   cora_b200::DevBuf<double> d_bval, d_sdiag, d_rem_val, d_long_val, d_dinv, d_diag;
@@ -96,5 +100,16 @@ struct cora_b200_handle {
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_n = 0;
   cora_b200::DevBuf<double> d_snap;  // snapshot of the resident iterate
+  // persistent TNT kernel (persistent.cuh)
+  cora_b200::DevBuf<double> d_longpart, d_ppartials, d_trace;
+  cora_b200::DevBuf<unsigned long long> d_bar;
+  cora_b200::DevBuf<int> d_cta_t0;
+  cora_b200::DevBuf<unsigned char> d_tntdev;
+  void *h_tntdev = nullptr;  // pinned TntDev
+  std::vector<double> h_trace;
+  int trace_cap = 0;
+  int persistent_grid = 0, persistent_grid_r = -1, persistent_nbuf = 0, persistent_threads = 256;
+  size_t persistent_smem = 0;
+  bool use_persistent = true;
   int snap_r = 0;
 };

@@ -52,6 +52,16 @@ struct DevLayout {
   const int *long_ptr;
   const unsigned *long_pk;
   const double *long_val;
+  int numChunks;              // hub rows split in chunks of kHubChunk entries (persistent kernel)
+  const int *chunk_beg;
+  const int *chunk_end;
+  const int *long_chunk_ptr;  // per hub group: first chunk
+  int TRP, maxTileSpill;      // per-tile spill slices (persistent kernel)
+  const long long *tile_sp_off;
+  const int *tile_sp_cnt;
+  const int *sp_gptr;
+  const unsigned *sp_pk;
+  const double *sp_val;
   const double *dinv;  // 1/diag(Q), internal order
   const int *int2ref;
 };

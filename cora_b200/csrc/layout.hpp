@@ -33,6 +33,7 @@ namespace cora_b200 {
 constexpr int kSMAX = 8;         // max block-ELL slots per pose
 constexpr int kLongGroup = 64;   // spill groups longer than this go to the hub kernel
 constexpr uint32_t kColMask = 0x3fffffffu;
+constexpr int kHubChunk = 512;   // hub-row entries per work item of the persistent kernel
 
 struct HostLayout {
   int d = 0, n = 0, m = 0, l = 0, D1 = 0;
@@ -52,6 +53,15 @@ struct HostLayout {
   std::vector<int32_t> tile_long_ptr, long_grp, long_ptr;
   std::vector<uint32_t> long_pk;
   std::vector<double> long_val;
+  std::vector<int32_t> chunk_beg, chunk_end, long_chunk_ptr;
+  // per-tile copy of the spill (persistent kernel: one bulk copy per tile): tile-local group
+  // pointers [numTiles][TRP], entries padded to a multiple of 4 per tile
+  int TRP = 0;
+  int64_t max_tile_spill = 0;
+  std::vector<int64_t> tile_sp_off;
+  std::vector<int32_t> tile_sp_cnt, sp_gptr;
+  std::vector<uint32_t> sp_pk;
+  std::vector<double> sp_val;
   std::vector<double> diag;  // N, internal order
   int64_t nnz_in = 0, nnz_block = 0, nnz_rem = 0, nnz_long = 0, max_slots = 0;
 
@@ -234,6 +244,41 @@ inline void build_layout(HostLayout &L, int d, int n, int m, int nt, const int32
     L.rem_val.swap(new_val);
     L.nnz_rem = (int64_t)L.rem_pk.size();
     L.nnz_long = (int64_t)L.long_pk.size();
+    // per-tile spill slices
+    L.TRP = L.TR + 4;
+    L.tile_sp_off.assign((size_t)L.numTiles + 1, 0);
+    L.tile_sp_cnt.assign((size_t)L.numTiles, 0);
+    L.sp_gptr.assign((size_t)L.numTiles * L.TRP, 0);
+    for (int t = 0; t < L.numTiles; ++t) {
+      const int64_t row0 = (int64_t)t * L.TR;
+      const int nR = (int)std::min<int64_t>(L.TR, N - row0);
+      const int nP = (int)std::max<int64_t>(0, std::min<int64_t>(L.TP, (int64_t)n - (int64_t)t * L.TP));
+      const int nS = nR - nP * D1;
+      int32_t *gp = L.sp_gptr.data() + (size_t)t * L.TRP;
+      int32_t cnt = 0;
+      for (int u = 0; u < nP + nS; ++u) {
+        const int64_t g = u < nP ? (int64_t)t * L.TP + u : (int64_t)n + (row0 + (int64_t)nP * D1 + (u - nP) - L.nPoseRows);
+        gp[u] = cnt;
+        for (int32_t k = L.grp_ptr[g]; k < L.grp_ptr[g + 1]; ++k) {
+          L.sp_pk.push_back(L.rem_pk[k]);
+          L.sp_val.push_back(L.rem_val[k]);
+          ++cnt;
+        }
+      }
+      for (int u = nP + nS; u < L.TRP; ++u) gp[u] = cnt;
+      L.max_tile_spill = std::max<int64_t>(L.max_tile_spill, cnt);
+      while (cnt % 4) { L.sp_pk.push_back(0); L.sp_val.push_back(0.0); ++cnt; }
+      L.tile_sp_cnt[t] = cnt;
+      L.tile_sp_off[t + 1] = L.tile_sp_off[t] + cnt;
+    }
+    L.long_chunk_ptr.assign(1, 0);
+    for (size_t q = 0; q < L.long_grp.size(); ++q) {
+      for (int32_t k = L.long_ptr[q]; k < L.long_ptr[q + 1]; k += kHubChunk) {
+        L.chunk_beg.push_back(k);
+        L.chunk_end.push_back(std::min<int32_t>(k + kHubChunk, L.long_ptr[q + 1]));
+      }
+      L.long_chunk_ptr.push_back((int32_t)L.chunk_beg.size());
+    }
   }
 }
 

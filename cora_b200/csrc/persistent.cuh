@@ -1,0 +1,940 @@
+// persistent.cuh -- the whole truncated-Newton trust-region solve as ONE persistent cooperative
+// kernel (one launch per TNT call; sm_100a, 148 SMs x resident CTAs).
+//
+//   TNT    libs/Optimization/include/Optimization/Riemannian/TNT.h:242-689
+//   STPCG  libs/Optimization/include/Optimization/LinearAlgebra/IterativeSolvers.h:166-426
+//   closures f / QM / metric / retract / precon: src/CORA.cpp:52-122
+//
+// Why: the multi-launch path (solver.cuh) spends ~170 us per CG iteration and ~1 ms per outer
+// iteration on launch latency, gated no-op launches and a one-CTA-per-hub-row kernel, against a
+// ~47 us HBM floor (profiles/README.md, r01a).  Here every CTA owns the tiles b, b+G, b+2G, ... for
+// the whole solve; phases are separated by a grid barrier (one atomic counter in L2), every inner
+// product is reduced through per-CTA partials that EVERY CTA sums in the same fixed order after the
+// barrier (deterministic, no broadcast needed), and all scalar logic of STPCG and TNT runs
+// redundantly and identically in every CTA.  One CG iteration is three phases:
+//   A  Hp = Hess[p] (Q p from the block-ELL slice staged in shared memory, neighbours of in-tile
+//      poses served from the staged tile, Riemannian epilogue) + <p,Hp>, <Hp,Hp>, <p,p>
+//   B  s += alpha p ; r += alpha Hp ; v = proj_Y(M^-1 r) ; <r,v>
+//   C  p' = -v + beta p  (double buffered) fused with the landmark hub-row partial sums of Q p',
+//      split in chunks over all CTAs, evaluated on the fly as -v[j] + beta p[j]
+// Vectors written by other CTAs during the kernel are read with ld.global.cg (L2-coherent); only
+// the data matrix goes through the non-coherent path.
+#pragma once
+#include "ops.cuh"
+
+namespace cora_b200 {
+
+constexpr int kPPart = 8;  // partial sums per CTA and reduction
+constexpr int kMaxTilesPerCta = 64;  // tile metadata cached in shared memory for the whole solve
+
+// trace rows in the device trace buffer (TNTResult, TNT.h:168-194)
+enum TraceRow { TR_F = 0, TR_G, TR_PG, TR_DELTA, TR_TIME, TR_HNORM, TR_HM, TR_RHO, TR_INNER, TR_ROWS };
+
+struct TntDev {  // results of one persistent TNT call (device -> host)
+  double f, gnorm, pgnorm, Delta, elapsed;
+  int status, num_outer, n_state, pad;
+  long long total_inner, barriers;
+  int perm[V_COUNT];  // perm[role] = index of the original buffer now playing that role
+  unsigned long long prof_ns[16];  // CTA 0's time per phase kind (PhaseId)
+  unsigned int prof_cnt[16];
+};
+enum PhaseId { PH_HUB = 0, PH_GRAD, PH_HESS, PH_UPDATE, PH_PUPDATE, PH_RETRACT, PH_PRECOND, PH_CGINIT, PH_SYNC, PH_MISC, PH_Q_WAIT, PH_Q_QX, PH_Q_EPI, PH_Q_STORE, PH_COUNT };
+
+struct PArgs {
+  double *v[V_COUNT];
+  double *longpart;             // 2 x numChunks x D1 x r
+  double *partials;             // 2 x (G*kPPart + 8)
+  unsigned long long *bar;      // grid barrier counter (zeroed by the host before the launch)
+  double *trace;                // TR_ROWS x trace_cap
+  TntDev *out;
+  unsigned long long *prof_all;  // [G][PH_COUNT] per-CTA phase times (nullptr: off)
+  const int *cta_t0;             // [G+1] cost-balanced contiguous tile ranges
+  cora_b200_tnt_params p;
+  int r, trace_cap, precond, nbuf;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---------------------------------------------------------------- async copies ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// One staging buffer of the tile pipeline: the tile's slice of the data matrix (block-ELL values and
+// columns, spill group pointers / entries) filled by bulk copies, and three tile-row slots of dense
+// vectors (padded layout of Geo<D>) filled by 8-byte cp.async.
+struct TileBuf {
+  double *sval, *spv, *slot[3];
+  int *scol, *gptr;
+  unsigned *spk;
+  unsigned long long *mbar;
+  int *meta;  // [0] = slots S of the tile
+};
+struct TileMeta {  // per owned tile, cached in shared memory at kernel start
+  long long boff, coff, spoff;
+  int S, nsp, lq0, lq1;
+};
+
+// Per-CTA context of the persistent kernel.
+struct PCtx {
+  int b, G, tid, nth, r, nbuf;
+  int t0, t1;           // the CTA's contiguous tile range
+  long long e0, e1;     // ... and its flat element range [e0, e1) of every N x r vector
+  unsigned long long *bar;
+  unsigned long long target;
+  double *partials;
+  int parity;
+  long long nbar;
+  unsigned long long prof_ns[PH_COUNT], tph, tsub;
+  unsigned int prof_cnt[PH_COUNT];
+  unsigned mpar0, mpar1;  // mbarrier phase parity per buffer
+  // shared memory
+  double *sred, *sbc, *sW;
+  const TileMeta *tmeta;
+  TileBuf tb0, tb1;
+  __device__ __forceinline__ TileBuf pick(int buf) const {
+    TileBuf B;
+    B.sval = buf ? tb1.sval : tb0.sval; B.spv = buf ? tb1.spv : tb0.spv;
+    B.slot[0] = buf ? tb1.slot[0] : tb0.slot[0]; B.slot[1] = buf ? tb1.slot[1] : tb0.slot[1];
+    B.slot[2] = buf ? tb1.slot[2] : tb0.slot[2];
+    B.scol = buf ? tb1.scol : tb0.scol; B.gptr = buf ? tb1.gptr : tb0.gptr; B.spk = buf ? tb1.spk : tb0.spk;
+    B.mbar = buf ? tb1.mbar : tb0.mbar; B.meta = buf ? tb1.meta : tb0.meta;
+    return B;
+  }
+};
+
+__device__ __forceinline__ void ph_begin(PCtx &c) {
+  if (c.tid == 0) c.tph = global_timer_ns();
+}
+__device__ __forceinline__ void ph_end(PCtx &c, int id) {
+  if (c.tid == 0) {
+    const unsigned long long t = global_timer_ns();
+    c.prof_ns[id] += t - c.tph;
+    c.prof_cnt[id] += 1;
+    c.tph = t;
+  }
+}
+
+__device__ __forceinline__ void sub_begin(PCtx &c) {
+  if (c.tid == 0) c.tsub = global_timer_ns();
+}
+__device__ __forceinline__ void sub_end(PCtx &c, int id) {
+  if (c.tid == 0) {
+    const unsigned long long t = global_timer_ns();
+    c.prof_ns[id] += t - c.tsub;
+    c.prof_cnt[id] += 1;
+    c.tsub = t;
+  }
+}
+
+__device__ __forceinline__ void grid_sync(PCtx &c) {
+  __syncthreads();
+  ph_begin(c);
+  if (c.tid == 0) {
+    c.target += (unsigned long long)c.G;
+    __threadfence();
+    atomicAdd(c.bar, 1ULL);
+    while (ld_acquire_u64(c.bar) < c.target) { }
+    __threadfence();
+  }
+  ++c.nbar;
+  ph_end(c, PH_SYNC);
+  __syncthreads();
+}
+
+// Sum K per-thread accumulators over the whole grid.  On return every thread of every CTA holds
+// the same totals (summed in a fixed order) and *now_ns = CTA 0's clock at the barrier.
+template <int K>
+__device__ __forceinline__ void grid_reduce(double (&acc)[K], PCtx &c, unsigned long long *now_ns) {
+  static_assert(K <= kPPart, "too many partials");
+  block_sum<K>(acc, c.sred);
+  double *part = c.partials + (size_t)c.parity * ((size_t)c.G * kPPart + 8);
+  if (c.tid == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) part[(size_t)c.b * kPPart + k] = acc[k];
+    if (c.b == 0) ((unsigned long long *)part)[(size_t)c.G * kPPart] = global_timer_ns();
+  }
+  grid_sync(c);
+  double t[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = 0.0;
+  for (int i = c.tid; i < c.G; i += c.nth)
+#pragma unroll
+    for (int k = 0; k < K; ++k) t[k] += __ldcg(part + (size_t)i * kPPart + k);
+  block_sum<K>(t, c.sred);
+  if (c.tid == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) c.sbc[k] = t[k];
+    c.sbc[K] = __longlong_as_double((long long)__ldcg((const unsigned long long *)part + (size_t)c.G * kPPart));
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = c.sbc[k];
+  if (now_ns) *now_ns = (unsigned long long)__double_as_longlong(c.sbc[K]);
+  __syncthreads();
+  c.parity ^= 1;
+}
+
+// ------------------------------------------------------------------ hub chunks ----
+// Partial sums of the landmark hub rows of Q x for x = a*X + b*V (V may be nullptr), one chunk of
+// at most kHubChunk entries per work item: longpart[chunk][row-in-group][column].
+template <int D>
+__device__ __forceinline__ void hub_phase(const DevLayout &L, PCtx &c, const double *X, double a, const double *V,
+                                          double bcoef, double *longpart) {
+  constexpr int D1 = D + 1;
+  const int r = c.r;
+  const int per = c.nth / r;
+  const int e = c.tid / r, cc = c.tid - e * r;
+  double *sm = c.sW;  // D1 * nth doubles: spans sW and the vector slots that follow it
+  ph_begin(c);
+  for (int ch = c.b; ch < L.numChunks; ch += c.G) {
+    double acc[D1];
+#pragma unroll
+    for (int q = 0; q < D1; ++q) acc[q] = 0.0;
+    if (e < per) {
+      const int k0 = L.chunk_beg[ch], k1 = L.chunk_end[ch];
+      for (int k = k0 + e; k < k1; k += per) {
+        const unsigned pk = __ldg(L.long_pk + k);
+        const int lr = (int)(pk >> 30);
+        const size_t o = (size_t)(pk & kColMask) * r + cc;
+        double x = a * __ldcg(X + o);
+        if (V != nullptr) x = fma(bcoef, __ldcg(V + o), x);
+        const double xv = __ldg(L.long_val + k) * x;
+#pragma unroll
+        for (int q = 0; q < D1; ++q) acc[q] += (lr == q) ? xv : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < D1; ++q) sm[q * c.nth + c.tid] = acc[q];
+    __syncthreads();
+    if (c.tid < D1 * r) {
+      const int q = c.tid / r, c2 = c.tid - q * r;
+      double s = 0.0;
+      for (int i = 0; i < per; ++i) s += sm[q * c.nth + i * r + c2];
+      longpart[((size_t)ch * D1 + q) * r + c2] = s;
+    }
+  }
+  __syncthreads();
+  ph_end(c, PH_HUB);
+}
+
+// tile geometry without touching global memory
+template <int D>
+__device__ __forceinline__ TileInfo tile_geom(const DevLayout &L, int t, int r) {
+  TileInfo T;
+  T.row0 = t * L.TR;
+  T.nR = min(L.TR, L.N - T.row0);
+  T.nP = max(0, min(L.TP, L.n - t * L.TP));
+  T.nS = T.nR - T.nP * (D + 1);
+  T.S = 0;
+  T.ebase = (long long)T.row0 * r;
+  return T;
+}
+
+// ---------------------------------------------------------------- tile pipeline ----
+// Issue the asynchronous loads of tile t into buffer `buf`: NV dense vectors (tile rows, padded
+// layout) by cp.async, and -- when NEEDQ -- the tile's data-matrix slice by TMA bulk copies.
+template <int D, bool NEEDQ, int NV>
+__device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
+                                              const double *v1, const double *v2) {
+  constexpr int D1 = D + 1;
+  const int r = c.r;
+  const Geo<D> geo(r);
+  const TileBuf B = c.pick(buf);
+  if (NEEDQ && c.tid == 0) {
+    const TileMeta M = c.tmeta[t - c.t0];
+    const int S = M.S, nsp = M.nsp;
+    B.meta[0] = S;
+    const unsigned bq = (unsigned)S * D1 * D1 * L.TP * 8u, bc = (unsigned)S * L.TP * 4u;
+    const unsigned bg = (unsigned)L.TRP * 4u, bp = (unsigned)nsp * 4u, bv = (unsigned)nsp * 8u;
+    mbar_expect_tx(B.mbar, bq + bc + bg + bp + bv);
+    if (S > 0) {
+      bulk_g2s(B.sval, L.bval + M.boff, bq, B.mbar);
+      bulk_g2s(B.scol, L.bcol + M.coff, bc, B.mbar);
+    }
+    bulk_g2s(B.gptr, L.sp_gptr + (size_t)t * L.TRP, bg, B.mbar);
+    if (nsp > 0) {
+      bulk_g2s(B.spk, L.sp_pk + M.spoff, bp, B.mbar);
+      bulk_g2s(B.spv, L.sp_val + M.spoff, bv, B.mbar);
+    }
+  }
+  const int row0 = t * L.TR;
+  const int nR = min(L.TR, L.N - row0);
+  const int nE = nR * r;
+  const long long eb = (long long)row0 * r;
+  for (int le = c.tid; le < nE; le += c.nth) {
+    const int lrow = le / r, cc = le - lrow * r;
+    const int so = geo.soff(lrow, cc);
+    if (NV > 0) cp_async8(B.slot[0] + so, v0 + eb + le);
+    if (NV > 1) cp_async8(B.slot[1] + so, v1 + eb + le);
+    if (NV > 2) cp_async8(B.slot[2] + so, v2 + eb + le);
+  }
+  if (NEEDQ) {
+    // halo of the multiplied vector: one pose block before and after the tile, so that the
+    // neighbours of an odometry chain never leave shared memory (slot pointers are one pose
+    // stride into their buffers; see the carve-up in the kernel)
+    const int hE = D1 * r;
+    if (c.tid < 2 * hE) {
+      const int side = c.tid / hE, le = c.tid - side * hE;
+      const int lrow = le / r, cc = le - lrow * r;
+      const int grow = side == 0 ? row0 - D1 + lrow : row0 + nR + lrow;
+      if (grow >= 0 && grow < L.N) {
+        const int hl = side == 0 ? lrow - D1 : nR + lrow;  // local row, may be negative
+        const int so = (hl + D1) * geo.RS + (geo.PADP ? (hl + D1) / D1 : 0) + cc - (D1 * geo.RS + geo.PADP);
+        cp_async8(B.slot[0] + so, v0 + (long long)grow * r + cc);
+      }
+    }
+  }
+  cp_async_commit();
+}
+
+// Top of a pipeline iteration: start tile t+1 (double buffered), then wait for tile t.
+template <int D, bool NEEDQ, int NV>
+__device__ __forceinline__ void tile_acquire(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
+                                             const double *v1, const double *v2) {
+  if (c.nbuf == 2 && t + 1 < c.t1) {
+    tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, buf ^ 1, v0, v1, v2);
+    cp_async_wait<1>();
+  } else {
+    cp_async_wait<0>();
+  }
+  if (NEEDQ) {
+    mbar_wait(buf ? c.tb1.mbar : c.tb0.mbar, buf ? c.mpar1 : c.mpar0);
+    if (buf) c.mpar1 ^= 1u; else c.mpar0 ^= 1u;
+  }
+  __syncthreads();
+}
+// Bottom: every thread is done with tile t's buffer.
+template <int D, bool NEEDQ, int NV>
+__device__ __forceinline__ void tile_release(const DevLayout &L, PCtx &c, int t, int &buf, const double *v0,
+                                             const double *v1, const double *v2) {
+  __syncthreads();
+  if (c.nbuf == 2) buf ^= 1;
+  else if (t + 1 < c.t1) tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, 0, v0, v1, v2);
+}
+
+// sW <- (Q X)[tile]; sX holds the tile rows of X plus one pose block of halo on either side
+// (staged), X is the global vector (columns outside the staged window, spill columns).
+template <int D>
+__device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInfo &T, const Geo<D> &geo, PCtx &c,
+                                        const TileBuf &B, const double *X, const double *sX,
+                                        const double *longpart) {
+  constexpr int D1 = D + 1;
+  const int r = c.r, TP = L.TP;
+  const int S = B.meta[0];
+  const int nPoseItems = T.nP * r;
+  const int winLo = max(T.row0 - D1, 0);
+  const int winHi = min(min(T.row0 + T.nR + D1, L.N), L.nPoseRows);  // exclusive, pose rows only
+  const int pstride = D1 * geo.RS + geo.PADP;
+  for (int it = c.tid; it < nPoseItems; it += c.nth) {
+    const int p = it / r, cc = it - p * r;
+    // spill columns first: their L2 round trip overlaps the block products below
+    const int k0 = B.gptr[p], k1 = B.gptr[p + 1];
+    double xs0 = 0.0, xs1 = 0.0;
+    if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
+    if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
+    double acc[D1];
+#pragma unroll
+    for (int a = 0; a < D1; ++a) acc[a] = 0.0;
+    for (int s = 0; s < S; ++s) {
+      const int jb = B.scol[s * TP + p];
+      double x[D1];
+      if (jb >= winLo && jb + D1 <= winHi) {
+        const int lp = (jb - T.row0 + D1) / D1 - 1;  // local pose index, -1 and nP are the halo
+        const double *xp = sX + lp * pstride + cc;
+#pragma unroll
+        for (int q = 0; q < D1; ++q) x[q] = xp[q * geo.RS];
+      } else {
+        const double *xp = X + (size_t)jb * r + cc;
+#pragma unroll
+        for (int q = 0; q < D1; ++q) x[q] = __ldcg(xp + q * r);
+      }
+      const double *bv = B.sval + (size_t)s * D1 * D1 * TP + p;
+#pragma unroll
+      for (int a = 0; a < D1; ++a)
+#pragma unroll
+        for (int q = 0; q < D1; ++q) acc[a] = fma(bv[(a * D1 + q) * TP], x[q], acc[a]);
+    }
+    for (int k = k0; k < k1; ++k) {
+      const unsigned pk = B.spk[k];
+      const int lr = (int)(pk >> 30);
+      const double xg = k == k0 ? xs0 : (k == k0 + 1 ? xs1 : __ldcg(X + (size_t)(pk & kColMask) * r + cc));
+      const double xv = B.spv[k] * xg;
+#pragma unroll
+      for (int a = 0; a < D1; ++a) acc[a] += (lr == a) ? xv : 0.0;
+    }
+    const int o = geo.pose_base(p) + cc;
+#pragma unroll
+    for (int a = 0; a < D1; ++a) c.sW[o + a * geo.RS] = acc[a];
+  }
+  // scalar rows (landmarks, ranges): diagonal + spill; two gathers in flight per item
+  const int nSI = T.nS * r;
+#pragma unroll 2
+  for (int j = c.tid; j < nSI; j += c.nth) {
+    const int sr = j / r, cc = j - sr * r;
+    const int lrow = T.nP * D1 + sr;
+    const int sidx = T.row0 + lrow - L.nPoseRows;
+    const int u = T.nP + sr;
+    const int k0 = B.gptr[u], k1 = B.gptr[u + 1];
+    double xs0 = 0.0, xs1 = 0.0;
+    if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
+    if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
+    double acc = __ldg(L.sdiag + sidx) * sX[geo.soff(lrow, cc)];
+    if (k0 < k1) acc = fma(B.spv[k0], xs0, acc);
+    if (k0 + 1 < k1) acc = fma(B.spv[k0 + 1], xs1, acc);
+    for (int k = k0 + 2; k < k1; ++k)
+      acc = fma(B.spv[k], __ldcg(X + (size_t)(B.spk[k] & kColMask) * r + cc), acc);
+    c.sW[geo.soff(lrow, cc)] = acc;
+  }
+  __syncthreads();
+  const TileMeta &M = c.tmeta[t - c.t0];
+  const int q0 = M.lq0, q1 = M.lq1;
+  for (int q = q0; q < q1; ++q) {
+    const int g = L.long_grp[q];
+    const int lrow0 = (g < L.n ? g * D1 : L.nPoseRows + (g - L.n)) - T.row0;
+    const int nrow = g < L.n ? D1 : 1;
+    const int c0 = L.long_chunk_ptr[q], c1 = L.long_chunk_ptr[q + 1];
+    for (int i = c.tid; i < nrow * r; i += c.nth) {
+      const int a = i / r, cc = i - a * r;
+      double s = 0.0;
+      for (int ch = c0; ch < c1; ++ch) s += __ldcg(longpart + ((size_t)ch * D1 + a) * r + cc);
+      c.sW[geo.soff(lrow0 + a, cc)] += s;
+    }
+  }
+  if (q1 > q0) __syncthreads();
+}
+
+// --------------------------------------------------------------------- phases ----
+// GRAD: out2 = Q X, out = proj_X(Q X); acc[0] += <X, QX>, acc[1] += <grad, grad>
+// HESS: out = Hess_Y[X] (G = Q Y);     acc[0] += <X, out>, acc[1] += <out, out>, acc[2] += <X, X>
+template <int D, int MODE>
+__device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const double *X, const double *Y,
+                                            const double *Gv, double *out, double *out2,
+                                            const double *longpart, double *acc) {
+  constexpr int NV = (MODE == QM_HESS) ? 3 : 1;
+  const int r = c.r;
+  const Geo<D> geo(r);
+  ph_begin(c);
+  int buf = 0;
+  if (c.t0 < c.t1) tile_prefetch<D, true, NV>(L, c, c.t0, 0, X, Y, Gv);
+  for (int t = c.t0; t < c.t1; ++t) {
+    sub_begin(c);
+    tile_acquire<D, true, NV>(L, c, t, buf, X, Y, Gv);
+    sub_end(c, PH_Q_WAIT);
+    const TileBuf B = c.pick(buf);
+    TileInfo T = tile_geom<D>(L, t, r);
+    const int nE = T.nR * r;
+    const double *sX = B.slot[0], *sY = B.slot[1], *sG = B.slot[2];
+    tile_qx<D>(L, t, T, geo, c, B, X, sX, longpart);
+    sub_end(c, PH_Q_QX);
+    if (MODE == QM_SPMM) {
+      for (int le = c.tid; le < nE; le += c.nth) {
+        const int lrow = le / r, cc = le - lrow * r;
+        out[T.ebase + le] = c.sW[geo.soff(lrow, cc)];
+      }
+    } else if (MODE == QM_GRAD) {
+      for (int le = c.tid; le < nE; le += c.nth) {
+        const int lrow = le / r, cc = le - lrow * r;
+        const int so = geo.soff(lrow, cc);
+        const double w = c.sW[so];
+        out2[T.ebase + le] = w;
+        acc[0] = fma(sX[so], w, acc[0]);
+      }
+      __syncthreads();
+      tile_epilogue<D, false>(L, T, geo, sX, nullptr, nullptr, c.sW);
+      __syncthreads();
+      for (int le = c.tid; le < nE; le += c.nth) {
+        const int lrow = le / r, cc = le - lrow * r;
+        const double w = c.sW[geo.soff(lrow, cc)];
+        out[T.ebase + le] = w;
+        acc[1] = fma(w, w, acc[1]);
+      }
+    } else {
+      tile_epilogue<D, true>(L, T, geo, sY, sG, sX, c.sW);
+      __syncthreads();
+      sub_end(c, PH_Q_EPI);
+      for (int le = c.tid; le < nE; le += c.nth) {
+        const int lrow = le / r, cc = le - lrow * r;
+        const int so = geo.soff(lrow, cc);
+        const double w = c.sW[so], dd = sX[so];
+        out[T.ebase + le] = w;
+        acc[0] = fma(dd, w, acc[0]);
+        acc[1] = fma(w, w, acc[1]);
+        acc[2] = fma(dd, dd, acc[2]);
+      }
+    }
+    tile_release<D, true, NV>(L, c, t, buf, X, Y, Gv);
+    sub_end(c, PH_Q_STORE);
+  }
+  ph_end(c, MODE == QM_HESS ? PH_HESS : PH_GRAD);
+}
+
+// STPCG update + preconditioner closure (IterativeSolvers.h:374-386, src/CORA.cpp:89-92):
+//   AXPY: R += alpha HP (tile pipeline)         then   V = proj_Y(z), z = R*dinv | R | Z
+//   acc[0] += <R, V>, acc[1] += <V, V>.   (S += alpha P is a separate flat pass: axpy_flat)
+template <int D, bool AXPY>
+__device__ __forceinline__ void update_phase(const DevLayout &L, PCtx &c, const double *Y, const double *HP,
+                                             double *R, const double *Z, double *V, double alpha, int zsrc,
+                                             double *acc) {
+  constexpr int NV = 3;
+  const int r = c.r;
+  const Geo<D> geo(r);
+  const double *third = AXPY ? HP : (zsrc == 2 ? Z : Y);
+  ph_begin(c);
+  int buf = 0;
+  if (c.t0 < c.t1) tile_prefetch<D, false, NV>(L, c, c.t0, 0, R, Y, third);
+  for (int t = c.t0; t < c.t1; ++t) {
+    tile_acquire<D, false, NV>(L, c, t, buf, R, Y, third);
+    const TileBuf B = c.pick(buf);
+    const TileInfo T = tile_geom<D>(L, t, r);
+    const int nE = T.nR * r;
+    double *sR = B.slot[0], *sY = B.slot[1], *s3 = B.slot[2];
+    double *sZ = c.sW;
+    for (int le = c.tid; le < nE; le += c.nth) {
+      const int lrow = le / r, cc = le - lrow * r;
+      const int so = geo.soff(lrow, cc);
+      double rr = sR[so];
+      if (AXPY) {
+        rr = fma(alpha, s3[so], rr);
+        R[T.ebase + le] = rr;
+        sR[so] = rr;
+      }
+      double z;
+      if (zsrc == 0) z = rr * __ldg(L.dinv + T.row0 + lrow);
+      else if (zsrc == 1) z = rr;
+      else z = s3[so];
+      sZ[so] = z;
+    }
+    __syncthreads();
+    tile_epilogue<D, false>(L, T, geo, sY, nullptr, nullptr, sZ);
+    __syncthreads();
+    for (int le = c.tid; le < nE; le += c.nth) {
+      const int lrow = le / r, cc = le - lrow * r;
+      const int so = geo.soff(lrow, cc);
+      const double v = sZ[so];
+      V[T.ebase + le] = v;
+      acc[0] = fma(sR[so], v, acc[0]);
+      acc[1] = fma(v, v, acc[1]);
+    }
+    tile_release<D, false, NV>(L, c, t, buf, R, Y, third);
+  }
+  ph_end(c, AXPY ? PH_UPDATE : PH_PRECOND);
+}
+
+// out = a*X + b*Y over the CTA's contiguous element range (Y may be nullptr); flat and unrolled
+__device__ __forceinline__ void axpby_flat(PCtx &c, double a, const double *X, double bcoef, const double *Y,
+                                           double *out) {
+  ph_begin(c);
+#pragma unroll 4
+  for (long long e = c.e0 + c.tid; e < c.e1; e += c.nth) {
+    double v = a * __ldcg(X + e);
+    if (Y != nullptr) v = fma(bcoef, __ldcg(Y + e), v);
+    out[e] = v;
+  }
+  ph_end(c, PH_PUPDATE);
+}
+
+// STPCG initialisation (IterativeSolvers.h:207-279): S = 0, R = grad, P = -v
+__device__ __forceinline__ void cg_init_flat(PCtx &c, const double *Gr, const double *Vv, double *S, double *R,
+                                             double *P) {
+  ph_begin(c);
+#pragma unroll 4
+  for (long long e = c.e0 + c.tid; e < c.e1; e += c.nth) {
+    S[e] = 0.0;
+    R[e] = __ldcg(Gr + e);
+    P[e] = -__ldcg(Vv + e);
+  }
+  ph_end(c, PH_CGINIT);
+}
+
+// acc[0] += <A, B> over the CTA's element range
+__device__ __forceinline__ void dot_flat(PCtx &c, const double *A, const double *B, double *acc) {
+#pragma unroll 4
+  for (long long e = c.e0 + c.tid; e < c.e1; e += c.nth) acc[0] = fma(__ldcg(A + e), __ldcg(B + e), acc[0]);
+}
+
+// XP = projectToManifold(X + S) (src/CORA_problem.cpp:905-938); acc[0] += <S,S>, acc[1] += <Gr,S>
+template <int D>
+__device__ __forceinline__ void retract_phase(const DevLayout &L, PCtx &c, const double *X, const double *S,
+                                              const double *Gr, double *XP, double *acc) {
+  constexpr int NV = 3;
+  const int r = c.r;
+  const Geo<D> geo(r);
+  double *sW = c.sW;
+  ph_begin(c);
+  int buf = 0;
+  if (c.t0 < c.t1) tile_prefetch<D, false, NV>(L, c, c.t0, 0, X, S, Gr);
+  for (int t = c.t0; t < c.t1; ++t) {
+    tile_acquire<D, false, NV>(L, c, t, buf, X, S, Gr);
+    const TileBuf B = c.pick(buf);
+    const TileInfo T = tile_geom<D>(L, t, r);
+    const int nE = T.nR * r;
+    for (int le = c.tid; le < nE; le += c.nth) {
+      const int lrow = le / r, cc = le - lrow * r;
+      const int so = geo.soff(lrow, cc);
+      const double s = B.slot[1][so];
+      acc[0] = fma(s, s, acc[0]);
+      acc[1] = fma(B.slot[2][so], s, acc[1]);
+      sW[so] = B.slot[0][so] + s;
+    }
+    __syncthreads();
+    for (int u = c.tid; u < T.nP + T.nS; u += c.nth) {
+      if (u < T.nP) {
+        stiefel_polar<D>(sW + geo.pose_base(u), r, geo.RS);
+      } else {
+        const int lrow = T.nP * (D + 1) + (u - T.nP);
+        if (T.row0 + lrow >= L.nPoseRows + L.l) {
+          double *w = sW + geo.soff(lrow, 0);
+          double s = 0.0;
+          for (int cc = 0; cc < r; ++cc) s = fma(w[cc], w[cc], s);
+          const double inv = 1.0 / sqrt(s);
+          for (int cc = 0; cc < r; ++cc) w[cc] *= inv;
+        }
+      }
+    }
+    __syncthreads();
+    for (int le = c.tid; le < nE; le += c.nth) {
+      const int lrow = le / r, cc = le - lrow * r;
+      XP[T.ebase + le] = sW[geo.soff(lrow, cc)];
+    }
+    tile_release<D, false, NV>(L, c, t, buf, X, S, Gr);
+  }
+  ph_end(c, PH_RETRACT);
+}
+
+// ============================================================ k_tnt_persistent ====
+template <int D>
+__global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout L, const PArgs A) {
+  constexpr int D1 = D + 1;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ CgCtrl cg;
+  __shared__ __align__(8) unsigned long long s_mbar[2];
+  __shared__ int s_meta[2][4];
+  __shared__ TileMeta s_tmeta[kMaxTilesPerCta];
+  PCtx c;
+  c.b = blockIdx.x; c.G = gridDim.x; c.tid = threadIdx.x; c.nth = blockDim.x; c.r = A.r; c.nbuf = A.nbuf;
+  c.bar = A.bar; c.target = 0; c.partials = A.partials; c.parity = 0; c.nbar = 0;
+#pragma unroll
+  for (int i = 0; i < PH_COUNT; ++i) { c.prof_ns[i] = 0; c.prof_cnt[i] = 0; }
+  c.tph = 0;
+  c.mpar0 = c.mpar1 = 0u;
+  const int r = A.r;
+  {
+    // contiguous tile range of this CTA and the matching flat element range
+    c.t0 = A.cta_t0[c.b];
+    c.t1 = A.cta_t0[c.b + 1];
+    c.e0 = (long long)c.t0 * L.TR * r;
+    c.e1 = min((long long)c.t1 * L.TR, (long long)L.N) * r;
+    if (c.e0 > c.e1) c.e0 = c.e1;
+    const Geo<D> geo(r);
+    const size_t nbv = (size_t)L.maxSlots * D1 * D1 * L.TP;              // doubles
+    const size_t ncol = ((size_t)L.maxSlots * L.TP + 3) & ~(size_t)3;    // ints
+    const size_t spcap = ((size_t)L.maxTileSpill + 3) & ~(size_t)3;      // entries
+    const size_t pstride = (size_t)D1 * geo.RS + geo.PADP;
+    const size_t vstride = ((size_t)L.TR * geo.RS + L.TP + 2 * pstride + 1) & ~(size_t)1;
+    double *p = smem;
+    c.sred = p; p += 64;
+    c.sbc = p; p += 16;
+    auto carve_q = [&](TileBuf &B) {
+      B.sval = p; p += nbv;
+      B.spv = p; p += spcap;
+      int *q = (int *)p;
+      B.scol = q; q += ncol;
+      B.gptr = q; q += L.TRP;
+      B.spk = (unsigned *)q; q += spcap;
+      p = (double *)q;
+    };
+    carve_q(c.tb0);
+    if (c.nbuf == 2) carve_q(c.tb1); else c.tb1 = c.tb0;
+    c.tb0.mbar = &s_mbar[0]; c.tb0.meta = s_meta[0];
+    c.tb1.mbar = &s_mbar[1]; c.tb1.meta = s_meta[1];
+    c.sW = p; p += vstride;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { c.tb0.slot[j] = p + pstride; p += vstride; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (c.nbuf == 2) { c.tb1.slot[j] = p + pstride; p += vstride; }
+      else c.tb1.slot[j] = c.tb0.slot[j];
+    }
+    c.tmeta = s_tmeta;
+    for (int i = c.tid; i < c.t1 - c.t0; i += c.nth) {
+      const int t = c.t0 + i;
+      TileMeta M;
+      M.boff = L.tile_boff[t]; M.coff = L.tile_coff[t]; M.spoff = L.tile_sp_off[t];
+      M.S = L.tile_slots[t]; M.nsp = L.tile_sp_cnt[t];
+      M.lq0 = L.tile_long_ptr[t]; M.lq1 = L.tile_long_ptr[t + 1];
+      s_tmeta[i] = M;
+    }
+    if (c.tid == 0) {
+      mbar_init(&s_mbar[0], 1);
+      mbar_init(&s_mbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  double *v[V_COUNT];
+  int perm[V_COUNT];
+#pragma unroll
+  for (int i = 0; i < V_COUNT; ++i) { v[i] = A.v[i]; perm[i] = i; }
+  auto swp = [&](int a, int b2) {
+    double *tp = v[a]; v[a] = v[b2]; v[b2] = tp;
+    const int ti = perm[a]; perm[a] = perm[b2]; perm[b2] = ti;
+  };
+  const cora_b200_tnt_params &P = A.p;
+  const size_t lpstride = (size_t)max(L.numChunks, 1) * D1 * r;
+  double *lp0 = A.longpart, *lp1 = A.longpart + lpstride;
+  const bool master = (c.b == 0 && c.tid == 0);
+  const double sqrt_eps = 1.4901161193847656e-08;
+  unsigned long long now = 0, t0 = 0;
+  int n_state = 0, n_iter = 0;
+  auto tr_state = [&](double el, double f, double g, double pg, double Dl) {
+    if (master && n_state < A.trace_cap) {
+      A.trace[(size_t)TR_TIME * A.trace_cap + n_state] = el;
+      A.trace[(size_t)TR_F * A.trace_cap + n_state] = f;
+      A.trace[(size_t)TR_G * A.trace_cap + n_state] = g;
+      A.trace[(size_t)TR_PG * A.trace_cap + n_state] = pg;
+      A.trace[(size_t)TR_DELTA * A.trace_cap + n_state] = Dl;
+    }
+    ++n_state;
+  };
+  auto tr_iter = [&](int inner, double hn, double hM, double rho) {
+    if (master && n_iter < A.trace_cap) {
+      A.trace[(size_t)TR_INNER * A.trace_cap + n_iter] = (double)inner;
+      A.trace[(size_t)TR_HNORM * A.trace_cap + n_iter] = hn;
+      A.trace[(size_t)TR_HM * A.trace_cap + n_iter] = hM;
+      A.trace[(size_t)TR_RHO * A.trace_cap + n_iter] = rho;
+    }
+    ++n_iter;
+  };
+  // preconditioned, projected vector: Vout = proj_Y(M^-1 Rin); sums <Rin,Vout>, <Vout,Vout>
+  auto precond_project = [&](const double *Y, double *Rin, double *Vout, double *acc2) {
+    update_phase<D, false>(L, c, Y, nullptr, Rin, nullptr, Vout, 0.0,
+                           A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, acc2);
+  };
+
+  // ---- TNT.h:372-392: f(x), QM(x), gradient norms ----
+  if (L.numChunks > 0) {
+    hub_phase<D>(L, c, v[V_X], 1.0, nullptr, 0.0, lp0);
+    grid_sync(c);
+  }
+  double fx, gnorm, pgnorm, rv_cur;
+  {
+    double acc[3] = {0.0, 0.0, 0.0};
+    qprod_phase<D, QM_GRAD>(L, c, v[V_X], nullptr, nullptr, v[V_GRAD], v[V_G], lp0, acc);
+    grid_reduce<3>(acc, c, &t0);
+    fx = 0.5 * acc[0];
+    gnorm = sqrt(acc[1]);
+    double a2[2] = {0.0, 0.0};
+    precond_project(v[V_X], v[V_GRAD], v[V_PG], a2);
+    grid_reduce<2>(a2, c, &now);
+    rv_cur = a2[0];
+    pgnorm = sqrt(a2[1]);
+  }
+  double Delta = P.Delta0;
+  int status = CORA_B200_TNT_ITERATION_LIMIT;
+  long long total_inner = 0;
+  int iteration = 0;
+  double el = 0.0;
+  for (; iteration < P.max_iterations; ++iteration) {
+    el = (double)(now - t0) * 1e-9;
+    if (P.max_computation_time > 0 && el > P.max_computation_time) {  // TNT.h:447-452
+      status = CORA_B200_TNT_ELAPSED_TIME;
+      break;
+    }
+    tr_state(el, fx, gnorm, pgnorm, Delta);
+    if (gnorm < P.gradient_tolerance) { status = CORA_B200_TNT_GRADIENT; break; }  // :474-481
+    if (pgnorm < P.preconditioned_gradient_tolerance) { status = CORA_B200_TNT_PRECONDITIONED_GRADIENT; break; }
+
+    // ---------------- STPCG (IterativeSolvers.h:207-426) ----------------
+    __syncthreads();
+    if (c.tid == 0) {
+      cg.mode = CG_MODE_STEP; cg.it = 0; cg.max_it = P.max_TPCG_iterations; cg.exit_reason = CG_EXIT_NONE;
+      cg.rv = rv_cur; cg.Delta = Delta; cg.Delta2 = Delta * Delta;
+      cg.sMp = 0.0; cg.sM2 = 0.0; cg.pM2 = rv_cur; cg.sM2_next = 0.0;
+      cg.alpha = cg.beta = cg.kappa = cg.sigma = 0.0; cg.hM = 0.0;
+      cg.eps = 1e-8; cg.kappa_fgr = P.kappa_fgr; cg.theta = P.theta;
+      const double r0 = sqrt(rv_cur);
+      cg.target = r0 * fmin(P.kappa_fgr, pow(r0, P.theta));  // :278-279
+      int done = 0;
+      if (cg.max_it <= 0) { cg.exit_reason = CG_EXIT_MAXIT; done = 1; }
+      else if (r0 <= cg.target) { cg.exit_reason = CG_EXIT_TARGET; done = 1; }
+      cg.state = done;
+    }
+    __syncthreads();
+    cg_init_flat(c, v[V_GRAD], v[V_PG], v[V_S], v[V_R], v[V_P]);
+    if (L.numChunks > 0) hub_phase<D>(L, c, v[V_PG], -1.0, nullptr, 0.0, lp0);
+    grid_sync(c);
+    while (cg.state == 0) {
+      double acc[3] = {0.0, 0.0, 0.0};
+      qprod_phase<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_G], v[V_HP], nullptr, lp0, acc);
+      grid_reduce<3>(acc, c, nullptr);
+      if (c.tid == 0) cg_post_hess(&cg, acc[0], acc[1], acc[2]);
+      __syncthreads();
+      if (cg.state != 0) break;  // p in ker(H): finished below
+      if (cg.mode == CG_MODE_BOUNDARY) {  // :355-361  s += sigma p
+        axpby_flat(c, 1.0, v[V_S], cg.sigma, v[V_P], v[V_S]);
+        grid_sync(c);
+        __syncthreads();
+        if (c.tid == 0) cg.state = 1;
+        __syncthreads();
+        break;
+      }
+      double a2[2] = {0.0, 0.0};
+      const double alpha = cg.alpha;
+      axpby_flat(c, 1.0, v[V_S], alpha, v[V_P], v[V_S]);  // s += alpha p  (:374)
+      update_phase<D, true>(L, c, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
+                            A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);
+      grid_reduce<2>(a2, c, nullptr);
+      if (c.tid == 0) cg_post_update(&cg, a2[0]);
+      __syncthreads();
+      if (cg.state != 0) break;
+      const double beta = cg.beta;
+      axpby_flat(c, beta, v[V_P], -1.0, v[V_V], v[V_T1]);  // p' = -v + beta p  (:420)
+      if (L.numChunks > 0) hub_phase<D>(L, c, v[V_P], beta, v[V_V], -1.0, lp0);
+      grid_sync(c);
+      swp(V_P, V_T1);
+    }
+    double hM = cg.hM;
+    const int inner = cg.it;
+    if (cg.exit_reason == CG_EXIT_KERNEL) {  // :305-338
+      double a1[1] = {0.0};
+      dot_flat(c, v[V_P], v[V_R], a1);
+      grid_reduce<1>(a1, c, nullptr);
+      double sMp = cg.sMp, sgn = 1.0;
+      if (a1[0] < 0) { sgn = -1.0; sMp = -sMp; }
+      const double sigma = (-sMp + sqrt(sMp * sMp + cg.pM2 * (cg.Delta2 - cg.sM2))) / cg.pM2;
+      axpby_flat(c, 1.0, v[V_S], sigma * sgn, v[V_P], v[V_S]);
+      grid_sync(c);
+      hM = cg.Delta;
+    }
+    total_inner += inner;
+
+    // ------------- proposed point, model decrease (TNT.h:503-512) -------------
+    double hnorm, gh;
+    {
+      double a2[2] = {0.0, 0.0};
+      retract_phase<D>(L, c, v[V_X], v[V_S], v[V_GRAD], v[V_XP], a2);
+      grid_reduce<2>(a2, c, nullptr);
+      hnorm = sqrt(a2[0]);
+      gh = a2[1];
+    }
+    if (L.numChunks > 0) {
+      hub_phase<D>(L, c, v[V_XP], 1.0, nullptr, 0.0, lp0);
+      hub_phase<D>(L, c, v[V_S], 1.0, nullptr, 0.0, lp1);
+      grid_sync(c);
+    }
+    double fxp, gnorm_p, hHh;
+    {
+      double a6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      qprod_phase<D, QM_GRAD>(L, c, v[V_XP], nullptr, nullptr, v[V_GRADP], v[V_GP], lp0, a6);
+      qprod_phase<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_G], v[V_HP], nullptr, lp1, a6 + 3);
+      grid_reduce<6>(a6, c, nullptr);
+      fxp = 0.5 * a6[0];
+      gnorm_p = sqrt(a6[1]);
+      hHh = a6[3];
+    }
+    double rv_prop, pgnorm_p;
+    {
+      double a2[2] = {0.0, 0.0};
+      precond_project(v[V_XP], v[V_GRADP], v[V_T0], a2);
+      grid_reduce<2>(a2, c, &now);
+      rv_prop = a2[0];
+      pgnorm_p = sqrt(a2[1]);
+    }
+    const double dm = -gh - 0.5 * hHh;
+    const double df = fx - fxp;
+    const double rel = df / (sqrt_eps + fabs(fx));
+    const double rho = df / dm;
+    const bool accepted = !isnan(rho) && rho > P.eta1;  // :532
+    tr_iter(inner, hnorm, hM, rho);
+    if (accepted) {
+      swp(V_X, V_XP);
+      fx = fxp;
+      if (rel < P.relative_decrease_tolerance) {  // :561-564
+        status = CORA_B200_TNT_RELATIVE_DECREASE;
+        ++iteration;
+        break;
+      }
+      if (hnorm < P.stepsize_tolerance) {  // :567-570
+        status = CORA_B200_TNT_STEPSIZE;
+        ++iteration;
+        break;
+      }
+      swp(V_G, V_GP);
+      swp(V_GRAD, V_GRADP);
+      swp(V_PG, V_T0);
+      rv_cur = rv_prop;
+      gnorm = gnorm_p;
+      pgnorm = pgnorm_p;
+    }
+    if (!isnan(rho) && rho >= P.eta2) {  // :590-603
+      Delta = fmax(P.alpha2 * hM, Delta);
+    } else if (isnan(rho) || rho < P.eta1) {
+      Delta = P.alpha1 * hM;
+      if (Delta < P.Delta_tolerance) {
+        status = CORA_B200_TNT_TRUST_REGION;
+        ++iteration;
+        break;
+      }
+    }
+  }
+  el = (double)((master ? global_timer_ns() : now) - t0) * 1e-9;
+  tr_state(el, fx, gnorm, pgnorm, Delta);
+  if (A.prof_all != nullptr && c.tid == 0)
+#pragma unroll
+    for (int i = 0; i < PH_COUNT; ++i) A.prof_all[(size_t)c.b * PH_COUNT + i] = c.prof_ns[i];
+  if (master) {
+    TntDev *o = A.out;
+    o->f = fx; o->gnorm = gnorm; o->pgnorm = pgnorm; o->Delta = Delta; o->elapsed = el;
+    o->status = status; o->num_outer = n_iter; o->n_state = n_state;
+    o->total_inner = total_inner; o->barriers = c.nbar;
+#pragma unroll
+    for (int i = 0; i < V_COUNT; ++i) o->perm[i] = perm[i];
+#pragma unroll
+    for (int i = 0; i < PH_COUNT; ++i) { o->prof_ns[i] = c.prof_ns[i]; o->prof_cnt[i] = c.prof_cnt[i]; }
+  }
+}
+
+}  // namespace cora_b200

@@ -13,6 +13,7 @@
 
 #include "chain_chol.cuh"
 #include "ops.cuh"
+#include "persistent.cuh"
 
 namespace cora_b200 {
 
@@ -197,11 +198,201 @@ inline void swap_vec(H *h, int a, int b) {
   std::swap(h->ws[a].n, h->ws[b].n);
 }
 
+// ------------------------------------------------------- persistent TNT (host) ---
+template <int D>
+inline size_t persistent_smem(const H *h, int r, int nbuf) {
+  const int D1 = D + 1;
+  const size_t nbv = (size_t)h->DL.maxSlots * D1 * D1 * h->DL.TP;
+  const size_t ncol = ((size_t)h->DL.maxSlots * h->DL.TP + 3) & ~(size_t)3;
+  const size_t spcap = ((size_t)h->DL.maxTileSpill + 3) & ~(size_t)3;
+  const size_t pstride = (size_t)D1 * (r | 1) + ((D1 % 2 == 0) ? 1 : 0);
+  const size_t vstride = ((size_t)h->DL.TR * (r | 1) + h->DL.TP + 2 * pstride + 1) & ~(size_t)1;
+  const size_t qbuf = (nbv + spcap) * sizeof(double) + (ncol + h->DL.TRP + spcap) * sizeof(int);
+  return 80 * sizeof(double) + nbuf * qbuf + (1 + 3 * (size_t)nbuf) * vstride * sizeof(double);
+}
+
+// One cooperative launch runs the whole trust-region solve on the resident iterate.
+inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200_tnt_result *res) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  const int64_t launches0 = h->launches;
+  if (h->persistent_grid_r != r) {
+    if (const char *e = getenv("CORA_B200_PTHREADS")) h->persistent_threads = std::max(64, std::min(256, atoi(e)));
+    // double-buffered tile pipeline when two CTAs of it fit on an SM, single-buffered otherwise
+    size_t smem = 0;
+    int nbuf = 2;
+    DISPATCH_D(h, smem = persistent_smem<DD>(h, r, 2));
+    if (const char *e = getenv("CORA_B200_NBUF")) nbuf = atoi(e) == 1 ? 1 : 2;
+    if (smem > 113 * 1024 && !getenv("CORA_B200_NBUF")) nbuf = 1;
+    DISPATCH_D(h, smem = persistent_smem<DD>(h, r, nbuf));
+    if (smem > 227 * 1024)
+      throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: tile working set exceeds shared memory at this rank");
+    h->persistent_nbuf = nbuf;
+    h->persistent_smem = smem;
+    int per_sm = 0;
+    DISPATCH_D(h, {
+      CUDA_CHECK(cudaFuncSetAttribute(k_tnt_persistent<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tnt_persistent<DD>, h->persistent_threads, smem));
+    });
+    if (per_sm < 1) throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel does not fit on an SM at this rank");
+    if (const char *e = getenv("CORA_B200_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+    int G0 = std::max(1, std::min(h->sm_count * per_sm, h->DL.numTiles));
+    // every CTA caches the metadata of its tiles in shared memory: at most kMaxTilesPerCta of them
+    if ((h->DL.numTiles + G0 - 1) / G0 + 1 > kMaxTilesPerCta)
+      throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many tiles per CTA");
+    h->persistent_grid = G0;
+    h->persistent_grid_r = r;
+    {  // cost-balanced contiguous partition: scalar-row tiles (two L2 gathers per element) weigh more
+      double ws = 0.4;
+      if (const char *e = getenv("CORA_B200_SCALAR_TILE_WEIGHT")) ws = atof(e);
+      const HostLayout &HL = h->HL;
+      std::vector<double> cost(HL.numTiles);
+      double total = 0.0;
+      for (int t = 0; t < HL.numTiles; ++t) {
+        const int64_t row0 = (int64_t)t * HL.TR;
+        const int nR = (int)std::min<int64_t>(HL.TR, HL.N - row0);
+        const int nP = (int)std::max<int64_t>(0, std::min<int64_t>(HL.TP, (int64_t)HL.n - (int64_t)t * HL.TP));
+        const int nS = nR - nP * HL.D1;
+        cost[t] = 1.0 + ws * (double)nS / HL.TR;
+        total += cost[t];
+      }
+      std::vector<int> t0(G0 + 1, HL.numTiles);
+      t0[0] = 0;
+      double accum = 0.0;
+      int b = 1;
+      for (int t = 0; t < HL.numTiles && b < G0; ++t) {
+        accum += cost[t];
+        while (b < G0 && accum >= total * b / G0) t0[b++] = t + 1;
+      }
+      for (int i = 1; i <= G0; ++i) {
+        t0[i] = std::max(t0[i], t0[i - 1]);
+        if (t0[i] - t0[i - 1] > kMaxTilesPerCta) throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many tiles per CTA");
+      }
+      t0[G0] = HL.numTiles;
+      h->d_cta_t0.upload(t0, h->stream);
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    }
+  }
+  const int G = h->persistent_grid;
+  const size_t smem = h->persistent_smem;
+  const size_t npart = 2 * ((size_t)G * kPPart + 8);
+  if (h->d_ppartials.n < npart) h->d_ppartials.alloc(npart);
+  const size_t nlp = 2 * (size_t)std::max(h->DL.numChunks, 1) * h->DL.D1 * h->ws_r;
+  if (h->d_longpart.n < nlp) h->d_longpart.alloc(nlp);
+  if (!h->d_bar.p) h->d_bar.alloc(1);
+  if (!h->d_tntdev.p) {
+    h->d_tntdev.alloc(sizeof(TntDev));
+    CUDA_CHECK(cudaMallocHost(&h->h_tntdev, sizeof(TntDev)));
+  }
+  const int cap = std::max(p.max_iterations + 2, 4);
+  if (h->trace_cap < cap) {
+    h->d_trace.alloc((size_t)TR_ROWS * cap);
+    h->h_trace.resize((size_t)TR_ROWS * cap);
+    h->trace_cap = cap;
+  }
+  PArgs A{};
+  for (int i = 0; i < V_COUNT; ++i) A.v[i] = h->ws[i].p;
+  A.longpart = h->d_longpart.p;
+  A.partials = h->d_ppartials.p;
+  A.bar = h->d_bar.p;
+  A.trace = h->d_trace.p;
+  A.out = (TntDev *)h->d_tntdev.p;
+  A.p = p;
+  A.r = r;
+  A.trace_cap = h->trace_cap;
+  A.precond = h->precond;
+  A.nbuf = h->persistent_nbuf;
+  A.cta_t0 = h->d_cta_t0.p;
+  const bool phase_prof = getenv("CORA_B200_PHASE_PROFILE") != nullptr;
+  DevBuf<unsigned long long> d_prof_all;
+  if (phase_prof) { d_prof_all.alloc((size_t)G * PH_COUNT); A.prof_all = d_prof_all.p; }
+  CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  CUDA_CHECK(cudaMemsetAsync(h->d_bar.p, 0, sizeof(unsigned long long), h->stream));
+  DevLayout Lc = h->DL;
+  void *args[] = {(void *)&Lc, (void *)&A};
+  DISPATCH_D(h, CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_tnt_persistent<DD>, dim3(G), dim3(h->persistent_threads), args,
+                                                       smem, h->stream)));
+  check_launch(h);
+  CUDA_CHECK(cudaMemcpyAsync(h->h_tntdev, h->d_tntdev.p, sizeof(TntDev), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h->h_trace.data(), h->d_trace.p, (size_t)TR_ROWS * h->trace_cap * sizeof(double),
+                             cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  CUDA_CHECK(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  const TntDev &o = *(const TntDev *)h->h_tntdev;
+  {  // mirror the kernel's buffer rotation
+    double *ptr[V_COUNT];
+    size_t cnt[V_COUNT];
+    for (int i = 0; i < V_COUNT; ++i) { ptr[i] = h->ws[o.perm[i]].p; cnt[i] = h->ws[o.perm[i]].n; }
+    for (int i = 0; i < V_COUNT; ++i) { h->ws[i].p = ptr[i]; h->ws[i].n = cnt[i]; }
+  }
+  const int cap_d = h->trace_cap;
+  const double *T = h->h_trace.data();
+  const int ns = std::min(o.n_state, res->trace_capacity), ni = std::min(o.num_outer, res->trace_capacity);
+  for (int i = 0; i < ns; ++i) {
+    if (res->time) res->time[i] = T[(size_t)TR_TIME * cap_d + i];
+    if (res->objective_values) res->objective_values[i] = T[(size_t)TR_F * cap_d + i];
+    if (res->gradient_norms) res->gradient_norms[i] = T[(size_t)TR_G * cap_d + i];
+    if (res->preconditioned_gradient_norms) res->preconditioned_gradient_norms[i] = T[(size_t)TR_PG * cap_d + i];
+    if (res->trust_region_radius) res->trust_region_radius[i] = T[(size_t)TR_DELTA * cap_d + i];
+  }
+  for (int i = 0; i < ni; ++i) {
+    if (res->inner_iterations) res->inner_iterations[i] = (int32_t)T[(size_t)TR_INNER * cap_d + i];
+    if (res->update_step_norms) res->update_step_norms[i] = T[(size_t)TR_HNORM * cap_d + i];
+    if (res->update_step_M_norms) res->update_step_M_norms[i] = T[(size_t)TR_HM * cap_d + i];
+    if (res->gain_ratios) res->gain_ratios[i] = T[(size_t)TR_RHO * cap_d + i];
+  }
+  if (p.verbose) {
+    for (int i = 0; i < o.num_outer && i + 1 < cap_d; ++i)
+      std::printf("Iter: %4d, time: %.3e, f: %.8e, |g|: %.3e, |M^{-1}g|: %.3e, Delta: %.3e, inner iters: %3d, "
+                  "|h|: %.3e, |h|_M: %.3e, df: %.6e, rho: %.3e. %s\n",
+                  i, T[(size_t)TR_TIME * cap_d + i], T[(size_t)TR_F * cap_d + i], T[(size_t)TR_G * cap_d + i],
+                  T[(size_t)TR_PG * cap_d + i], T[(size_t)TR_DELTA * cap_d + i], (int)T[(size_t)TR_INNER * cap_d + i],
+                  T[(size_t)TR_HNORM * cap_d + i], T[(size_t)TR_HM * cap_d + i],
+                  T[(size_t)TR_F * cap_d + i] - T[(size_t)TR_F * cap_d + i + 1], T[(size_t)TR_RHO * cap_d + i],
+                  T[(size_t)TR_RHO * cap_d + i] > p.eta1 ? "Step accepted" : "Step REJECTED!");
+    std::printf("\n");
+  }
+  if (getenv("CORA_B200_PHASE_PROFILE")) {
+    static const char *names[PH_COUNT] = {"hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc", "q.wait", "q.qx", "q.epi", "q.store"};
+    std::printf("[persistent] grid %d, nbuf %d, smem %zu, barriers %lld, outer %d, CG %lld, device %.3f ms\n", G, h->persistent_nbuf, smem, o.barriers, o.num_outer, o.total_inner, ms);
+    for (int i = 0; i < PH_COUNT; ++i)
+      if (o.prof_cnt[i]) std::printf("  %-8s n=%6u total %9.1f us  avg %8.2f us\n", names[i], o.prof_cnt[i], o.prof_ns[i] * 1e-3, o.prof_ns[i] * 1e-3 / o.prof_cnt[i]);
+    std::vector<unsigned long long> pa((size_t)G * PH_COUNT);
+    CUDA_CHECK(cudaMemcpy(pa.data(), d_prof_all.p, pa.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < PH_COUNT; ++i) {
+      if (!o.prof_cnt[i]) continue;
+      std::vector<double> col(G);
+      for (int b = 0; b < G; ++b) col[b] = pa[(size_t)b * PH_COUNT + i] * 1e-3 / o.prof_cnt[i];
+      std::vector<double> srt(col);
+      std::sort(srt.begin(), srt.end());
+      int amax = 0;
+      for (int b = 0; b < G; ++b) if (col[b] > col[amax]) amax = b;
+      std::printf("  per-CTA avg %-8s min %7.2f  med %7.2f  p90 %7.2f  max %7.2f (cta %d)  last-cta %7.2f\n", names[i], srt[0], srt[G / 2], srt[(G * 9) / 10], srt[G - 1], amax, col[G - 1]);
+    }
+  }
+  res->f = o.f;
+  res->gradfx_norm = o.gnorm;
+  res->preconditioned_gradfx_norm = o.pgnorm;
+  res->elapsed_time = std::chrono::duration<double>(clk::now() - t0).count();
+  res->device_time = ms * 1e-3;
+  res->status = o.status;
+  res->num_outer = o.num_outer;
+  res->total_inner = o.total_inner;
+  res->kernel_launches = h->launches - launches0;
+  h->resident_r = r;
+}
+
 inline void tnt_resident(H *h, int r, const cora_b200_tnt_params &p, cora_b200_tnt_result *res) {
   check_geom_rank(r);
   if (h->precond != CORA_B200_PRECON_JACOBI && h->precond != CORA_B200_PRECON_REG_CHOLESKY)
     throw Error(CORA_B200_EINVAL, "The desired preconditioner is not implemented");
   ensure_workspace(h, r);
+  if (h->use_persistent && h->precond == CORA_B200_PRECON_JACOBI) {
+    tnt_persistent(h, r, p, res);
+    return;
+  }
   using clk = std::chrono::steady_clock;
   const auto t0 = clk::now();
   auto elapsed = [&]() { return std::chrono::duration<double>(clk::now() - t0).count(); };
