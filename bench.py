@@ -89,28 +89,65 @@ class ClockSampler:
 def build_problem():
     from cora_b200 import capi, synthetic
     w = WORKLOAD
-    arrays, _ = synthetic.make_arrays(w["n"], w["l"], w["m"], d=w["d"], seed=w["seed"])
+    arrays, gt = synthetic.make_arrays(w["n"], w["l"], w["m"], d=w["d"], seed=w["seed"])
     Q = capi.assemble(w["d"], w["n"], w["l"], arrays)
     m = len(arrays["rg_w"])
-    return arrays, Q, m
+    return arrays, gt, Q, m
 
 
-def initial_guess(arrays, seed):
-    """Odometry initialisation (examples/paper_experiments.cpp:426-534): chained odometry, random
-    landmarks, a random SO(r) right factor -- `seed` selects the restart."""
+def initial_guess(arrays, gt, seed, kind):
+    """warm: ground truth perturbed by Exp(N(0,0.05^2)) / N(0,0.5^2 m) -- the regime in which STPCG runs its
+    full iteration budget; odom: the cold start of the reference's paper experiments
+    (examples/paper_experiments.cpp:426-534); `seed` selects the restart (perturbation + SO(r) factor)."""
     from cora_b200 import synthetic
     w = WORKLOAD
-    return synthetic.odometry_initialization(w["d"], w["n"], w["l"], arrays, w["rank"], seed=seed)
+    if kind == "odom":
+        return synthetic.odometry_initialization(w["d"], w["n"], w["l"], arrays, w["rank"], seed=seed)
+    return synthetic.perturbed_ground_truth(w["d"], w["n"], w["l"], arrays, gt, w["rank"], seed=seed)
 
 
 def config_dict(args, N, nnz, m):
     w = WORKLOAD
     return {"workload": "synthetic 100k-pose SE(3) + 20k range factors (BASELINE configs[2]), rank %d" % w["rank"],
             "n_poses": w["n"], "n_landmarks": w["l"], "n_ranges": int(m), "N": int(N), "nnz": int(nnz),
-            "rank": w["rank"], "preconditioner": "Jacobi", "outer_iterations_per_step": args.outer, "untimed_startup_outer_iterations": args.pre_outer,
-            "max_TPCG_iterations": 80, "init": "odometry chain + random landmarks + random SO(r) factor (paper_experiments.cpp:426-534)", "restarts": "one restart per GPU (seed = rank)",
-            "l2": "working set of one CG iteration (Q 52 MB + 10 vectors x 16.8 MB) exceeds the 126 MB L2; "
+            "rank": w["rank"], "preconditioner": "Jacobi", "outer_iterations_per_step": args.outer,
+            "untimed_startup_outer_iterations": args.pre_outer, "max_TPCG_iterations": 80,
+            "init": {"warm": "ground truth perturbed (rotations 0.05 rad, positions 0.5 m), random SO(r) factor",
+                     "odom": "odometry chain + random landmarks + random SO(r) factor "
+                             "(paper_experiments.cpp:426-534)"}[args.init],
+            "restarts": "one restart per GPU (seed = rank)",
+            "l2": "working set of one CG iteration (Q 41 MB + 8 vectors x 16.8 MB = 175 MB) exceeds the 126 MB L2; "
                   "no explicit flush"}
+
+
+def cpu_tnt_sample(arrays, gt, Q, m, args, steps, warmup, threads, min_seconds=0.0):
+    """The CPU restatement of the reference (oracle/cpu_ref.cpp) on a bounded sample of the workload:
+    the same problem and initial guess, `ref_pre` untimed outer iterations, then steps of one TNT outer
+    iteration with at most `ref_cg` CG iterations.  Returns (CG it/s, CG iterations, seconds, threads)."""
+    from cora_b200 import capi
+    from oracle import cpu_ref
+    w = WORKLOAD
+    R = cpu_ref.CpuRef(w["d"], w["n"], m, w["n"] + w["l"], Q, preconditioner=1, threads=threads)
+    x = R.project_to_manifold(initial_guess(arrays, gt, 0, args.init))
+    pre = R.tnt(x, capi.default_tnt_params(max_iterations=args.ref_pre, max_TPCG_iterations=args.ref_cg,
+                                           max_computation_time=0.0))
+    x, delta = pre.x, pre.trust_region_radius[-1]
+    its, T = 0, 0.0
+    s = -1
+    while True:
+        s += 1
+        if s >= warmup + steps and (min_seconds <= 0 or T >= min_seconds or s >= warmup + 40):
+            break
+        prm = capi.default_tnt_params(max_iterations=1, max_TPCG_iterations=args.ref_cg, Delta0=delta,
+                                      max_computation_time=0.0)
+        t0 = time.perf_counter()
+        res = R.tnt(x, prm)
+        dt = time.perf_counter() - t0
+        x, delta = res.x, res.trust_region_radius[-1]
+        if s >= warmup:
+            its += int(sum(res.inner_iterations))
+            T += dt
+    return its / max(T, 1e-12), its, T, R.threads
 
 
 # ------------------------------------------------------------------ reference arm ---
@@ -118,41 +155,23 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cora_oracle as co
-    arrays, Q, m = build_problem()
+    arrays, gt, Q, m = build_problem()
     w = WORKLOAD
-    p = co.Problem.from_arrays(w["d"], w["n"], w["l"], arrays, rank=w["rank"], preconditioner=co.JACOBI)
-    p.Q = Q.tocsr()
-    p._update_preconditioner()
-    p.up_to_date = True
-    N = p.N
-    x = p.project_to_manifold(initial_guess(arrays, 0))
-    # bounded sample: one outer iteration with at most `ref_cg` CG iterations per step
-    prm = co.cora_tnt_params(max_iterations=1, max_TPCG_iterations=args.ref_cg)
-    # the CPU sample starts where CG iterations are counted: grow the trust region first
-    # (from a random point the first STPCG calls end on the boundary at iteration 0)
-    pre = co.problem_tnt(p, x, co.cora_tnt_params(max_iterations=args.ref_pre, max_TPCG_iterations=args.ref_cg))
-    x, prm.Delta0 = pre.x, pre.trust_region_radius[-1]
-    its, t_steps = 0, []
-    for s in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        res = co.problem_tnt(p, x, prm)
-        dt = time.perf_counter() - t0
-        x = res.x
-        prm.Delta0 = res.trust_region_radius[-1]
-        if s >= args.warmup:
-            its += int(sum(res.inner_iterations))
-            t_steps.append(dt)
-    T = sum(t_steps)
-    val = its / T
-    sample = "%d steps x (1 TNT outer iteration, <= %d CG iterations) of the same problem, NumPy/SciPy restatement" % (
-        args.steps, args.ref_cg)
+    N = w["d"] * w["n"] + m + w["n"] + w["l"]
+    threads = os.cpu_count() or 1
+    val, its, T, used = cpu_tnt_sample(arrays, gt, Q, m, args, args.steps, args.warmup, threads)
+    sample = ("%d steps x (1 TNT outer iteration, <= %d CG iterations) of the same problem after %d untimed outer "
+              "iterations; C++ restatement of the reference CPU path (oracle/cpu_ref.cpp: CSR, column-major, "
+              "per-column SpMM, reference operation counts), %d threads; %d CG iterations in %.1f s"
+              % (args.steps, args.ref_cg, args.ref_pre, used, its, T))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_dict(args, N, Q.nnz, m),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference itself cannot be built on this image (needs Eigen3 + SuiteSparse): this is the "
+                    "oracle's C++ port, kind=port"}
     print(json.dumps(line))
 
 
@@ -172,7 +191,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.barrier()
-    arrays, Q, m = build_problem()
+    arrays, gt, Q, m = build_problem()
     w = WORKLOAD
     d, n, l, r = w["d"], w["n"], w["l"], w["rank"]
     N = d * n + m + n + l
@@ -181,10 +200,9 @@ def run_ours(args):
     ab = algorithmic_bytes(Q.nnz, N, r)
     prm = capi.default_tnt_params(max_iterations=args.outer, max_computation_time=0.0)
 
-    x0 = h.project_to_manifold(initial_guess(arrays, rank))
+    x0 = h.project_to_manifold(initial_guess(arrays, gt, rank, args.init))
     pin_in = torch.empty((r, N), dtype=torch.float64).pin_memory()   # column-major N x r
     pin_out = torch.empty((r, N), dtype=torch.float64).pin_memory()
-    pin_in.numpy()[:] = x0.T
 
     def barrier():
         if world > 1:
@@ -195,17 +213,22 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        its = launches = 0
+        its = launches = outer = 0
+        prof = {}
         for _ in range(nsteps):
-            a, b = step_fn()
+            a, b, c, p = step_fn()
             its += a
             launches += b
+            outer += c
+            for k, (us, cnt) in (p or {}).items():
+                u0, c0 = prof.get(k, (0.0, 0))
+                prof[k] = (u0 + us, c0 + cnt)
         e1.record()
         barrier()
-        return e0.elapsed_time(e1) * 1e-3, its, launches
+        return e0.elapsed_time(e1) * 1e-3, its, launches, outer, prof
 
-    # ---- untimed: leave the start-up phase (STPCG ends on the trust-region boundary after 0-3
-    # iterations until the radius has grown) so that the timed steps are CG iterations ----
+    # ---- untimed: leave the start-up phase (the trust region grows from Delta0 = 5; STPCG ends on
+    # its boundary after 0-3 iterations until then) so that the timed steps are CG iterations ----
     h.set_iterate(x0)
     pre = h.tnt_resident(capi.default_tnt_params(max_iterations=args.pre_outer, max_computation_time=0.0))
     delta_warm = pre.trust_region_radius[-1]
@@ -215,6 +238,7 @@ def run_ours(args):
 
     # ---- value leg: iterate resident in HBM ----
     prm.Delta0 = delta_warm
+    dev_time = [0.0]
 
     def step_resident():
         res = h.tnt_resident(prm)
@@ -222,22 +246,18 @@ def run_ours(args):
         if res.status != "IterationLimit":        # converged inside the bench: start the slice again
             h.restore_iterate()
             prm.Delta0 = delta_warm
-        return int(sum(res.inner_iterations)), res.kernel_launches
+        dev_time[0] += res.device_time
+        prof, _, _ = h.phase_profile()
+        return int(sum(res.inner_iterations)), res.kernel_launches, len(res.inner_iterations), prof
 
     timed(step_resident, args.warmup)
     sampler = ClockSampler(local)
     sampler.start()
-    h.profile_hessvec(0)
-    T, its, launches = timed(step_resident, args.steps)
+    dev_time[0] = 0.0
+    T, its, launches, outer, prof = timed(step_resident, args.steps)
     clocks = sampler.stop()
-
-    # ---- dominant kernel, timed live with CUDA events around each launch in the CG loop ----
-    h.profile_hessvec(4096)
-    timed(step_resident, max(1, min(args.steps, 2)))
-    ms = h.profile_read()
-    h.profile_hessvec(0)
-    ms = ms[ms > 0.25 * np.median(ms)] if len(ms) else ms   # drop gated no-op launches
-    t_hess = float(np.mean(ms)) * 1e-3 if len(ms) else float("nan")
+    t_kernel = dev_time[0]   # CUDA events on the launching stream around the persistent kernel of every step
+    _, grid, _ = h.phase_profile()
 
     # ---- e2e leg: host buffers in, host buffers out, every step ----
     lib = capi.load()
@@ -255,14 +275,15 @@ def run_ours(args):
         else:
             pin_in.copy_(pin_warm)
             prm.Delta0 = delta_warm
-        return int(resC.total_inner), int(resC.kernel_launches)
+        return int(resC.total_inner), int(resC.kernel_launches), int(resC.num_outer), None
 
     prm.Delta0 = delta_warm
     timed(step_e2e, args.warmup)
-    Te, its_e, _ = timed(step_e2e, args.steps)
+    Te, its_e, _, _, _ = timed(step_e2e, args.steps)
 
     # ---- aggregate over ranks ----
     vals = torch.tensor([T, Te, float(its), float(its_e), float(launches)], dtype=torch.float64, device="cuda")
+    its_rank0, outer_rank0 = its, outer
     if world > 1:
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
@@ -274,10 +295,25 @@ def run_ours(args):
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
         else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        ach = ab["hessvec"] / t_hess / 1e9
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md) (of fallback)"
+        # algorithmic bytes of everything the kernel did in the timed steps: per CG iteration
+        # B_cgiter, per outer iteration retract 4V + f/grad product Q+3V + model Hess-vec Q+4V +
+        # preconditioned gradient 3V+8N + STPCG init 5V
+        V = 8 * N * r
+        q = 12 * Q.nnz + 4 * (N + 1)
+        b_outer = 2 * q + 19 * V + 8 * N
+        total_bytes = its_rank0 * ab["cg_iter"] + outer_rank0 * b_outer
+        ach = total_bytes / t_kernel / 1e9
+        phases = {}
+        for k, (us, cnt) in prof.items():
+            if cnt:
+                phases[k] = {"avg_us": us / cnt, "count": cnt}
+        if "hess" in phases:
+            phases["hess"]["algorithmic_bytes"] = ab["hessvec"]
+            phases["hess"]["achieved_gbs"] = ab["hessvec"] / (phases["hess"]["avg_us"] * 1e-6) / 1e9
+            phases["hess"]["frac"] = phases["hess"]["achieved_gbs"] / peak
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -287,41 +323,29 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * N * r),
                         "d2h_bytes_per_step": int(8 * N * r)},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "k_qprod<3> (fused Hessian-vector product)",
+                "roofline": {"bound": "hbm",
+                             "kernel": "k_tnt_persistent<3>: one cooperative launch per step runs the whole TNT slice "
+                                       "(%d CG iterations + %d outer iterations per launch on average)"
+                                       % (its_rank0 // max(1, args.steps), outer_rank0 // max(1, args.steps)),
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["hessvec"],
-                             "avg_launch_us": 1e6 * t_hess, "launches_timed": int(len(ms)),
-                             "traffic": None,
-                             "cg_iteration": {"algorithmic_bytes": ab["cg_iter"],
-                                              "achieved": ab["cg_iter"] * its / world / T / 1e9,
-                                              "frac": ab["cg_iter"] * its / world / T / 1e9 / peak}}}
+                             "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": total_bytes / max(1, args.steps),
+                             "avg_launch_us": 1e6 * t_kernel / max(1, args.steps), "launches_timed": args.steps,
+                             "traffic": None, "grid": grid,
+                             "timing": "CUDA events on the launching stream around every launch of the timed steps",
+                             "phases_in_kernel_globaltimer_cta0": phases}}
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(arrays, Q, m, args)
+            v, cits, cT, used = cpu_tnt_sample(arrays, gt, Q, m, args, 2, 0, os.cpu_count() or 1, min_seconds=10.0)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": used, "kind": "port",
+                "sample": "steps of (1 TNT outer iteration, <= %d CG iterations) for >= 10 s of the same problem and initial guess after "
+                          "%d untimed outer iterations; C++ restatement of the reference CPU path (oracle/cpu_ref.cpp), "
+                          "%d threads; %d CG iterations in %.1f s" % (args.ref_cg, args.ref_pre, used, cits, cT)}
         print(json.dumps(line))
     h.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def cpu_baseline(arrays, Q, m, args):
-    """The oracle (a CPU restatement of the reference, `kind: port`) on a bounded sample."""
-    from oracle import cora_oracle as co
-    w = WORKLOAD
-    p = co.Problem.from_arrays(w["d"], w["n"], w["l"], arrays, rank=w["rank"], preconditioner=co.JACOBI)
-    p.Q = Q.tocsr()
-    p._update_preconditioner()
-    p.up_to_date = True
-    x = p.project_to_manifold(initial_guess(arrays, 0))
-    pre = co.problem_tnt(p, x, co.cora_tnt_params(max_iterations=args.ref_pre, max_TPCG_iterations=args.ref_cg))
-    prm = co.cora_tnt_params(max_iterations=2, max_TPCG_iterations=args.ref_cg, Delta0=pre.trust_region_radius[-1])
-    t0 = time.perf_counter()
-    res = co.problem_tnt(p, pre.x, prm)
-    dt = time.perf_counter() - t0
-    its = int(sum(res.inner_iterations))
-    return {"value": its / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "2 TNT outer iterations (<= %d CG iterations each) of the same problem, same x0, after 14 untimed outer iterations, "
-                      "NumPy/SciPy restatement, %d CG iterations in %.1f s" % (args.ref_cg, its, dt)}
 
 
 def main():
@@ -331,10 +355,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--outer", type=int, default=5, help="TNT outer iterations per step")
-    ap.add_argument("--pre-outer", type=int, default=40,
+    ap.add_argument("--init", default="warm", choices=["warm", "odom"])
+    ap.add_argument("--pre-outer", type=int, default=12,
                     help="untimed TNT outer iterations before the first step (trust-region start-up)")
-    ap.add_argument("--ref-cg", type=int, default=20, help="CG cap per outer iteration of the CPU sample")
-    ap.add_argument("--ref-pre", type=int, default=14, help="untimed outer iterations before the CPU sample")
+    ap.add_argument("--ref-cg", type=int, default=40, help="CG cap per outer iteration of the CPU sample")
+    ap.add_argument("--ref-pre", type=int, default=8, help="untimed outer iterations before the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -120,7 +120,7 @@ SYMBOLS = [
     "cora_b200_tnt_resident", "cora_b200_spmm_resident", "cora_b200_certify", "cora_b200_saddle_escape",
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
-    "cora_b200_profile_read", "cora_b200_debug_chain_host",
+    "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile",
 ]
 
 
@@ -464,6 +464,20 @@ class Handle:
         _check(self._lib.cora_b200_profile_read(self._h, C.c_int(capacity),
                                                 ms.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n)))
         return ms[: n.value].astype(np.float64)
+
+    PHASES = ["hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc",
+              "q.wait", "q.qx", "q.epi", "q.store"]
+
+    def phase_profile(self):
+        """In-kernel phase profile of the last persistent TNT call: {phase: (total_us, count)}, grid, barriers."""
+        tot = np.zeros(16)
+        cnt = np.zeros(16, dtype=np.int64)
+        n, grid, bars = C.c_int(0), C.c_int(0), C.c_int64(0)
+        _check(self._lib.cora_b200_phase_profile(self._h, C.c_int(16), _p(tot),
+                                                 cnt.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n),
+                                                 C.byref(grid), C.byref(bars)))
+        prof = {name: (float(tot[i]), int(cnt[i])) for i, name in enumerate(self.PHASES[: n.value])}
+        return prof, grid.value, bars.value
 
     def spmm_resident(self, reps):
         ms = C.c_float()

@@ -157,6 +157,23 @@ extern "C" int cora_b200_profile_read(cora_b200_t *h, int capacity, float *ms, i
   API_END
 }
 
+extern "C" int cora_b200_phase_profile(cora_b200_t *h, int capacity, double *total_us, int64_t *count,
+                                       int *n_kinds, int *grid, int64_t *barriers) {
+  API_BEGIN
+  require(h && total_us && count && n_kinds, "NULL argument");
+  require(h->h_tntdev != nullptr, "no persistent TNT call has run on this handle");
+  const TntDev &o = *(const TntDev *)h->h_tntdev;
+  const int n = std::min(capacity, (int)PH_COUNT);
+  for (int i = 0; i < n; ++i) {
+    total_us[i] = o.prof_ns[i] * 1e-3;
+    count[i] = o.prof_cnt[i];
+  }
+  *n_kinds = n;
+  if (grid) *grid = h->persistent_grid;
+  if (barriers) *barriers = o.barriers;
+  API_END
+}
+
 extern "C" int cora_b200_certify(cora_b200_t *h, int r, const double *Y, double eta, int nx,
                                  const double *bootstrap, int bootstrap_cols, int max_iters, int *is_certified,
                                  double *theta, double *x, double *all_eigvecs, int all_eigvecs_cols_capacity,

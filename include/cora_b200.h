@@ -185,6 +185,12 @@ int cora_b200_restore_iterate(cora_b200_t *h);
  * inside STPCG): enable with max_samples > 0, read back the milliseconds of each launch */
 int cora_b200_profile_hessvec(cora_b200_t *h, int max_samples);
 int cora_b200_profile_read(cora_b200_t *h, int capacity, float *ms, int *count);
+/* in-kernel phase profile of the last persistent TNT call (CTA 0's %globaltimer): for each phase
+ * kind k < *n_kinds, total_us[k] and count[k].  Kinds, in order: hub, grad, hess, update, pupdate,
+ * retract, precond, cginit, sync, misc, q.wait, q.qx, q.epi, q.store (persistent.cuh PhaseId).
+ * *grid / *barriers: CTAs of the cooperative launch and grid barriers executed. */
+int cora_b200_phase_profile(cora_b200_t *h, int capacity, double *total_us, int64_t *count,
+                            int *n_kinds, int *grid, int64_t *barriers);
 /* timed data-matrix products on the resident iterate: reps launches of Q*X, returns
  * the CUDA-event milliseconds for all of them (roofline leg of bench.py) */
 int cora_b200_spmm_resident(cora_b200_t *h, int reps, float *ms_total);

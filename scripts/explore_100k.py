@@ -1,5 +1,5 @@
 """Exploration on the GPU box: TNT traces and staircase timing on the synthetic 100k problem.
-usage: explore_100k.py [n_poses] [precon 1|3] [outer] [mode tnt|solve] [init odom|random]"""
+usage: explore_100k.py [n_poses] [precon 1|3] [outer] [mode tnt|solve] [init odom|warm|random]"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,7 +12,7 @@ outer = int(sys.argv[3]) if len(sys.argv) > 3 else 60
 mode = sys.argv[4] if len(sys.argv) > 4 else "tnt"
 l, m, d, r = max(10, n // 10000), n // 5, 3, 5
 t0 = time.time()
-arrays, _ = synthetic.make_arrays(n, l, m, d=d, seed=42)
+arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=42)
 Q = capi.assemble(d, n, l, arrays)
 m = len(arrays["rg_w"])
 N = d * n + m + n + l
@@ -22,6 +22,7 @@ h = capi.Handle(d, n, m, n + l, Q, preconditioner=pre)
 print("handle (precon %d) in %.2fs" % (pre, time.time() - t0), flush=True)
 init = sys.argv[5] if len(sys.argv) > 5 else "odom"
 x0 = (synthetic.odometry_initialization(d, n, l, arrays, r, seed=0) if init == "odom" else
+      synthetic.perturbed_ground_truth(d, n, l, arrays, gt, r, seed=0) if init == "warm" else
       np.asfortranarray(np.random.default_rng(0).uniform(-1, 1, size=(N, r))))
 if mode == "tnt":
     x0 = h.project_to_manifold(x0)
