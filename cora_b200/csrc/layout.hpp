@@ -33,7 +33,7 @@ namespace cora_b200 {
 constexpr int kSMAX = 8;         // max block-ELL slots per pose
 constexpr int kLongGroup = 64;   // spill groups longer than this go to the hub kernel
 constexpr uint32_t kColMask = 0x3fffffffu;
-constexpr int kHubChunk = 512;   // hub-row entries per work item of the persistent kernel
+constexpr int kHubChunk = 128;   // hub-row entries per work item of the persistent kernel
 
 struct HostLayout {
   int d = 0, n = 0, m = 0, l = 0, D1 = 0;

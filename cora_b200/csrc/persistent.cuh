@@ -49,6 +49,8 @@ struct PArgs {
   TntDev *out;
   unsigned long long *prof_all;  // [G][PH_COUNT] per-CTA phase times (nullptr: off)
   const int *cta_t0;             // [G+1] cost-balanced contiguous tile ranges
+  double *lam[2];                // Lambda blocks sym(Y_i (QY)_i^T) per tile [a][b][pose] (current / proposal)
+  double *lamS[2];               // lambda_k = (QY)_k . y_k per scalar row (0 for landmark rows)
   cora_b200_tnt_params p;
   int r, trace_cap, precond, nbuf;
 };
@@ -68,6 +70,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -105,7 +110,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, unsign
 // columns, spill group pointers / entries) filled by bulk copies, and three tile-row slots of dense
 // vectors (padded layout of Geo<D>) filled by 8-byte cp.async.
 struct TileBuf {
-  double *sval, *spv, *slot[3];
+  double *sval, *spv, *slam, *slot[3];
   int *scol, *gptr;
   unsigned *spk;
   unsigned long long *mbar;
@@ -125,46 +130,61 @@ struct PCtx {
   unsigned long long target;
   double *partials;
   int parity;
-  long long nbar;
-  unsigned long long prof_ns[PH_COUNT], tph, tsub;
-  unsigned int prof_cnt[PH_COUNT];
+  int nbar;
   unsigned mpar0, mpar1;  // mbarrier phase parity per buffer
-  // shared memory
+  // shared memory (everything that lives for the whole solve is kept THERE, not in registers: the
+  // hot loops need the register file)
+  unsigned long long *prof_ns, *tph;   // [PH_COUNT], [2] written by thread 0 only
+  unsigned int *prof_cnt;
   double *sred, *sbc, *sW;
   const TileMeta *tmeta;
-  TileBuf tb0, tb1;
+  unsigned long long *mbar;  // [2]
+  int *meta;                 // [2][4]
+  // carve-up of the dynamic shared memory in doubles from `smem`: buffer k of the data-matrix slice
+  // starts at qbase + k*qstride, vector slot j of buffer k at vbase + (k*3 + j)*vstride + pstride
+  double *smem;
+  int qbase, qstride, vbase, vstride, pstride, nbv, spcap, ncol, TRP, nlam;
   __device__ __forceinline__ TileBuf pick(int buf) const {
     TileBuf B;
-    B.sval = buf ? tb1.sval : tb0.sval; B.spv = buf ? tb1.spv : tb0.spv;
-    B.slot[0] = buf ? tb1.slot[0] : tb0.slot[0]; B.slot[1] = buf ? tb1.slot[1] : tb0.slot[1];
-    B.slot[2] = buf ? tb1.slot[2] : tb0.slot[2];
-    B.scol = buf ? tb1.scol : tb0.scol; B.gptr = buf ? tb1.gptr : tb0.gptr; B.spk = buf ? tb1.spk : tb0.spk;
-    B.mbar = buf ? tb1.mbar : tb0.mbar; B.meta = buf ? tb1.meta : tb0.meta;
+    double *q = smem + qbase + (nbuf == 2 ? buf : 0) * qstride;
+    B.sval = q;
+    B.spv = q + nbv;
+    B.slam = nullptr;
+    int *qi = (int *)(q + nbv + spcap);
+    B.scol = qi;
+    B.gptr = qi + ncol;
+    B.spk = (unsigned *)(qi + ncol + TRP);
+    double *vb = smem + vbase + (nbuf == 2 ? buf : 0) * 3 * vstride + pstride;
+    B.slot[0] = vb;
+    B.slot[1] = vb + vstride;
+    B.slot[2] = vb + 2 * vstride;
+    B.mbar = mbar + buf;
+    B.meta = meta + 4 * buf;
     return B;
   }
 };
 
 __device__ __forceinline__ void ph_begin(PCtx &c) {
-  if (c.tid == 0) c.tph = global_timer_ns();
+  if (c.tid == 0) c.tph[0] = global_timer_ns();
 }
 __device__ __forceinline__ void ph_end(PCtx &c, int id) {
   if (c.tid == 0) {
     const unsigned long long t = global_timer_ns();
-    c.prof_ns[id] += t - c.tph;
+    c.prof_ns[id] += t - c.tph[0];
     c.prof_cnt[id] += 1;
-    c.tph = t;
+    c.tph[0] = t;
   }
 }
 
 __device__ __forceinline__ void sub_begin(PCtx &c) {
-  if (c.tid == 0) c.tsub = global_timer_ns();
+  if (c.tid == 0) c.tph[1] = global_timer_ns();
 }
 __device__ __forceinline__ void sub_end(PCtx &c, int id) {
   if (c.tid == 0) {
     const unsigned long long t = global_timer_ns();
-    c.prof_ns[id] += t - c.tsub;
+    c.prof_ns[id] += t - c.tph[1];
     c.prof_cnt[id] += 1;
-    c.tsub = t;
+    c.tph[1] = t;
   }
 }
 
@@ -278,7 +298,7 @@ __device__ __forceinline__ TileInfo tile_geom(const DevLayout &L, int t, int r) 
 // layout) by cp.async, and -- when NEEDQ -- the tile's data-matrix slice by TMA bulk copies.
 template <int D, bool NEEDQ, int NV>
 __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
-                                              const double *v1, const double *v2) {
+                                              const double *v1, const double *v2, const double *lam = nullptr) {
   constexpr int D1 = D + 1;
   const int r = c.r;
   const Geo<D> geo(r);
@@ -333,15 +353,15 @@ __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t
 // Top of a pipeline iteration: start tile t+1 (double buffered), then wait for tile t.
 template <int D, bool NEEDQ, int NV>
 __device__ __forceinline__ void tile_acquire(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
-                                             const double *v1, const double *v2) {
+                                             const double *v1, const double *v2, const double *lam = nullptr) {
   if (c.nbuf == 2 && t + 1 < c.t1) {
-    tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, buf ^ 1, v0, v1, v2);
+    tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, buf ^ 1, v0, v1, v2, lam);
     cp_async_wait<1>();
   } else {
     cp_async_wait<0>();
   }
   if (NEEDQ) {
-    mbar_wait(buf ? c.tb1.mbar : c.tb0.mbar, buf ? c.mpar1 : c.mpar0);
+    mbar_wait(c.mbar + buf, buf ? c.mpar1 : c.mpar0);
     if (buf) c.mpar1 ^= 1u; else c.mpar0 ^= 1u;
   }
   __syncthreads();
@@ -349,10 +369,10 @@ __device__ __forceinline__ void tile_acquire(const DevLayout &L, PCtx &c, int t,
 // Bottom: every thread is done with tile t's buffer.
 template <int D, bool NEEDQ, int NV>
 __device__ __forceinline__ void tile_release(const DevLayout &L, PCtx &c, int t, int &buf, const double *v0,
-                                             const double *v1, const double *v2) {
+                                             const double *v1, const double *v2, const double *lam = nullptr) {
   __syncthreads();
   if (c.nbuf == 2) buf ^= 1;
-  else if (t + 1 < c.t1) tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, 0, v0, v1, v2);
+  else if (t + 1 < c.t1) tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, 0, v0, v1, v2, lam);
 }
 
 // sW <- (Q X)[tile]; sX holds the tile rows of X plus one pose block of halo on either side
@@ -360,7 +380,7 @@ __device__ __forceinline__ void tile_release(const DevLayout &L, PCtx &c, int t,
 template <int D>
 __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInfo &T, const Geo<D> &geo, PCtx &c,
                                         const TileBuf &B, const double *X, const double *sX,
-                                        const double *longpart) {
+                                        const double *longpart, const double *slam, const double *lamS) {
   constexpr int D1 = D + 1;
   const int r = c.r, TP = L.TP;
   const int S = B.meta[0];
@@ -375,6 +395,11 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
     double xs0 = 0.0, xs1 = 0.0;
     if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
     if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
+    double lm[D * D];  // Lambda block of the pose (global, written by this CTA in the last GRAD phase)
+    if (slam != nullptr) {
+#pragma unroll
+      for (int i = 0; i < D * D; ++i) lm[i] = __ldcg(slam + i * TP + p);
+    }
     double acc[D1];
 #pragma unroll
     for (int a = 0; a < D1; ++a) acc[a] = 0.0;
@@ -396,6 +421,13 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
       for (int a = 0; a < D1; ++a)
 #pragma unroll
         for (int q = 0; q < D1; ++q) acc[a] = fma(bv[(a * D1 + q) * TP], x[q], acc[a]);
+    }
+    if (slam != nullptr) {  // (Q - Lambda) x: the curvature term of the Riemannian Hessian
+      const double *xp = sX + p * pstride + cc;
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int q = 0; q < D; ++q) acc[a] = fma(-lm[a * D + q], xp[q * geo.RS], acc[a]);
     }
     for (int k = k0; k < k1; ++k) {
       const unsigned pk = B.spk[k];
@@ -421,7 +453,9 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
     double xs0 = 0.0, xs1 = 0.0;
     if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
     if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
-    double acc = __ldg(L.sdiag + sidx) * sX[geo.soff(lrow, cc)];
+    double dg = __ldg(L.sdiag + sidx);
+    if (lamS != nullptr) dg -= __ldcg(lamS + sidx);
+    double acc = dg * sX[geo.soff(lrow, cc)];
     if (k0 < k1) acc = fma(B.spv[k0], xs0, acc);
     if (k0 + 1 < k1) acc = fma(B.spv[k0 + 1], xs1, acc);
     for (int k = k0 + 2; k < k1; ++k)
@@ -446,28 +480,132 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
   if (q1 > q0) __syncthreads();
 }
 
+// Riemannian epilogue over a staged tile with D threads per pose (thread (p, a) owns row a of the
+// pose block): W <- proj_Y(W - [CURV] sym(Y G^T) Dd), result written to sOut (a different buffer, so
+// that no thread overwrites a row its neighbours still read).  Row form of
+// src/CORA_problem.cpp:782-867 / StiefelProduct.cpp:38-55 / ObliqueManifold.cpp:16-27.
+// Contains block barriers: every thread of the CTA must call it.
+template <int D, bool CURV>
+__device__ __forceinline__ void tile_epilogue2(const DevLayout &L, const TileInfo &T, const Geo<D> &geo, PCtx &c,
+                                               const double *sY, const double *sG, const double *sDd, double *sW,
+                                               double *sOut, double *lam_out = nullptr, double *lamS_out = nullptr) {
+  const int r = c.r, RS = geo.RS;
+  const int nPU = T.nP * D;
+  if (CURV) {
+    for (int u = c.tid; u < nPU + T.nS; u += c.nth) {
+      if (u < nPU) {
+        const int p = u / D, a = u - p * D;
+        const int o = geo.pose_base(p);
+        const double *y = sY + o, *g = sG + o, *dd = sDd + o;
+        double Pr[D], Pc[D];  // P[a][b], P[b][a] with P = Y G^T
+#pragma unroll
+        for (int b = 0; b < D; ++b) { Pr[b] = 0.0; Pc[b] = 0.0; }
+        for (int cc = 0; cc < r; ++cc) {
+          const double ya = y[a * RS + cc], ga = g[a * RS + cc];
+#pragma unroll
+          for (int b = 0; b < D; ++b) {
+            Pr[b] = fma(ya, g[b * RS + cc], Pr[b]);
+            Pc[b] = fma(y[b * RS + cc], ga, Pc[b]);
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < D; ++b) Pr[b] = 0.5 * (Pr[b] + Pc[b]);
+        double *w = sW + o + a * RS;
+        for (int cc = 0; cc < r; ++cc) {
+          double s = w[cc];
+#pragma unroll
+          for (int b = 0; b < D; ++b) s = fma(-Pr[b], dd[b * RS + cc], s);
+          w[cc] = s;
+        }
+      } else {
+        const int lrow = T.nP * (D + 1) + (u - nPU);
+        if (T.row0 + lrow >= L.nPoseRows + L.l) {
+          const int o = geo.soff(lrow, 0);
+          oblique_curvature(sY + o, sG + o, sDd + o, sW + o, r);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int u = c.tid; u < nPU + T.nS; u += c.nth) {
+    if (u < nPU) {
+      const int p = u / D, a = u - p * D;
+      const int o = geo.pose_base(p);
+      const double *y = sY + o, *w = sW + o;
+      double Pr[D], Pc[D];  // P[a][b], P[b][a] with P = Y W^T
+#pragma unroll
+      for (int b = 0; b < D; ++b) { Pr[b] = 0.0; Pc[b] = 0.0; }
+      for (int cc = 0; cc < r; ++cc) {
+        const double ya = y[a * RS + cc], wa = w[a * RS + cc];
+#pragma unroll
+        for (int b = 0; b < D; ++b) {
+          Pr[b] = fma(ya, w[b * RS + cc], Pr[b]);
+          Pc[b] = fma(y[b * RS + cc], wa, Pc[b]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < D; ++b) Pr[b] = 0.5 * (Pr[b] + Pc[b]);
+      if (lam_out != nullptr)  // W = Q Y here: row a of Lambda_p = sym(Y_p (QY)_p^T)
+#pragma unroll
+        for (int b = 0; b < D; ++b) lam_out[(a * D + b) * L.TP + p] = Pr[b];
+      double *out = sOut + o + a * RS;
+      for (int cc = 0; cc < r; ++cc) {
+        double s = w[a * RS + cc];
+#pragma unroll
+        for (int b = 0; b < D; ++b) s = fma(-Pr[b], y[b * RS + cc], s);
+        out[cc] = s;
+      }
+    } else {
+      const int lrow = T.nP * (D + 1) + (u - nPU);
+      const int o = geo.soff(lrow, 0);
+      if (T.row0 + lrow >= L.nPoseRows + L.l) {
+        double s = 0.0;
+        for (int cc = 0; cc < r; ++cc) s = fma(sY[o + cc], sW[o + cc], s);
+        for (int cc = 0; cc < r; ++cc) sOut[o + cc] = fma(-s, sY[o + cc], sW[o + cc]);
+        if (lamS_out != nullptr) lamS_out[T.row0 + lrow - L.nPoseRows] = s;
+      } else {
+        for (int cc = 0; cc < r; ++cc) sOut[o + cc] = sW[o + cc];  // landmark rows: Euclidean
+        if (lamS_out != nullptr) lamS_out[T.row0 + lrow - L.nPoseRows] = 0.0;
+      }
+    }
+  }
+  // translation rows of the poses are Euclidean: copy them through
+  for (int p = c.tid; p < T.nP; p += c.nth) {
+    const int o = geo.pose_base(p) + D * RS;
+    for (int cc = 0; cc < r; ++cc) sOut[o + cc] = sW[o + cc];
+  }
+  __syncthreads();
+}
+
 // --------------------------------------------------------------------- phases ----
 // GRAD: out2 = Q X, out = proj_X(Q X); acc[0] += <X, QX>, acc[1] += <grad, grad>
 // HESS: out = Hess_Y[X] (G = Q Y);     acc[0] += <X, out>, acc[1] += <out, out>, acc[2] += <X, X>
 template <int D, int MODE>
 __device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const double *X, const double *Y,
-                                            const double *Gv, double *out, double *out2,
-                                            const double *longpart, double *acc) {
-  constexpr int NV = (MODE == QM_HESS) ? 3 : 1;
+                                            double *out, double *out2, const double *longpart, double *lam,
+                                            double *lamS, double *acc) {
+  // GRAD: X is the point itself (one slot), lam / lamS are WRITTEN (Lambda blocks at X)
+  // HESS: X is the tangent vector, Y the base point (two slots), lam / lamS are READ:
+  //       Hess_Y[X] = proj_Y((Q - Lambda(Y)) X)   (src/CORA_problem.cpp:822-867 with the
+  //       SymBlockDiagProduct of Y and grad F hoisted out of the CG loop: it does not depend on X)
+  constexpr int NV = (MODE == QM_HESS) ? 2 : 1;
+  const double *lam_in = (MODE == QM_HESS) ? lam : nullptr;
   const int r = c.r;
   const Geo<D> geo(r);
   ph_begin(c);
   int buf = 0;
-  if (c.t0 < c.t1) tile_prefetch<D, true, NV>(L, c, c.t0, 0, X, Y, Gv);
+  if (c.t0 < c.t1) tile_prefetch<D, true, NV>(L, c, c.t0, 0, X, Y, nullptr, lam_in);
   for (int t = c.t0; t < c.t1; ++t) {
     sub_begin(c);
-    tile_acquire<D, true, NV>(L, c, t, buf, X, Y, Gv);
+    tile_acquire<D, true, NV>(L, c, t, buf, X, Y, nullptr, lam_in);
     sub_end(c, PH_Q_WAIT);
     const TileBuf B = c.pick(buf);
     TileInfo T = tile_geom<D>(L, t, r);
     const int nE = T.nR * r;
-    const double *sX = B.slot[0], *sY = B.slot[1], *sG = B.slot[2];
-    tile_qx<D>(L, t, T, geo, c, B, X, sX, longpart);
+    const double *sX = B.slot[0], *sY = B.slot[1];
+    double *sO = B.slot[2];
+    tile_qx<D>(L, t, T, geo, c, B, X, sX, longpart, MODE == QM_HESS ? lam + (size_t)t * c.nlam : nullptr,
+               MODE == QM_HESS ? lamS : nullptr);
     sub_end(c, PH_Q_QX);
     if (MODE == QM_SPMM) {
       for (int le = c.tid; le < nE; le += c.nth) {
@@ -482,30 +620,27 @@ __device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const d
         out2[T.ebase + le] = w;
         acc[0] = fma(sX[so], w, acc[0]);
       }
-      __syncthreads();
-      tile_epilogue<D, false>(L, T, geo, sX, nullptr, nullptr, c.sW);
-      __syncthreads();
+      tile_epilogue2<D, false>(L, T, geo, c, sX, nullptr, nullptr, c.sW, sO, lam + (size_t)t * c.nlam, lamS);
       for (int le = c.tid; le < nE; le += c.nth) {
         const int lrow = le / r, cc = le - lrow * r;
-        const double w = c.sW[geo.soff(lrow, cc)];
+        const double w = sO[geo.soff(lrow, cc)];
         out[T.ebase + le] = w;
         acc[1] = fma(w, w, acc[1]);
       }
     } else {
-      tile_epilogue<D, true>(L, T, geo, sY, sG, sX, c.sW);
-      __syncthreads();
+      tile_epilogue2<D, false>(L, T, geo, c, sY, nullptr, nullptr, c.sW, sO);
       sub_end(c, PH_Q_EPI);
       for (int le = c.tid; le < nE; le += c.nth) {
         const int lrow = le / r, cc = le - lrow * r;
         const int so = geo.soff(lrow, cc);
-        const double w = c.sW[so], dd = sX[so];
+        const double w = sO[so], dd = sX[so];
         out[T.ebase + le] = w;
         acc[0] = fma(dd, w, acc[0]);
         acc[1] = fma(w, w, acc[1]);
         acc[2] = fma(dd, dd, acc[2]);
       }
     }
-    tile_release<D, true, NV>(L, c, t, buf, X, Y, Gv);
+    tile_release<D, true, NV>(L, c, t, buf, X, Y, nullptr, lam_in);
     sub_end(c, PH_Q_STORE);
   }
   ph_end(c, MODE == QM_HESS ? PH_HESS : PH_GRAD);
@@ -548,12 +683,11 @@ __device__ __forceinline__ void update_phase(const DevLayout &L, PCtx &c, const 
       sZ[so] = z;
     }
     __syncthreads();
-    tile_epilogue<D, false>(L, T, geo, sY, nullptr, nullptr, sZ);
-    __syncthreads();
+    tile_epilogue2<D, false>(L, T, geo, c, sY, nullptr, nullptr, sZ, s3);  // slot 2 is consumed: reuse as output
     for (int le = c.tid; le < nE; le += c.nth) {
       const int lrow = le / r, cc = le - lrow * r;
       const int so = geo.soff(lrow, cc);
-      const double v = sZ[so];
+      const double v = s3[so];
       V[T.ebase + le] = v;
       acc[0] = fma(sR[so], v, acc[0]);
       acc[1] = fma(v, v, acc[1]);
@@ -572,6 +706,19 @@ __device__ __forceinline__ void axpby_flat(PCtx &c, double a, const double *X, d
     double v = a * __ldcg(X + e);
     if (Y != nullptr) v = fma(bcoef, __ldcg(Y + e), v);
     out[e] = v;
+  }
+  ph_end(c, PH_PUPDATE);
+}
+
+// s += alpha p ; p' = -v + beta p   (IterativeSolvers.h:374,420) in one pass over the CTA's elements
+__device__ __forceinline__ void cg_pupdate_flat(PCtx &c, double alpha, double beta, double *S, const double *P,
+                                                const double *V, double *Pn) {
+  ph_begin(c);
+#pragma unroll 4
+  for (long long e = c.e0 + c.tid; e < c.e1; e += c.nth) {
+    const double p = __ldcg(P + e);
+    S[e] = fma(alpha, p, __ldcg(S + e));
+    Pn[e] = fma(beta, p, -__ldcg(V + e));
   }
   ph_end(c, PH_PUPDATE);
 }
@@ -653,51 +800,40 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
   __shared__ __align__(8) unsigned long long s_mbar[2];
   __shared__ int s_meta[2][4];
   __shared__ TileMeta s_tmeta[kMaxTilesPerCta];
+  __shared__ unsigned long long s_prof_ns[PH_COUNT], s_tph[2];
+  __shared__ unsigned int s_prof_cnt[PH_COUNT];
+  __shared__ double *s_v[V_COUNT];  // the work vectors by role; rotated by thread 0 (swp)
+  __shared__ int s_perm[V_COUNT];
   PCtx c;
   c.b = blockIdx.x; c.G = gridDim.x; c.tid = threadIdx.x; c.nth = blockDim.x; c.r = A.r; c.nbuf = A.nbuf;
   c.bar = A.bar; c.target = 0; c.partials = A.partials; c.parity = 0; c.nbar = 0;
-#pragma unroll
-  for (int i = 0; i < PH_COUNT; ++i) { c.prof_ns[i] = 0; c.prof_cnt[i] = 0; }
-  c.tph = 0;
+  c.prof_ns = s_prof_ns; c.prof_cnt = s_prof_cnt; c.tph = s_tph;
   c.mpar0 = c.mpar1 = 0u;
   const int r = A.r;
   {
-    // contiguous tile range of this CTA and the matching flat element range
     c.t0 = A.cta_t0[c.b];
     c.t1 = A.cta_t0[c.b + 1];
     c.e0 = (long long)c.t0 * L.TR * r;
     c.e1 = min((long long)c.t1 * L.TR, (long long)L.N) * r;
     if (c.e0 > c.e1) c.e0 = c.e1;
     const Geo<D> geo(r);
-    const size_t nbv = (size_t)L.maxSlots * D1 * D1 * L.TP;              // doubles
-    const size_t ncol = ((size_t)L.maxSlots * L.TP + 3) & ~(size_t)3;    // ints
-    const size_t spcap = ((size_t)L.maxTileSpill + 3) & ~(size_t)3;      // entries
-    const size_t pstride = (size_t)D1 * geo.RS + geo.PADP;
-    const size_t vstride = ((size_t)L.TR * geo.RS + L.TP + 2 * pstride + 1) & ~(size_t)1;
-    double *p = smem;
-    c.sred = p; p += 64;
-    c.sbc = p; p += 16;
-    auto carve_q = [&](TileBuf &B) {
-      B.sval = p; p += nbv;
-      B.spv = p; p += spcap;
-      int *q = (int *)p;
-      B.scol = q; q += ncol;
-      B.gptr = q; q += L.TRP;
-      B.spk = (unsigned *)q; q += spcap;
-      p = (double *)q;
-    };
-    carve_q(c.tb0);
-    if (c.nbuf == 2) carve_q(c.tb1); else c.tb1 = c.tb0;
-    c.tb0.mbar = &s_mbar[0]; c.tb0.meta = s_meta[0];
-    c.tb1.mbar = &s_mbar[1]; c.tb1.meta = s_meta[1];
-    c.sW = p; p += vstride;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { c.tb0.slot[j] = p + pstride; p += vstride; }
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (c.nbuf == 2) { c.tb1.slot[j] = p + pstride; p += vstride; }
-      else c.tb1.slot[j] = c.tb0.slot[j];
-    }
+    c.nbv = L.maxSlots * D1 * D1 * L.TP;              // doubles
+    c.ncol = (L.maxSlots * L.TP + 3) & ~3;            // ints
+    c.spcap = (L.maxTileSpill + 3) & ~3;              // entries
+    c.TRP = L.TRP;
+    c.pstride = D1 * geo.RS + geo.PADP;
+    c.vstride = (L.TR * geo.RS + L.TP + 2 * c.pstride + 1) & ~1;
+    c.nlam = D * D * L.TP;
+    c.qstride = c.nbv + c.spcap + (c.ncol + c.TRP + c.spcap) / 2;  // doubles (int regions are multiples of 4)
+    c.smem = smem;
+    c.sred = smem;
+    c.sbc = smem + 64;
+    c.qbase = 80;
+    const int after_q = c.qbase + c.nbuf * c.qstride;
+    c.sW = smem + after_q;
+    c.vbase = after_q + c.vstride;
+    c.mbar = s_mbar;
+    c.meta = &s_meta[0][0];
     c.tmeta = s_tmeta;
     for (int i = c.tid; i < c.t1 - c.t0; i += c.nth) {
       const int t = c.t0 + i;
@@ -707,24 +843,30 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
       M.lq0 = L.tile_long_ptr[t]; M.lq1 = L.tile_long_ptr[t + 1];
       s_tmeta[i] = M;
     }
+    if (c.tid < PH_COUNT) { s_prof_ns[c.tid] = 0; s_prof_cnt[c.tid] = 0; }
+    if (c.tid < V_COUNT) { s_v[c.tid] = A.v[c.tid]; s_perm[c.tid] = c.tid; }
     if (c.tid == 0) {
+      s_tph[0] = s_tph[1] = 0;
       mbar_init(&s_mbar[0], 1);
       mbar_init(&s_mbar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
   }
-  double *v[V_COUNT];
-  int perm[V_COUNT];
-#pragma unroll
-  for (int i = 0; i < V_COUNT; ++i) { v[i] = A.v[i]; perm[i] = i; }
+  double *const *v = s_v;
+  // rotate two roles; callers guarantee that every thread is past its last use of the old pointers
   auto swp = [&](int a, int b2) {
-    double *tp = v[a]; v[a] = v[b2]; v[b2] = tp;
-    const int ti = perm[a]; perm[a] = perm[b2]; perm[b2] = ti;
+    __syncthreads();
+    if (c.tid == 0) {
+      double *tp = s_v[a]; s_v[a] = s_v[b2]; s_v[b2] = tp;
+      const int ti = s_perm[a]; s_perm[a] = s_perm[b2]; s_perm[b2] = ti;
+    }
+    __syncthreads();
   };
   const cora_b200_tnt_params &P = A.p;
   const size_t lpstride = (size_t)max(L.numChunks, 1) * D1 * r;
   double *lp0 = A.longpart, *lp1 = A.longpart + lpstride;
+  double *lamc = A.lam[0], *lamp = A.lam[1], *lamSc = A.lamS[0], *lamSp = A.lamS[1];
   const bool master = (c.b == 0 && c.tid == 0);
   const double sqrt_eps = 1.4901161193847656e-08;
   unsigned long long now = 0, t0 = 0;
@@ -754,6 +896,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
                            A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, acc2);
   };
 
+  if (A.prof_all != nullptr) {  // barrier latency calibration (profiling runs only)
+    for (int i = 0; i < 16; ++i) grid_sync(c);
+    if (c.tid == 0) { s_prof_ns[PH_MISC] = s_prof_ns[PH_SYNC]; s_prof_cnt[PH_MISC] = s_prof_cnt[PH_SYNC]; s_prof_ns[PH_SYNC] = 0; s_prof_cnt[PH_SYNC] = 0; }
+    __syncthreads();
+  }
   // ---- TNT.h:372-392: f(x), QM(x), gradient norms ----
   if (L.numChunks > 0) {
     hub_phase<D>(L, c, v[V_X], 1.0, nullptr, 0.0, lp0);
@@ -762,7 +909,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
   double fx, gnorm, pgnorm, rv_cur;
   {
     double acc[3] = {0.0, 0.0, 0.0};
-    qprod_phase<D, QM_GRAD>(L, c, v[V_X], nullptr, nullptr, v[V_GRAD], v[V_G], lp0, acc);
+    qprod_phase<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
     grid_reduce<3>(acc, c, &t0);
     fx = 0.5 * acc[0];
     gnorm = sqrt(acc[1]);
@@ -808,7 +955,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
     grid_sync(c);
     while (cg.state == 0) {
       double acc[3] = {0.0, 0.0, 0.0};
-      qprod_phase<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_G], v[V_HP], nullptr, lp0, acc);
+      qprod_phase<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
       grid_reduce<3>(acc, c, nullptr);
       if (c.tid == 0) cg_post_hess(&cg, acc[0], acc[1], acc[2]);
       __syncthreads();
@@ -823,15 +970,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
       }
       double a2[2] = {0.0, 0.0};
       const double alpha = cg.alpha;
-      axpby_flat(c, 1.0, v[V_S], alpha, v[V_P], v[V_S]);  // s += alpha p  (:374)
       update_phase<D, true>(L, c, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
                             A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);
       grid_reduce<2>(a2, c, nullptr);
       if (c.tid == 0) cg_post_update(&cg, a2[0]);
       __syncthreads();
-      if (cg.state != 0) break;
+      if (cg.state != 0) {
+        // s += alpha p of the last iteration (:374); s is read next by this CTA only (retraction)
+        axpby_flat(c, 1.0, v[V_S], alpha, v[V_P], v[V_S]);
+        break;
+      }
       const double beta = cg.beta;
-      axpby_flat(c, beta, v[V_P], -1.0, v[V_V], v[V_T1]);  // p' = -v + beta p  (:420)
+      cg_pupdate_flat(c, alpha, beta, v[V_S], v[V_P], v[V_V], v[V_T1]);  // s += alpha p ; p' = -v + beta p
       if (L.numChunks > 0) hub_phase<D>(L, c, v[V_P], beta, v[V_V], -1.0, lp0);
       grid_sync(c);
       swp(V_P, V_T1);
@@ -868,8 +1018,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
     double fxp, gnorm_p, hHh;
     {
       double a6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      qprod_phase<D, QM_GRAD>(L, c, v[V_XP], nullptr, nullptr, v[V_GRADP], v[V_GP], lp0, a6);
-      qprod_phase<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_G], v[V_HP], nullptr, lp1, a6 + 3);
+      qprod_phase<D, QM_GRAD>(L, c, v[V_XP], nullptr, v[V_GRADP], v[V_GP], lp0, lamp, lamSp, a6);
+      qprod_phase<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_HP], nullptr, lp1, lamc, lamSc, a6 + 3);
       grid_reduce<6>(a6, c, nullptr);
       fxp = 0.5 * a6[0];
       gnorm_p = sqrt(a6[1]);
@@ -904,6 +1054,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
       }
       swp(V_G, V_GP);
       swp(V_GRAD, V_GRADP);
+      { double *tq = lamc; lamc = lamp; lamp = tq; tq = lamSc; lamSc = lamSp; lamSp = tq; }
       swp(V_PG, V_T0);
       rv_cur = rv_prop;
       gnorm = gnorm_p;
@@ -924,16 +1075,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
   tr_state(el, fx, gnorm, pgnorm, Delta);
   if (A.prof_all != nullptr && c.tid == 0)
 #pragma unroll
-    for (int i = 0; i < PH_COUNT; ++i) A.prof_all[(size_t)c.b * PH_COUNT + i] = c.prof_ns[i];
+    for (int i = 0; i < PH_COUNT; ++i) A.prof_all[(size_t)c.b * PH_COUNT + i] = s_prof_ns[i];
   if (master) {
     TntDev *o = A.out;
     o->f = fx; o->gnorm = gnorm; o->pgnorm = pgnorm; o->Delta = Delta; o->elapsed = el;
     o->status = status; o->num_outer = n_iter; o->n_state = n_state;
-    o->total_inner = total_inner; o->barriers = c.nbar;
+    o->total_inner = total_inner; o->barriers = (long long)c.nbar;
 #pragma unroll
-    for (int i = 0; i < V_COUNT; ++i) o->perm[i] = perm[i];
+    for (int i = 0; i < V_COUNT; ++i) o->perm[i] = s_perm[i];
 #pragma unroll
-    for (int i = 0; i < PH_COUNT; ++i) { o->prof_ns[i] = c.prof_ns[i]; o->prof_cnt[i] = c.prof_cnt[i]; }
+    for (int i = 0; i < PH_COUNT; ++i) { o->prof_ns[i] = s_prof_ns[i]; o->prof_cnt[i] = s_prof_cnt[i]; }
   }
 }
 

@@ -280,6 +280,11 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   const size_t nlp = 2 * (size_t)std::max(h->DL.numChunks, 1) * h->DL.D1 * h->ws_r;
   if (h->d_longpart.n < nlp) h->d_longpart.alloc(nlp);
   if (!h->d_bar.p) h->d_bar.alloc(1);
+  {
+    const size_t nl = (size_t)h->DL.numTiles * h->DL.d * h->DL.d * h->DL.TP, ns = (size_t)h->DL.l + h->DL.m + 1;
+    if (h->d_lamT.n < 2 * nl) h->d_lamT.alloc(2 * nl);
+    if (h->d_lamS.n < 2 * ns) h->d_lamS.alloc(2 * ns);
+  }
   if (!h->d_tntdev.p) {
     h->d_tntdev.alloc(sizeof(TntDev));
     CUDA_CHECK(cudaMallocHost(&h->h_tntdev, sizeof(TntDev)));
@@ -303,6 +308,8 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   A.precond = h->precond;
   A.nbuf = h->persistent_nbuf;
   A.cta_t0 = h->d_cta_t0.p;
+  A.lam[0] = h->d_lamT.p; A.lam[1] = h->d_lamT.p + h->d_lamT.n / 2;
+  A.lamS[0] = h->d_lamS.p; A.lamS[1] = h->d_lamS.p + h->d_lamS.n / 2;
   const bool phase_prof = getenv("CORA_B200_PHASE_PROFILE") != nullptr;
   DevBuf<unsigned long long> d_prof_all;
   if (phase_prof) { d_prof_all.alloc((size_t)G * PH_COUNT); A.prof_all = d_prof_all.p; }
