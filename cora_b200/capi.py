@@ -466,14 +466,14 @@ class Handle:
         return ms[: n.value].astype(np.float64)
 
     PHASES = ["hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc",
-              "q.wait", "q.qx", "q.epi", "q.store"]
+              "q.wait", "q.qx", "q.epi", "q.store", "ch.pre", "ch.fwd", "ch.bwd", "ch.border", "ch.post"]
 
     def phase_profile(self):
         """In-kernel phase profile of the last persistent TNT call: {phase: (total_us, count)}, grid, barriers."""
-        tot = np.zeros(16)
-        cnt = np.zeros(16, dtype=np.int64)
+        tot = np.zeros(24)
+        cnt = np.zeros(24, dtype=np.int64)
         n, grid, bars = C.c_int(0), C.c_int(0), C.c_int64(0)
-        _check(self._lib.cora_b200_phase_profile(self._h, C.c_int(16), _p(tot),
+        _check(self._lib.cora_b200_phase_profile(self._h, C.c_int(24), _p(tot),
                                                  cnt.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(n),
                                                  C.byref(grid), C.byref(bars)))
         prof = {name: (float(tot[i]), int(cnt[i])) for i, name in enumerate(self.PHASES[: n.value])}

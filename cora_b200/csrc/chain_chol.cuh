@@ -30,8 +30,19 @@
 
 namespace cora_b200 {
 
-constexpr int kChunk = 16;   // chain blocks per chunk (15 interior + 1 separator)
-constexpr int kTopMax = 32;  // a level with at most this many blocks is solved by one thread per column
+// prefetch one cache line into L2 (device only): the per-chunk substitutions are serial chains of
+// small block steps whose coefficients stream from HBM; requesting step j+1 while step j computes
+// turns a DRAM round trip per step into an L2 hit
+CB_HD void chain_prefetch(const double *p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
+constexpr int kChunk = 8;    // chain blocks per chunk (7 interior + 1 separator): the substitutions are serial per chunk, so the chunk length times the number of levels is the latency of one apply
+constexpr int kTopMax = 8;   // a level with at most this many blocks is solved by one thread per column
 
 // ----------------------------------------------------------- B x B block helpers ---
 template <int B>
@@ -216,6 +227,8 @@ CB_HD void forward_chunk(const ChunkGeo G, int k, int col, int ld, const double 
     }
     if (j == L) break;
     const double *f = fwd + (size_t)j * 3 * BB * K + k;
+    if (j + 1 < L)
+      for (int e = 0; e < 3 * BB; ++e) chain_prefetch(f + (size_t)(3 * BB + e) * K);
     double y[B];
     for (int a = 0; a < B; ++a) {
       double s = b[a];
@@ -260,6 +273,8 @@ CB_HD void backward_chunk(const ChunkGeo G, int k, int col, int ld, const double
   for (int j = L - 1; j >= 0; --j) {
     const int g = g0 + j;
     const double *f = bwd + (size_t)j * 2 * BB * K + k;
+    if (j > 0)
+      for (int e = 0; e < 2 * BB; ++e) chain_prefetch(f - (size_t)(2 * BB - e) * K);
     double x[B];
     for (int a = 0; a < B; ++a) {
       double s = sol[((size_t)g * B + a) * ld + col];

@@ -13,7 +13,7 @@
 
 #include "chain_chol.cuh"
 #include "ops.cuh"
-#include "persistent.cuh"
+#include "persistent_kernel.cuh"
 
 namespace cora_b200 {
 
@@ -308,6 +308,27 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   A.precond = h->precond;
   A.nbuf = h->persistent_nbuf;
   A.cta_t0 = h->d_cta_t0.p;
+  if (h->precond == CORA_B200_PRECON_REG_CHOLESKY) {
+    ChainChol *C = h->chol;
+    if (!C) throw Error(CORA_B200_ERUNTIME, "RegularizedCholesky factor missing");
+    chain_ensure_ws(h, C, r);
+    ChainDev &cd = A.chain;
+    cd.nl = (int)C->levels.size();
+    if (cd.nl > kMaxChainLevels) throw Error(CORA_B200_ERUNTIME, "chain factor has too many levels");
+    cd.n = C->host.n; cd.l = C->host.l; cd.m = C->host.m;
+    cd.pinned_pose_row = C->host.pinned_pose_row; cd.pinned_landmark = C->host.pinned_landmark;
+    for (int lv = 0; lv < cd.nl; ++lv) {
+      ChainLevelDev *Dv = C->levels[lv];
+      cd.G[lv] = Dv->G; cd.fwd[lv] = Dv->fwd.p; cd.bwd[lv] = Dv->bwd.p; cd.UR[lv] = Dv->UR.p;
+      cd.sol[lv] = Dv->sol.p; cd.rhs[lv] = Dv->rhs.p; cd.cL[lv] = Dv->cL.p; cd.cR[lv] = Dv->cR.p;
+    }
+    cd.rinc_ptr = C->rinc_ptr.p; cd.rinc_k = C->rinc_k.p; cd.rend_x = C->rend_x.p; cd.bl_ptr = C->bl_ptr.p;
+    cd.bl_row = C->bl_row.p; cd.rinc_e = C->rinc_e.p; cd.rdinv = C->rdinv.p; cd.rend_e = C->rend_e.p;
+    cd.bl_val = C->bl_val.p; cd.W = C->W.p; cd.SLinv = C->SLinv.p; cd.u = C->u.p; cd.Y = C->Y.p;
+    const size_t vstride = ((size_t)h->DL.TR * (r | 1) + h->DL.TP) & ~(size_t)1;
+    if ((size_t)cd.l * r > 6 * vstride)
+      throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many landmarks for the shared-memory border solve");
+  }
   A.lam[0] = h->d_lamT.p; A.lam[1] = h->d_lamT.p + h->d_lamT.n / 2;
   A.lamS[0] = h->d_lamS.p; A.lamS[1] = h->d_lamS.p + h->d_lamS.n / 2;
   const bool phase_prof = getenv("CORA_B200_PHASE_PROFILE") != nullptr;
@@ -362,7 +383,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
     std::printf("\n");
   }
   if (getenv("CORA_B200_PHASE_PROFILE")) {
-    static const char *names[PH_COUNT] = {"hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc", "q.wait", "q.qx", "q.epi", "q.store"};
+    static const char *names[PH_COUNT] = {"hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc", "q.wait", "q.qx", "q.epi", "q.store", "ch.pre", "ch.fwd", "ch.bwd", "ch.border", "ch.post"};
     std::printf("[persistent] grid %d, nbuf %d, smem %zu, barriers %lld, outer %d, CG %lld, device %.3f ms\n", G, h->persistent_nbuf, smem, o.barriers, o.num_outer, o.total_inner, ms);
     for (int i = 0; i < PH_COUNT; ++i)
       if (o.prof_cnt[i]) std::printf("  %-8s n=%6u total %9.1f us  avg %8.2f us\n", names[i], o.prof_cnt[i], o.prof_ns[i] * 1e-3, o.prof_ns[i] * 1e-3 / o.prof_cnt[i]);
@@ -396,7 +417,7 @@ inline void tnt_resident(H *h, int r, const cora_b200_tnt_params &p, cora_b200_t
   if (h->precond != CORA_B200_PRECON_JACOBI && h->precond != CORA_B200_PRECON_REG_CHOLESKY)
     throw Error(CORA_B200_EINVAL, "The desired preconditioner is not implemented");
   ensure_workspace(h, r);
-  if (h->use_persistent && h->precond == CORA_B200_PRECON_JACOBI) {
+  if (h->use_persistent && (h->precond == CORA_B200_PRECON_JACOBI || h->precond == CORA_B200_PRECON_REG_CHOLESKY)) {
     tnt_persistent(h, r, p, res);
     return;
   }

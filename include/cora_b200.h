@@ -187,7 +187,8 @@ int cora_b200_profile_hessvec(cora_b200_t *h, int max_samples);
 int cora_b200_profile_read(cora_b200_t *h, int capacity, float *ms, int *count);
 /* in-kernel phase profile of the last persistent TNT call (CTA 0's %globaltimer): for each phase
  * kind k < *n_kinds, total_us[k] and count[k].  Kinds, in order: hub, grad, hess, update, pupdate,
- * retract, precond, cginit, sync, misc, q.wait, q.qx, q.epi, q.store (persistent.cuh PhaseId).
+ * retract, precond, cginit, sync, misc, q.wait, q.qx, q.epi, q.store, ch.pre, ch.fwd, ch.bwd,
+ * ch.border, ch.post (persistent.cuh PhaseId).
  * *grid / *barriers: CTAs of the cooperative launch and grid barriers executed. */
 int cora_b200_phase_profile(cora_b200_t *h, int capacity, double *total_us, int64_t *count,
                             int *n_kinds, int *grid, int64_t *barriers);
