@@ -281,6 +281,20 @@ def run_ours(args):
     timed(step_e2e, args.warmup)
     Te, its_e, _, _, _ = timed(step_e2e, args.steps)
 
+    # ---- the only exchange of the multi-GPU path: gather the best restart (outside the timed region) ----
+    gather = None
+    if world > 1:
+        from cora_b200 import restarts
+        xr = np.ascontiguousarray(pin_out.numpy().T)           # N x r, this rank's iterate after the e2e leg
+        comm = restarts.make_native_comm(dist, local)
+        barrier()
+        tg = time.perf_counter()
+        win, wf, _ = restarts.gather_best(dist, float(resC.f), False, xr, handle=h, comm=comm)
+        torch.cuda.synchronize()
+        gather = {"winner_rank": int(win), "winner_f": float(wf), "ms": 1e3 * (time.perf_counter() - tg),
+                  "bytes_broadcast": int(8 * N * r), "transport": "ncclAllGather + ncclBroadcast (library communicator)"}
+        comm.close()
+
     # ---- aggregate over ranks ----
     vals = torch.tensor([T, Te, float(its), float(its_e), float(launches)], dtype=torch.float64, device="cuda")
     its_rank0, outer_rank0 = its, outer
@@ -322,7 +336,7 @@ def run_ours(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * N * r),
                         "d2h_bytes_per_step": int(8 * N * r)},
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches), "gather_best": gather,
                 "roofline": {"bound": "hbm",
                              "kernel": "k_tnt_persistent<3>: one cooperative launch per step runs the whole TNT slice "
                                        "(%d CG iterations + %d outer iterations per launch on average)"

@@ -121,6 +121,7 @@ SYMBOLS = [
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
     "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile",
+    "cora_b200_select_best", "cora_b200_nccl_unique_id", "cora_b200_nccl_init", "cora_b200_nccl_destroy",
 ]
 
 
@@ -149,6 +150,35 @@ def _check(code):
     if code == ENOTIMPL:
         raise NotImplementedInReference(code, msg)
     raise CoraB200Error(code, msg)
+
+
+def select_best(f, certified) -> int:
+    """The winner rule of cora_b200_gather_best (pure host function)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    c = np.ascontiguousarray(certified, dtype=np.int32)
+    w = C.c_int(0)
+    _check(load().cora_b200_select_best(C.c_int(len(f)), _p(f), c.ctypes.data_as(C.POINTER(C.c_int)), C.byref(w)))
+    return w.value
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load().cora_b200_nccl_unique_id(buf))
+    return buf.raw
+
+
+class NcclComm:
+    """ncclComm_t created from a unique id (cora_b200_nccl_init)."""
+
+    def __init__(self, device, world_size, rank, unique_id: bytes):
+        self._c = C.c_void_p()
+        _check(load().cora_b200_nccl_init(C.byref(self._c), C.c_int(device), C.c_int(world_size), C.c_int(rank),
+                                          C.c_char_p(unique_id)))
+
+    def close(self):
+        if self._c:
+            load().cora_b200_nccl_destroy(self._c)
+            self._c = C.c_void_p()
 
 
 def device_count() -> int:
@@ -516,6 +546,15 @@ class Handle:
         out = np.empty((self.N, self.d), order="F")
         _check(self._lib.cora_b200_project_solution(self._h, Y.shape[1], _p(Y), _p(out)))
         return out
+
+    def gather_best(self, comm: "NcclComm", world_size, rank, f, certified, X):
+        """All ranks call this with their own (f, certified, X [N x r_max]); returns (winner_rank, winner_f, X_winner)."""
+        X = np.array(self._mat(X), order="F", copy=True)
+        w, wf = C.c_int(0), C.c_double(0)
+        _check(self._lib.cora_b200_gather_best(comm._c, self._h, C.c_int(world_size), C.c_int(rank),
+                                               C.c_int(X.shape[1]), C.c_double(f), C.c_int(int(certified)), _p(X),
+                                               C.byref(w), C.byref(wf)))
+        return w.value, wf.value, X
 
     def solve(self, X0, max_rank=20, params: Optional[TntParams] = None, verbose=False):
         X0 = self._mat(X0)

@@ -1,9 +1,125 @@
-// capi_dist.cu -- multi-GPU helper (NCCL): gather the best certified solution.
+// capi_dist.cu -- multi-GPU helper: independent restarts / staircase ranks run one per
+// GPU with NO collective on the data path; the only exchange is the final gather of the best
+// certified solution: ncclAllGather of a {f, certified} record, arg-min on every rank, ncclBroadcast
+// of the winner's iterate over NVLink/NVSwitch.  NCCL is resolved with dlopen at first use (the
+// library has no link-time dependency on it: CPU-only hosts load libcora_b200.so without NCCL).
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "ops.cuh"
 
 using namespace cora_b200;
 
-extern "C" int cora_b200_gather_best(void *, cora_b200_t *, int, int, int, double, int, double *, int *, double *) {
-  set_last_error("gather_best not implemented yet");
-  return CORA_B200_ENOTIMPL;
+namespace {
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi &nccl() {
+  static NcclApi api;
+  if (api.lib) return api;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) {
+    api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) throw Error(CORA_B200_ERUNTIME, std::string("cannot load NCCL (libnccl.so.2): ") + dlerror());
+  auto sym = [&](const char *s) {
+    void *p = dlsym(api.lib, s);
+    if (!p) throw Error(CORA_B200_ERUNTIME, std::string("NCCL symbol missing: ") + s);
+    return p;
+  };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+  api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  return api;
+}
+void nccl_check(ncclResult_t r, const char *what) {
+  if (r != ncclSuccess) throw Error(CORA_B200_ERUNTIME, std::string(what) + ": " + nccl().GetErrorString(r));
+}
+}  // namespace
+
+// arg-min of f over the certified ranks, over all ranks when none is certified (ties: lowest rank)
+extern "C" int cora_b200_select_best(int world_size, const double *f, const int *certified, int *winner) {
+  API_BEGIN
+  require(world_size > 0 && f && certified && winner, "bad argument");
+  int best = -1;
+  bool any = false;
+  for (int i = 0; i < world_size; ++i) any = any || certified[i] != 0;
+  for (int i = 0; i < world_size; ++i) {
+    if (any && !certified[i]) continue;
+    if (f[i] != f[i]) continue;  // NaN never wins
+    if (best < 0 || f[i] < f[best]) best = i;
+  }
+  *winner = best < 0 ? 0 : best;
+  API_END
+}
+
+extern "C" int cora_b200_nccl_unique_id(void *id128) {
+  API_BEGIN
+  require(id128 != nullptr, "NULL id buffer");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  nccl_check(nccl().GetUniqueId((ncclUniqueId *)id128), "ncclGetUniqueId");
+  API_END
+}
+
+extern "C" int cora_b200_nccl_init(void **comm, int device, int world_size, int rank, const void *id128) {
+  API_BEGIN
+  require(comm && id128 && world_size > 0 && rank >= 0 && rank < world_size, "bad argument");
+  CUDA_CHECK(cudaSetDevice(device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  ncclComm_t c = nullptr;
+  nccl_check(nccl().CommInitRank(&c, world_size, id, rank), "ncclCommInitRank");
+  *comm = (void *)c;
+  API_END
+}
+
+extern "C" int cora_b200_nccl_destroy(void *comm) {
+  API_BEGIN
+  if (comm) nccl_check(nccl().CommDestroy((ncclComm_t)comm), "ncclCommDestroy");
+  API_END
+}
+
+extern "C" int cora_b200_gather_best(void *nccl_comm, cora_b200_t *h, int world_size, int my_rank, int r_max,
+                                     double f, int certified, double *X_inout, int *winner_rank, double *winner_f) {
+  API_BEGIN
+  require(nccl_comm && h && X_inout && winner_rank, "NULL argument");
+  require(world_size > 0 && my_rank >= 0 && my_rank < world_size && r_max > 0, "bad argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  ensure_workspace(h, r_max);
+  ncclComm_t comm = (ncclComm_t)nccl_comm;
+  const size_t nE = (size_t)h->DL.N * r_max;
+  DevBuf<double> rec;
+  rec.alloc(2 * (size_t)world_size + 2);
+  double mine[2] = {f, certified ? 1.0 : 0.0};
+  CUDA_CHECK(cudaMemcpyAsync(rec.p + 2 * world_size, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  nccl_check(nccl().AllGather(rec.p + 2 * world_size, rec.p, 2, ncclDouble, comm, h->stream), "ncclAllGather");
+  std::vector<double> all(2 * (size_t)world_size);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), rec.p, all.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  std::vector<double> fs(world_size);
+  std::vector<int> cs(world_size);
+  for (int i = 0; i < world_size; ++i) { fs[i] = all[2 * i]; cs[i] = all[2 * i + 1] != 0.0; }
+  int win = 0;
+  if (cora_b200_select_best(world_size, fs.data(), cs.data(), &win) != CORA_B200_OK)
+    throw Error(CORA_B200_ERUNTIME, cora_b200_last_error());
+  // the winner's iterate (reference layout, N x r_max column-major, zero padded by the caller)
+  if (my_rank == win)
+    CUDA_CHECK(cudaMemcpyAsync(h->d_stage.p, X_inout, nE * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  nccl_check(nccl().Broadcast(h->d_stage.p, h->d_stage.p, nE, ncclDouble, win, comm, h->stream), "ncclBroadcast");
+  if (my_rank != win)
+    CUDA_CHECK(cudaMemcpyAsync(X_inout, h->d_stage.p, nE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  *winner_rank = win;
+  if (winner_f) *winner_f = fs[win];
+  API_END
 }

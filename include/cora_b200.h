@@ -256,6 +256,15 @@ int cora_b200_solve(cora_b200_t *h, int r0, const double *X0, int max_rank,
 int cora_b200_gather_best(void *nccl_comm, cora_b200_t *h, int world_size, int my_rank,
                           int r_max, double f, int certified, double *X_inout,
                           int *winner_rank, double *winner_f);
+/* the selection rule of gather_best as a pure host function (CPU-testable): arg-min of f over the
+ * certified ranks, over all ranks when none is certified; ties go to the lowest rank */
+int cora_b200_select_best(int world_size, const double *f, const int *certified, int *winner);
+/* NCCL communicator plumbing (libnccl is dlopen-ed at first use): rank 0 creates the 128-byte
+ * unique id and ships it to the other ranks by any out-of-band channel; every rank then calls
+ * cora_b200_nccl_init with its CUDA device. */
+int cora_b200_nccl_unique_id(void *id128);
+int cora_b200_nccl_init(void **comm, int device, int world_size, int rank, const void *id128);
+int cora_b200_nccl_destroy(void *comm);
 
 /* ---- host-side assembly of the data matrix: Problem::fillDataMatrix and friends
  * (src/CORA_problem.cpp:115-377, 625-712) from the flattened measurement stacks, in
