@@ -96,12 +96,16 @@ extern "C" int cora_b200_spmm_resident(cora_b200_t *h, int reps, float *ms_total
   require(h->resident_r > 0, "no resident iterate: call cora_b200_set_iterate first");
   CUDA_CHECK(cudaSetDevice(h->device));
   const int r = h->resident_r;
-  CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-  for (int i = 0; i < reps; ++i)
-    launch_qprod(h, QM_SPMM, h->ws[V_X].p, nullptr, nullptr, h->ws[V_G].p, nullptr, r, POST_STORE, SC_TMP, nullptr);
-  CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
-  CUDA_CHECK(cudaEventSynchronize(h->ev1));
-  CUDA_CHECK(cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
+  if (h->use_persistent) {
+    *ms_total = spmm_persistent(h, r, h->ws[V_X].p, h->ws[V_G].p, reps);
+  } else {
+    CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < reps; ++i)
+      launch_qprod(h, QM_SPMM, h->ws[V_X].p, nullptr, nullptr, h->ws[V_G].p, nullptr, r, POST_STORE, SC_TMP, nullptr);
+    CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+    CUDA_CHECK(cudaEventSynchronize(h->ev1));
+    CUDA_CHECK(cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
+  }
   API_END
 }
 

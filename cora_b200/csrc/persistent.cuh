@@ -279,6 +279,17 @@ __device__ __forceinline__ TileInfo tile_geom(const DevLayout &L, int t, int r) 
   return T;
 }
 
+// metadata of tile t: cached in shared memory for the CTA's first kMaxTilesPerCta tiles, read from
+// global memory beyond that (very large problems: 1M poses = 74 tiles per CTA)
+__device__ __forceinline__ TileMeta tile_meta(const DevLayout &L, const PCtx &c, int t) {
+  if (t - c.t0 < kMaxTilesPerCta) return c.tmeta[t - c.t0];
+  TileMeta M;
+  M.boff = __ldg(L.tile_boff + t); M.coff = __ldg(L.tile_coff + t); M.spoff = __ldg(L.tile_sp_off + t);
+  M.S = __ldg(L.tile_slots + t); M.nsp = __ldg(L.tile_sp_cnt + t);
+  M.lq0 = __ldg(L.tile_long_ptr + t); M.lq1 = __ldg(L.tile_long_ptr + t + 1);
+  return M;
+}
+
 // ---------------------------------------------------------------- tile pipeline ----
 // Issue the asynchronous loads of tile t into buffer `buf`: NV dense vectors (tile rows, padded
 // layout) by cp.async, and -- when NEEDQ -- the tile's data-matrix slice by TMA bulk copies.
@@ -290,7 +301,7 @@ __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t
   const Geo<D> geo(r);
   const TileBuf B = c.pick(buf);
   if (NEEDQ && c.tid == 0) {
-    const TileMeta M = c.tmeta[t - c.t0];
+    const TileMeta M = tile_meta(L, c, t);
     const int S = M.S, nsp = M.nsp;
     B.meta[0] = S;
     const unsigned bq = (unsigned)S * D1 * D1 * L.TP * 8u, bc = (unsigned)S * L.TP * 4u;
@@ -449,7 +460,7 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
     c.sW[geo.soff(lrow, cc)] = acc;
   }
   __syncthreads();
-  const TileMeta &M = c.tmeta[t - c.t0];
+  const TileMeta M = tile_meta(L, c, t);
   const int q0 = M.lq0, q1 = M.lq1;
   for (int q = q0; q < q1; ++q) {
     const int g = L.long_grp[q];

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
     c.mbar = s_mbar;
     c.meta = &s_meta[0][0];
     c.tmeta = s_tmeta;
-    for (int i = c.tid; i < c.t1 - c.t0; i += c.nth) {
+    for (int i = c.tid; i < min(c.t1 - c.t0, kMaxTilesPerCta); i += c.nth) {
       const int t = c.t0 + i;
       TileMeta M;
       M.boff = L.tile_boff[t]; M.coff = L.tile_coff[t]; M.spoff = L.tile_sp_off[t];
@@ -331,6 +331,79 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
     for (int i = 0; i < V_COUNT; ++i) o->perm[i] = s_perm[i];
 #pragma unroll
     for (int i = 0; i < PH_COUNT; ++i) { o->prof_ns[i] = s_prof_ns[i]; o->prof_cnt[i] = s_prof_cnt[i]; }
+  }
+}
+
+
+// ============================================================ k_spmm_persistent ====
+// `reps` data-matrix products out = Q X through the same tile pipeline (roofline leg of bench.py /
+// scripts/sweep_1m.py; Problem::dataMatrixProduct, src/CORA_problem.cpp:742-757).
+template <int D>
+__global__ void __launch_bounds__(kThreads, 2) k_spmm_persistent(const DevLayout L, const PArgs A, const double *X,
+                                                                 double *out, int reps) {
+  constexpr int D1 = D + 1;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) unsigned long long s_mbar[2];
+  __shared__ int s_meta[2][4];
+  __shared__ TileMeta s_tmeta[kMaxTilesPerCta];
+  __shared__ unsigned long long s_prof_ns[PH_COUNT], s_tph[2];
+  __shared__ unsigned int s_prof_cnt[PH_COUNT];
+  PCtx c;
+  c.b = blockIdx.x; c.G = gridDim.x; c.tid = threadIdx.x; c.nth = blockDim.x; c.r = A.r; c.nbuf = A.nbuf;
+  c.bar = A.bar; c.target = 0; c.partials = A.partials; c.parity = 0; c.nbar = 0;
+  c.prof_ns = s_prof_ns; c.prof_cnt = s_prof_cnt; c.tph = s_tph;
+  c.mpar0 = c.mpar1 = 0u;
+  const int r = A.r;
+  {
+    c.t0 = A.cta_t0[c.b];
+    c.t1 = A.cta_t0[c.b + 1];
+    c.e0 = (long long)c.t0 * L.TR * r;
+    c.e1 = min((long long)c.t1 * L.TR, (long long)L.N) * r;
+    if (c.e0 > c.e1) c.e0 = c.e1;
+    const Geo<D> geo(r);
+    c.nbv = L.maxSlots * D1 * D1 * L.TP;              // doubles
+    c.ncol = (L.maxSlots * L.TP + 3) & ~3;            // ints
+    c.spcap = (L.maxTileSpill + 3) & ~3;              // entries
+    c.TRP = L.TRP;
+    c.pstride = D1 * geo.RS + geo.PADP;
+    c.vstride = (L.TR * geo.RS + L.TP + 2 * c.pstride + 1) & ~1;
+    c.nlam = D * D * L.TP;
+    c.qstride = c.nbv + c.spcap + (c.ncol + c.TRP + c.spcap) / 2;  // doubles (int regions are multiples of 4)
+    c.smem = smem;
+    c.sred = smem;
+    c.sbc = smem + 64;
+    c.qbase = 80;
+    const int after_q = c.qbase + c.nbuf * c.qstride;
+    c.sW = smem + after_q;
+    c.vbase = after_q + c.vstride;
+    c.mbar = s_mbar;
+    c.meta = &s_meta[0][0];
+    c.tmeta = s_tmeta;
+    for (int i = c.tid; i < min(c.t1 - c.t0, kMaxTilesPerCta); i += c.nth) {
+      const int t = c.t0 + i;
+      TileMeta M;
+      M.boff = L.tile_boff[t]; M.coff = L.tile_coff[t]; M.spoff = L.tile_sp_off[t];
+      M.S = L.tile_slots[t]; M.nsp = L.tile_sp_cnt[t];
+      M.lq0 = L.tile_long_ptr[t]; M.lq1 = L.tile_long_ptr[t + 1];
+      s_tmeta[i] = M;
+    }
+    if (c.tid < PH_COUNT) { s_prof_ns[c.tid] = 0; s_prof_cnt[c.tid] = 0; }
+    if (c.tid == 0) {
+      s_tph[0] = s_tph[1] = 0;
+      mbar_init(&s_mbar[0], 1);
+      mbar_init(&s_mbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  double *lp0 = A.longpart;
+  for (int rep = 0; rep < reps; ++rep) {
+    if (L.numChunks > 0) {
+      hub_phase<D>(L, c, X, 1.0, nullptr, 0.0, lp0);
+      grid_sync(c);
+    }
+    qprod_phase<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
+    grid_sync(c);
   }
 }
 

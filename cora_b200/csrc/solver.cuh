@@ -212,10 +212,8 @@ inline size_t persistent_smem(const H *h, int r, int nbuf) {
 }
 
 // One cooperative launch runs the whole trust-region solve on the resident iterate.
-inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200_tnt_result *res) {
-  using clk = std::chrono::steady_clock;
-  const auto t0 = clk::now();
-  const int64_t launches0 = h->launches;
+// grid / shared-memory configuration of the persistent kernels at rank r (cached per rank)
+inline void persistent_configure(H *h, int r) {
   if (h->persistent_grid_r != r) {
     if (const char *e = getenv("CORA_B200_PTHREADS")) h->persistent_threads = std::max(64, std::min(256, atoi(e)));
     // double-buffered tile pipeline when two CTAs of it fit on an SM, single-buffered otherwise
@@ -237,9 +235,6 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
     if (per_sm < 1) throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel does not fit on an SM at this rank");
     if (const char *e = getenv("CORA_B200_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
     int G0 = std::max(1, std::min(h->sm_count * per_sm, h->DL.numTiles));
-    // every CTA caches the metadata of its tiles in shared memory: at most kMaxTilesPerCta of them
-    if ((h->DL.numTiles + G0 - 1) / G0 + 1 > kMaxTilesPerCta)
-      throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many tiles per CTA");
     h->persistent_grid = G0;
     h->persistent_grid_r = r;
     {  // cost-balanced contiguous partition: scalar-row tiles (two L2 gathers per element) weigh more
@@ -266,13 +261,19 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
       }
       for (int i = 1; i <= G0; ++i) {
         t0[i] = std::max(t0[i], t0[i - 1]);
-        if (t0[i] - t0[i - 1] > kMaxTilesPerCta) throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many tiles per CTA");
       }
       t0[G0] = HL.numTiles;
       h->d_cta_t0.upload(t0, h->stream);
       CUDA_CHECK(cudaStreamSynchronize(h->stream));
     }
   }
+}
+
+inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200_tnt_result *res) {
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  const int64_t launches0 = h->launches;
+  persistent_configure(h, r);
   const int G = h->persistent_grid;
   const size_t smem = h->persistent_smem;
   const size_t npart = 2 * ((size_t)G * kPPart + 8);
@@ -410,6 +411,36 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   res->total_inner = o.total_inner;
   res->kernel_launches = h->launches - launches0;
   h->resident_r = r;
+}
+
+// reps x (out = Q X) through the tile pipeline of the persistent kernel; returns the CUDA-event milliseconds
+inline float spmm_persistent(H *h, int r, const double *X, double *out, int reps) {
+  persistent_configure(h, r);
+  const int G = h->persistent_grid;
+  const size_t nlp = 2 * (size_t)std::max(h->DL.numChunks, 1) * h->DL.D1 * h->ws_r;
+  if (h->d_longpart.n < nlp) h->d_longpart.alloc(nlp);
+  if (!h->d_bar.p) h->d_bar.alloc(1);
+  PArgs A{};
+  A.longpart = h->d_longpart.p;
+  A.bar = h->d_bar.p;
+  A.r = r;
+  A.nbuf = h->persistent_nbuf;
+  A.cta_t0 = h->d_cta_t0.p;
+  CUDA_CHECK(cudaMemsetAsync(h->d_bar.p, 0, sizeof(unsigned long long), h->stream));
+  DevLayout Lc = h->DL;
+  void *args[] = {(void *)&Lc, (void *)&A, (void *)&X, (void *)&out, (void *)&reps};
+  DISPATCH_D(h, CUDA_CHECK(cudaFuncSetAttribute(k_spmm_persistent<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)h->persistent_smem)));
+  CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  DISPATCH_D(h, CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_spmm_persistent<DD>, dim3(G),
+                                                       dim3(h->persistent_threads), args, h->persistent_smem,
+                                                       h->stream)));
+  check_launch(h);
+  CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  CUDA_CHECK(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  return ms;
 }
 
 inline void tnt_resident(H *h, int r, const cora_b200_tnt_params &p, cora_b200_tnt_result *res) {
