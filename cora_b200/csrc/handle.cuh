@@ -110,6 +110,10 @@ struct cora_b200_handle {
   int trace_cap = 0;
   int persistent_grid = 0, persistent_grid_r = -1, persistent_nbuf = 0, persistent_threads = 256;
   size_t persistent_smem = 0;
+  // bit 0: STPCG update / preconditioner projection in the group-per-pose register form (update_reg);
+  // bit 1: Hessian / gradient products in the hybrid form (TMA-staged operands + register compute, qprod_hyb)
+  // instead of the shared-memory epilogue (qprod_phase)
+  int persistent_regpath = 1;
   bool use_persistent = true;
   int snap_r = 0;
 };

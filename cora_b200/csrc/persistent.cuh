@@ -295,7 +295,7 @@ __device__ __forceinline__ TileMeta tile_meta(const DevLayout &L, const PCtx &c,
 // layout) by cp.async, and -- when NEEDQ -- the tile's data-matrix slice by TMA bulk copies.
 template <int D, bool NEEDQ, int NV>
 __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
-                                              const double *v1, const double *v2, const double *lam = nullptr) {
+                                              const double *v1, const double *v2, const double *bsrc = nullptr) {
   constexpr int D1 = D + 1;
   const int r = c.r;
   const Geo<D> geo(r);
@@ -308,7 +308,7 @@ __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t
     const unsigned bg = (unsigned)L.TRP * 4u, bp = (unsigned)nsp * 4u, bv = (unsigned)nsp * 8u;
     mbar_expect_tx(B.mbar, bq + bc + bg + bp + bv);
     if (S > 0) {
-      bulk_g2s(B.sval, L.bval + M.boff, bq, B.mbar);
+      bulk_g2s(B.sval, (bsrc != nullptr ? bsrc : L.bval) + M.boff, bq, B.mbar);
       bulk_g2s(B.scol, L.bcol + M.coff, bc, B.mbar);
     }
     bulk_g2s(B.gptr, L.sp_gptr + (size_t)t * L.TRP, bg, B.mbar);
@@ -350,9 +350,9 @@ __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t
 // Top of a pipeline iteration: start tile t+1 (double buffered), then wait for tile t.
 template <int D, bool NEEDQ, int NV>
 __device__ __forceinline__ void tile_acquire(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
-                                             const double *v1, const double *v2, const double *lam = nullptr) {
+                                             const double *v1, const double *v2, const double *bsrc = nullptr) {
   if (c.nbuf == 2 && t + 1 < c.t1) {
-    tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, buf ^ 1, v0, v1, v2, lam);
+    tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, buf ^ 1, v0, v1, v2, bsrc);
     cp_async_wait<1>();
   } else {
     cp_async_wait<0>();
@@ -366,10 +366,41 @@ __device__ __forceinline__ void tile_acquire(const DevLayout &L, PCtx &c, int t,
 // Bottom: every thread is done with tile t's buffer.
 template <int D, bool NEEDQ, int NV>
 __device__ __forceinline__ void tile_release(const DevLayout &L, PCtx &c, int t, int &buf, const double *v0,
-                                             const double *v1, const double *v2, const double *lam = nullptr) {
+                                             const double *v1, const double *v2, const double *bsrc = nullptr) {
   __syncthreads();
   if (c.nbuf == 2) buf ^= 1;
-  else if (t + 1 < c.t1) tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, 0, v0, v1, v2, lam);
+  else if (t + 1 < c.t1) tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, 0, v0, v1, v2, bsrc);
+}
+
+// Sums of the hub-row chunk partials of the tile's long groups, one warp per (group row, column) with the
+// chunks strided over the lanes and a fixed-order xor tree: hub[(q - lq0) * hub_stride + a * r + cc].
+// (A landmark row couples to thousands of poses: 33 chunks per row at 100k poses -- summed by one thread
+// this was a 16 us straggler on the CTA that owns the landmark rows.)
+// rows per long group stored in the hub scratch: d+1 if the tile has pose hubs, 1 if only scalar rows
+template <int D>
+__device__ __forceinline__ int hub_stride(const DevLayout &L, const TileMeta &M, int r) {
+  return (M.lq1 > M.lq0 && L.long_grp[M.lq0] < L.n) ? (D + 1) * r : r;
+}
+
+template <int D>
+__device__ __forceinline__ void tile_hub_sums(const DevLayout &L, PCtx &c, const TileMeta &M, const double *longpart,
+                                              double *hub) {
+  constexpr int D1 = D + 1;
+  const int r = c.r;
+  const int lane = c.tid & 31, warp = c.tid >> 5, nwarps = c.nth >> 5;
+  const int hs = hub_stride<D>(L, M, r);
+  const int npairs = (M.lq1 - M.lq0) * hs;
+  for (int pair = warp; pair < npairs; pair += nwarps) {
+    const int q = M.lq0 + pair / hs;
+    const int rem = pair - (q - M.lq0) * hs;
+    const int a = rem / r, cc = rem - a * r;
+    const int c0 = L.long_chunk_ptr[q], c1 = L.long_chunk_ptr[q + 1];
+    double sacc = 0.0;
+    for (int ch = c0 + lane; ch < c1; ch += 32) sacc += __ldcg(longpart + ((size_t)ch * D1 + a) * r + cc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+    if (lane == 0) hub[pair] = sacc;
+  }
 }
 
 // sW <- (Q X)[tile]; sX holds the tile rows of X plus one pose block of halo on either side
@@ -392,11 +423,6 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
     double xs0 = 0.0, xs1 = 0.0;
     if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
     if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
-    double lm[D * D];  // Lambda block of the pose (global, written by this CTA in the last GRAD phase)
-    if (slam != nullptr) {
-#pragma unroll
-      for (int i = 0; i < D * D; ++i) lm[i] = __ldcg(slam + i * TP + p);
-    }
     double acc[D1];
 #pragma unroll
     for (int a = 0; a < D1; ++a) acc[a] = 0.0;
@@ -418,13 +444,6 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
       for (int a = 0; a < D1; ++a)
 #pragma unroll
         for (int q = 0; q < D1; ++q) acc[a] = fma(bv[(a * D1 + q) * TP], x[q], acc[a]);
-    }
-    if (slam != nullptr) {  // (Q - Lambda) x: the curvature term of the Riemannian Hessian
-      const double *xp = sX + p * pstride + cc;
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-#pragma unroll
-        for (int q = 0; q < D; ++q) acc[a] = fma(-lm[a * D + q], xp[q * geo.RS], acc[a]);
     }
     for (int k = k0; k < k1; ++k) {
       const unsigned pk = B.spk[k];
@@ -450,8 +469,7 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
     double xs0 = 0.0, xs1 = 0.0;
     if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
     if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
-    double dg = __ldg(L.sdiag + sidx);
-    if (lamS != nullptr) dg -= __ldcg(lamS + sidx);
+    const double dg = lamS != nullptr ? __ldcg(lamS + sidx) : __ldg(L.sdiag + sidx);  // lamS: diag(Q) - lambda_k
     double acc = dg * sX[geo.soff(lrow, cc)];
     if (k0 < k1) acc = fma(B.spv[k0], xs0, acc);
     if (k0 + 1 < k1) acc = fma(B.spv[k0 + 1], xs1, acc);
@@ -461,20 +479,23 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
   }
   __syncthreads();
   const TileMeta M = tile_meta(L, c, t);
-  const int q0 = M.lq0, q1 = M.lq1;
-  for (int q = q0; q < q1; ++q) {
-    const int g = L.long_grp[q];
-    const int lrow0 = (g < L.n ? g * D1 : L.nPoseRows + (g - L.n)) - T.row0;
-    const int nrow = g < L.n ? D1 : 1;
-    const int c0 = L.long_chunk_ptr[q], c1 = L.long_chunk_ptr[q + 1];
-    for (int i = c.tid; i < nrow * r; i += c.nth) {
-      const int a = i / r, cc = i - a * r;
-      double s = 0.0;
-      for (int ch = c0; ch < c1; ++ch) s += __ldcg(longpart + ((size_t)ch * D1 + a) * r + cc);
-      c.sW[geo.soff(lrow0 + a, cc)] += s;
+  if (M.lq1 > M.lq0) {
+    double *hub = B.slot[2];  // free at this point in every mode (the epilogue output is written later)
+    tile_hub_sums<D>(L, c, M, longpart, hub);
+    __syncthreads();
+    const int hs = hub_stride<D>(L, M, r);
+    for (int i = c.tid; i < (M.lq1 - M.lq0) * hs; i += c.nth) {
+      const int ql = i / hs;
+      const int rem = i - ql * hs;
+      const int a = rem / r, cc = rem - a * r;
+      const int g = L.long_grp[M.lq0 + ql];
+      const int nrow = g < L.n ? D1 : 1;
+      if (a >= nrow) continue;
+      const int lrow0 = (g < L.n ? g * D1 : L.nPoseRows + (g - L.n)) - T.row0;
+      c.sW[geo.soff(lrow0 + a, cc)] += hub[i];
     }
+    __syncthreads();
   }
-  if (q1 > q0) __syncthreads();
 }
 
 // Riemannian epilogue over a staged tile with D threads per pose (thread (p, a) owns row a of the
@@ -485,7 +506,8 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
 template <int D, bool CURV>
 __device__ __forceinline__ void tile_epilogue2(const DevLayout &L, const TileInfo &T, const Geo<D> &geo, PCtx &c,
                                                const double *sY, const double *sG, const double *sDd, double *sW,
-                                               double *sOut, double *lam_out = nullptr, double *lamS_out = nullptr) {
+                                               double *sOut, double *lam_out = nullptr, double *lamS_out = nullptr,
+                                               const double *sv0 = nullptr) {
   const int r = c.r, RS = geo.RS;
   const int nPU = T.nP * D;
   if (CURV) {
@@ -542,9 +564,12 @@ __device__ __forceinline__ void tile_epilogue2(const DevLayout &L, const TileInf
       }
 #pragma unroll
       for (int b = 0; b < D; ++b) Pr[b] = 0.5 * (Pr[b] + Pc[b]);
-      if (lam_out != nullptr)  // W = Q Y here: row a of Lambda_p = sym(Y_p (QY)_p^T)
+      if (lam_out != nullptr)  // W = Q Y here: row a of Lambda_p = sym(Y_p (QY)_p^T); store (Q - Lambda) diag block
 #pragma unroll
-        for (int b = 0; b < D; ++b) lam_out[(a * D + b) * L.TP + p] = Pr[b];
+        for (int b = 0; b < D; ++b) {
+          const int e = (a * (D + 1) + b) * L.TP + p;
+          lam_out[e] = sv0[e] - Pr[b];
+        }
       double *out = sOut + o + a * RS;
       for (int cc = 0; cc < r; ++cc) {
         double s = w[a * RS + cc];
@@ -559,10 +584,10 @@ __device__ __forceinline__ void tile_epilogue2(const DevLayout &L, const TileInf
         double s = 0.0;
         for (int cc = 0; cc < r; ++cc) s = fma(sY[o + cc], sW[o + cc], s);
         for (int cc = 0; cc < r; ++cc) sOut[o + cc] = fma(-s, sY[o + cc], sW[o + cc]);
-        if (lamS_out != nullptr) lamS_out[T.row0 + lrow - L.nPoseRows] = s;
+        if (lamS_out != nullptr) lamS_out[T.row0 + lrow - L.nPoseRows] = __ldg(L.sdiag + T.row0 + lrow - L.nPoseRows) - s;
       } else {
         for (int cc = 0; cc < r; ++cc) sOut[o + cc] = sW[o + cc];  // landmark rows: Euclidean
-        if (lamS_out != nullptr) lamS_out[T.row0 + lrow - L.nPoseRows] = 0.0;
+        if (lamS_out != nullptr) lamS_out[T.row0 + lrow - L.nPoseRows] = __ldg(L.sdiag + T.row0 + lrow - L.nPoseRows);
       }
     }
   }
@@ -581,8 +606,9 @@ template <int D, int MODE>
 __device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const double *X, const double *Y,
                                             double *out, double *out2, const double *longpart, double *lam,
                                             double *lamS, double *acc) {
-  // GRAD: X is the point itself (one slot), lam / lamS are WRITTEN (Lambda blocks at X)
-  // HESS: X is the tangent vector, Y the base point (two slots), lam / lamS are READ:
+  // lam: a full copy of the block-ELL values whose diagonal blocks hold Q - Lambda(X); lamS: diag(Q) - lambda_k
+  // of the scalar rows.  GRAD (X is the point itself, one slot) WRITES them for its tiles; HESS (X the
+  // tangent vector, Y the base point, two slots) streams them instead of Q:
   //       Hess_Y[X] = proj_Y((Q - Lambda(Y)) X)   (src/CORA_problem.cpp:822-867 with the
   //       SymBlockDiagProduct of Y and grad F hoisted out of the CG loop: it does not depend on X)
   constexpr int NV = (MODE == QM_HESS) ? 2 : 1;
@@ -601,8 +627,7 @@ __device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const d
     const int nE = T.nR * r;
     const double *sX = B.slot[0], *sY = B.slot[1];
     double *sO = B.slot[2];
-    tile_qx<D>(L, t, T, geo, c, B, X, sX, longpart, MODE == QM_HESS ? lam + (size_t)t * c.nlam : nullptr,
-               MODE == QM_HESS ? lamS : nullptr);
+    tile_qx<D>(L, t, T, geo, c, B, X, sX, longpart, nullptr, MODE == QM_HESS ? lamS : nullptr);
     sub_end(c, PH_Q_QX);
     if (MODE == QM_SPMM) {
       for (int le = c.tid; le < nE; le += c.nth) {
@@ -617,7 +642,8 @@ __device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const d
         out2[T.ebase + le] = w;
         acc[0] = fma(sX[so], w, acc[0]);
       }
-      tile_epilogue2<D, false>(L, T, geo, c, sX, nullptr, nullptr, c.sW, sO, lam + (size_t)t * c.nlam, lamS);
+      tile_epilogue2<D, false>(L, T, geo, c, sX, nullptr, nullptr, c.sW, sO, lam + tile_meta(L, c, t).boff, lamS, B.sval);
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // the patched blocks are read by TMA bulk copies later
       for (int le = c.tid; le < nE; le += c.nth) {
         const int lrow = le / r, cc = le - lrow * r;
         const double w = sO[geo.soff(lrow, cc)];

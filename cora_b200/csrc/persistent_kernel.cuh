@@ -4,6 +4,7 @@
 #pragma once
 #include "persistent.cuh"
 #include "persistent_chain.cuh"
+#include "persistent_reg.cuh"
 
 namespace cora_b200 {
 
@@ -20,6 +21,7 @@ struct PArgs {
   double *lamS[2];               // lambda_k = (QY)_k . y_k per scalar row (0 for landmark rows)
   cora_b200_tnt_params p;
   int r, trace_cap, precond, nbuf;
+  int regpath;                   // 1: register/shuffle phases (persistent_reg.cuh), 0: shared-memory tile pipeline
   ChainDev chain;                // RegularizedCholesky factor (precond == CORA_B200_PRECON_REG_CHOLESKY)
 };
 
@@ -126,13 +128,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
   const bool use_chain = (A.precond == CORA_B200_PRECON_REG_CHOLESKY);
   // Rin must be complete grid-wide (a barrier lies between its producer and this call)
   auto precond_project = [&](const double *Y, double *Rin, double *Vout, double *acc2) {
+    const double *Zin = nullptr;
+    int zsrc = A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1;
     if (use_chain) {
       chain_apply_persistent<D>(A.chain, c, Rin, v[V_Z]);
-      update_phase<D, false>(L, c, Y, nullptr, Rin, v[V_Z], Vout, 0.0, 2, acc2);
-    } else {
-      update_phase<D, false>(L, c, Y, nullptr, Rin, nullptr, Vout, 0.0,
-                             A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, acc2);
+      Zin = v[V_Z];
+      zsrc = 2;
     }
+    if (A.regpath & 1) update_reg<D, false>(L, c, Y, nullptr, Rin, Zin, Vout, 0.0, zsrc, acc2);
+    else update_phase<D, false>(L, c, Y, nullptr, Rin, Zin, Vout, 0.0, zsrc, acc2);
   };
 
   if (A.prof_all != nullptr) {  // barrier latency calibration (profiling runs only)
@@ -148,7 +152,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
   double fx, gnorm, pgnorm, rv_cur;
   {
     double acc[3] = {0.0, 0.0, 0.0};
-    qprod_phase<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
+    if (A.regpath & 2) qprod_hyb<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
+    else qprod_phase<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
     grid_reduce<3>(acc, c, &t0);
     fx = 0.5 * acc[0];
     gnorm = sqrt(acc[1]);
@@ -194,7 +199,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
     grid_sync(c);
     while (cg.state == 0) {
       double acc[3] = {0.0, 0.0, 0.0};
-      qprod_phase<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
+      if (A.regpath & 2) qprod_hyb<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
+      else qprod_phase<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
       grid_reduce<3>(acc, c, nullptr);
       if (c.tid == 0) cg_post_hess(&cg, acc[0], acc[1], acc[2]);
       __syncthreads();
@@ -213,7 +219,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
         axpby_flat(c, 1.0, v[V_R], alpha, v[V_HP], v[V_R]);  // r += alpha Hp  (:377)
         grid_sync(c);
         chain_apply_persistent<D>(A.chain, c, v[V_R], v[V_Z]);
-        update_phase<D, false>(L, c, v[V_X], nullptr, v[V_R], v[V_Z], v[V_V], 0.0, 2, a2);
+        if (A.regpath & 1) update_reg<D, false>(L, c, v[V_X], nullptr, v[V_R], v[V_Z], v[V_V], 0.0, 2, a2);
+        else update_phase<D, false>(L, c, v[V_X], nullptr, v[V_R], v[V_Z], v[V_V], 0.0, 2, a2);
+      } else if (A.regpath & 1) {
+        update_reg<D, true>(L, c, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
+                            A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);
       } else {
         update_phase<D, true>(L, c, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
                               A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);
@@ -264,8 +274,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
     double fxp, gnorm_p, hHh;
     {
       double a6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      qprod_phase<D, QM_GRAD>(L, c, v[V_XP], nullptr, v[V_GRADP], v[V_GP], lp0, lamp, lamSp, a6);
-      qprod_phase<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_HP], nullptr, lp1, lamc, lamSc, a6 + 3);
+      if (A.regpath & 2) {
+        qprod_hyb<D, QM_GRAD>(L, c, v[V_XP], nullptr, v[V_GRADP], v[V_GP], lp0, lamp, lamSp, a6);
+        qprod_hyb<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_HP], nullptr, lp1, lamc, lamSc, a6 + 3);
+      } else {
+        qprod_phase<D, QM_GRAD>(L, c, v[V_XP], nullptr, v[V_GRADP], v[V_GP], lp0, lamp, lamSp, a6);
+        qprod_phase<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_HP], nullptr, lp1, lamc, lamSc, a6 + 3);
+      }
       grid_reduce<6>(a6, c, nullptr);
       fxp = 0.5 * a6[0];
       gnorm_p = sqrt(a6[1]);
@@ -402,7 +417,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_spmm_persistent(const DevLayout
       hub_phase<D>(L, c, X, 1.0, nullptr, 0.0, lp0);
       grid_sync(c);
     }
-    qprod_phase<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
+    if (A.regpath & 2) qprod_hyb<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
+    else qprod_phase<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
     grid_sync(c);
   }
 }

@@ -215,6 +215,7 @@ inline size_t persistent_smem(const H *h, int r, int nbuf) {
 // grid / shared-memory configuration of the persistent kernels at rank r (cached per rank)
 inline void persistent_configure(H *h, int r) {
   if (h->persistent_grid_r != r) {
+    if (const char *e = getenv("CORA_B200_REG")) h->persistent_regpath = atoi(e);
     if (const char *e = getenv("CORA_B200_PTHREADS")) h->persistent_threads = std::max(64, std::min(256, atoi(e)));
     // double-buffered tile pipeline when two CTAs of it fit on an SM, single-buffered otherwise
     size_t smem = 0;
@@ -227,6 +228,17 @@ inline void persistent_configure(H *h, int r) {
       throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: tile working set exceeds shared memory at this rank");
     h->persistent_nbuf = nbuf;
     h->persistent_smem = smem;
+    {  // the hub-row scratch of a tile lives in one vector slot
+      const HostLayout &HL = h->HL;
+      const size_t vstride = ((size_t)HL.TR * (r | 1) + HL.TP) & ~(size_t)1;
+      for (int t = 0; t < HL.numTiles; ++t) {
+        const int q0 = HL.tile_long_ptr[t], q1 = HL.tile_long_ptr[t + 1];
+        if (q1 == q0) continue;
+        const size_t hs = HL.long_grp[q0] < HL.n ? (size_t)HL.D1 * r : (size_t)r;
+        if ((size_t)(q1 - q0) * hs > vstride)
+          throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many hub rows in one tile for the shared-memory scratch");
+      }
+    }
     int per_sm = 0;
     DISPATCH_D(h, {
       CUDA_CHECK(cudaFuncSetAttribute(k_tnt_persistent<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -282,9 +294,17 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   if (h->d_longpart.n < nlp) h->d_longpart.alloc(nlp);
   if (!h->d_bar.p) h->d_bar.alloc(1);
   {
-    const size_t nl = (size_t)h->DL.numTiles * h->DL.d * h->DL.d * h->DL.TP, ns = (size_t)h->DL.l + h->DL.m + 1;
-    if (h->d_lamT.n < 2 * nl) h->d_lamT.alloc(2 * nl);
-    if (h->d_lamS.n < 2 * ns) h->d_lamS.alloc(2 * ns);
+    // two copies (current / proposal) of the block values with Q - Lambda on the diagonal blocks, and of
+    // diag(Q) - lambda_k of the scalar rows; everything but those entries is Q and is copied once
+    const size_t nl = std::max<size_t>((size_t)h->HL.tile_boff[h->HL.numTiles], 1), ns = (size_t)h->DL.l + h->DL.m + 1;
+    if (h->d_lamT.n < 2 * nl) {
+      h->d_lamT.alloc(2 * nl);
+      h->d_lamS.alloc(2 * ns);
+      for (int k = 0; k < 2; ++k) {
+        CUDA_CHECK(cudaMemcpyAsync(h->d_lamT.p + k * nl, h->d_bval.p, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_CHECK(cudaMemcpyAsync(h->d_lamS.p + k * ns, h->d_sdiag.p, (ns - 1) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      }
+    }
   }
   if (!h->d_tntdev.p) {
     h->d_tntdev.alloc(sizeof(TntDev));
@@ -308,6 +328,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   A.trace_cap = h->trace_cap;
   A.precond = h->precond;
   A.nbuf = h->persistent_nbuf;
+  A.regpath = h->persistent_regpath;
   A.cta_t0 = h->d_cta_t0.p;
   if (h->precond == CORA_B200_PRECON_REG_CHOLESKY) {
     ChainChol *C = h->chol;
@@ -425,6 +446,7 @@ inline float spmm_persistent(H *h, int r, const double *X, double *out, int reps
   A.bar = h->d_bar.p;
   A.r = r;
   A.nbuf = h->persistent_nbuf;
+  A.regpath = h->persistent_regpath;
   A.cta_t0 = h->d_cta_t0.p;
   CUDA_CHECK(cudaMemsetAsync(h->d_bar.p, 0, sizeof(unsigned long long), h->stream));
   DevLayout Lc = h->DL;

