@@ -733,12 +733,25 @@ __device__ __forceinline__ void axpby_flat(PCtx &c, double a, const double *X, d
   ph_end(c, PH_PUPDATE);
 }
 
-// s += alpha p ; p' = -v + beta p   (IterativeSolvers.h:374,420) in one pass over the CTA's elements
+// s += alpha p ; p' = -v + beta p   (IterativeSolvers.h:374,420) in one pass over the CTA's elements,
+// 16-byte accesses (the CTA's element range starts at a multiple of TR*r, which is even)
 __device__ __forceinline__ void cg_pupdate_flat(PCtx &c, double alpha, double beta, double *S, const double *P,
                                                 const double *V, double *Pn) {
   ph_begin(c);
+  const long long n2 = (c.e1 - c.e0) >> 1;
+  const double2 *P2 = reinterpret_cast<const double2 *>(P + c.e0), *V2 = reinterpret_cast<const double2 *>(V + c.e0);
+  double2 *S2 = reinterpret_cast<double2 *>(S + c.e0), *Pn2 = reinterpret_cast<double2 *>(Pn + c.e0);
 #pragma unroll 4
-  for (long long e = c.e0 + c.tid; e < c.e1; e += c.nth) {
+  for (long long i = c.tid; i < n2; i += c.nth) {
+    const double2 p = __ldcg(P2 + i), v = __ldcg(V2 + i);
+    double2 s = __ldcg(S2 + i), pn;
+    s.x = fma(alpha, p.x, s.x); s.y = fma(alpha, p.y, s.y);
+    pn.x = fma(beta, p.x, -v.x); pn.y = fma(beta, p.y, -v.y);
+    S2[i] = s;
+    Pn2[i] = pn;
+  }
+  if (c.tid == 0 && ((c.e1 - c.e0) & 1)) {  // odd tail (last CTA only)
+    const long long e = c.e1 - 1;
     const double p = __ldcg(P + e);
     S[e] = fma(alpha, p, __ldcg(S + e));
     Pn[e] = fma(beta, p, -__ldcg(V + e));
