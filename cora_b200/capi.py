@@ -121,6 +121,7 @@ SYMBOLS = [
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
     "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile",
+    "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
     "cora_b200_select_best", "cora_b200_nccl_unique_id", "cora_b200_nccl_init", "cora_b200_nccl_destroy",
 ]
 
@@ -257,6 +258,30 @@ def debug_chain_host(d, n, m, nt, Q, shift, pin_last=True, V=None):
                                              C.c_int(r), _p(V) if V is not None else None,
                                              _p(out) if out is not None else None, C.byref(pd)))
     return bool(pd.value), out
+
+
+def parse_pyfg(path_or_text, from_text=False):
+    """PyFG file (or text) -> (d, n_poses, n_landmarks, measurement stacks) through the C++ parser."""
+    lib = load()
+    g = C.c_void_p()
+    _check(lib.cora_b200_pyfg_parse(C.c_char_p(path_or_text.encode()), C.c_int(int(from_text)), C.byref(g)))
+    try:
+        d, n, l = C.c_int(), C.c_int(), C.c_int()
+        E, Ep, m = C.c_int64(), C.c_int64(), C.c_int64()
+        _check(lib.cora_b200_pyfg_sizes(g, C.byref(d), C.byref(n), C.byref(l), C.byref(E), C.byref(Ep), C.byref(m)))
+        d, n, l, E, Ep, m = d.value, n.value, l.value, E.value, Ep.value, m.value
+        i64, f64 = np.int64, np.float64
+        A = dict(rp_i=np.zeros(E, i64), rp_j=np.zeros(E, i64), rp_t=np.zeros((E, d), f64), rp_tau=np.zeros(E, f64),
+                 rot_i=np.zeros(Ep, i64), rot_j=np.zeros(Ep, i64), rot_R=np.zeros((Ep, d, d), f64),
+                 rot_kappa=np.zeros(Ep, f64), rg_a=np.zeros(m, i64), rg_b=np.zeros(m, i64), rg_r=np.zeros(m, f64),
+                 rg_w=np.zeros(m, f64))
+        pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        _check(lib.cora_b200_pyfg_arrays(g, pi(A["rp_i"]), pi(A["rp_j"]), _p(A["rp_t"]), _p(A["rp_tau"]),
+                                         pi(A["rot_i"]), pi(A["rot_j"]), _p(A["rot_R"]), _p(A["rot_kappa"]),
+                                         pi(A["rg_a"]), pi(A["rg_b"]), _p(A["rg_r"]), _p(A["rg_w"])))
+        return d, n, l, A
+    finally:
+        lib.cora_b200_pyfg_free(g)
 
 
 def assemble(d, n, l, arrays):

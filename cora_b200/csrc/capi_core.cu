@@ -2,6 +2,7 @@
 #include <mutex>
 
 #include "assemble.hpp"
+#include "pyfg.hpp"
 #include "chain_chol.cuh"
 #include "ops.cuh"
 #include "solver.cuh"
@@ -429,6 +430,59 @@ extern "C" int cora_b200_assemble(int d, int n_poses, int n_landmarks, int64_t E
     std::vector<double>().swap(g_asm_val);
   }
   API_END
+}
+
+// ------------------------------------------------------------------- PyFG parser ----
+struct cora_b200_pyfg {
+  cora_b200::PyfgProblem P;
+};
+
+extern "C" int cora_b200_pyfg_parse(const char *path_or_text, int from_text, cora_b200_pyfg_t **out) {
+  API_BEGIN
+  require(path_or_text && out, "NULL argument");
+  cora_b200_pyfg *g = new cora_b200_pyfg();
+  try {
+    if (from_text) {
+      std::istringstream in{std::string(path_or_text)};
+      parse_pyfg(in, g->P);
+    } else {
+      std::ifstream in(path_or_text);
+      if (!in.good()) throw Error(CORA_B200_ERUNTIME, std::string("Could not open file ") + path_or_text);
+      parse_pyfg(in, g->P);
+    }
+  } catch (...) {
+    delete g;
+    throw;
+  }
+  *out = g;
+  API_END
+}
+
+extern "C" int cora_b200_pyfg_sizes(const cora_b200_pyfg_t *g, int *d, int *n_poses, int *n_landmarks, int64_t *E,
+                                    int64_t *Ep, int64_t *m) {
+  API_BEGIN
+  require(g && d && n_poses && n_landmarks && E && Ep && m, "NULL argument");
+  *d = g->P.d; *n_poses = (int)g->P.n(); *n_landmarks = (int)g->P.l();
+  *E = (int64_t)g->P.rp_tau.size(); *Ep = (int64_t)g->P.rot_kappa.size(); *m = (int64_t)g->P.rg_w.size();
+  API_END
+}
+
+extern "C" int cora_b200_pyfg_arrays(const cora_b200_pyfg_t *g, int64_t *rp_i, int64_t *rp_j, double *rp_t,
+                                     double *rp_tau, int64_t *rot_i, int64_t *rot_j, double *rot_R,
+                                     double *rot_kappa, int64_t *rg_a, int64_t *rg_b, double *rg_r, double *rg_w) {
+  API_BEGIN
+  require(g != nullptr, "NULL argument");
+  const PyfgProblem &P = g->P;
+  auto cp = [](auto &v, auto *dst) { if (!v.empty()) { if (!dst) throw Error(CORA_B200_EINVAL, "NULL output array"); std::copy(v.begin(), v.end(), dst); } };
+  cp(P.rp_i, rp_i); cp(P.rp_j, rp_j); cp(P.rp_t, rp_t); cp(P.rp_tau, rp_tau);
+  cp(P.rot_i, rot_i); cp(P.rot_j, rot_j); cp(P.rot_R, rot_R); cp(P.rot_kappa, rot_kappa);
+  cp(P.rg_a, rg_a); cp(P.rg_b, rg_b); cp(P.rg_r, rg_r); cp(P.rg_w, rg_w);
+  API_END
+}
+
+extern "C" int cora_b200_pyfg_free(cora_b200_pyfg_t *g) {
+  delete g;
+  return CORA_B200_OK;
 }
 
 // Test hook (CPU only): the chain factorisation + solve executed on the host through the SAME

@@ -279,6 +279,22 @@ int cora_b200_assemble(int d, int n_poses, int n_landmarks, int64_t E, const int
                        const double *rg_r, const double *rg_w, int64_t *nnz, int32_t *rowptr,
                        int32_t *col, double *val);
 
+/* ---- PyFG text -> measurement stacks (host): parsePyfgTextToProblem (src/pyfg_text_parser.cpp:112-321)
+ * with the data model of src/CORA_problem.cpp:24-113 and the precisions of
+ * include/CORA/Measurements.h:79-152.  `path_or_text` is a file name, or the file contents when
+ * from_text != 0.  Errors as the reference: unknown keyword / malformed line -> ERUNTIME, duplicate
+ * variable or measurement, unknown symbol -> EINVAL.  The stacks (caller-allocated with the sizes
+ * cora_b200_pyfg_sizes reports; rp_t is E x d, rot_R is Ep x d x d row-major) are the input of
+ * cora_b200_assemble. */
+typedef struct cora_b200_pyfg cora_b200_pyfg_t;
+int cora_b200_pyfg_parse(const char *path_or_text, int from_text, cora_b200_pyfg_t **out);
+int cora_b200_pyfg_sizes(const cora_b200_pyfg_t *g, int *d, int *n_poses, int *n_landmarks, int64_t *E,
+                         int64_t *Ep, int64_t *m);
+int cora_b200_pyfg_arrays(const cora_b200_pyfg_t *g, int64_t *rp_i, int64_t *rp_j, double *rp_t,
+                          double *rp_tau, int64_t *rot_i, int64_t *rot_j, double *rot_R,
+                          double *rot_kappa, int64_t *rg_a, int64_t *rg_b, double *rg_r, double *rg_w);
+int cora_b200_pyfg_free(cora_b200_pyfg_t *g);
+
 /* ---- test hooks (no compute): the internal device layout, rebuilt into CSR on
  * the host so the CPU test-suite can check the permutation / block-ELL / spill
  * split without a GPU.  Buffers are caller-allocated (nnz entries). */
