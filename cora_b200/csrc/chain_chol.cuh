@@ -24,8 +24,10 @@
 
 #ifdef __CUDACC__
 #define CB_HD __host__ __device__ __forceinline__
+#define CB_UNROLL _Pragma("unroll")
 #else
 #define CB_HD inline
+#define CB_UNROLL
 #endif
 
 namespace cora_b200 {
@@ -209,6 +211,7 @@ CB_HD void forward_chunk(const ChunkGeo G, int k, int col, int ld, const double 
   const int g0 = G.first(k), L = G.interior(k), K = G.K;
   const bool hasR = G.has_right(k);
   double w[B], acc[B];
+  CB_UNROLL
   for (int a = 0; a < B; ++a) { w[a] = 0.0; acc[a] = 0.0; }
   const int nodes = L + (hasR ? 1 : 0);
   for (int j = 0; j < nodes; ++j) {
@@ -216,13 +219,16 @@ CB_HD void forward_chunk(const ChunkGeo G, int k, int col, int ld, const double 
     double b[B];
     if (rhs_prev != nullptr) {
       const size_t s = (size_t)((g + 1) * c_prev - 1);
+      CB_UNROLL
       for (int a = 0; a < B; ++a)
         b[a] = rhs_prev[(s * B + a) * ld + col] - cR_prev[((size_t)g * B + a) * ld + col] -
                cL_prev[((size_t)(g + 1) * B + a) * ld + col];
       if (j == L)  // the separator: keep its right-hand side for the next level
+        CB_UNROLL
         for (int a = 0; a < B; ++a) rhs_cur[((size_t)g * B + a) * ld + col] = b[a];
     } else {
       if (j == L) break;  // level 0: the separator's b stays where it is (sol is in place)
+      CB_UNROLL
       for (int a = 0; a < B; ++a) b[a] = sol[((size_t)g * B + a) * ld + col];
     }
     if (j == L) break;
@@ -230,27 +236,36 @@ CB_HD void forward_chunk(const ChunkGeo G, int k, int col, int ld, const double 
     if (j + 1 < L)
       for (int e = 0; e < 3 * BB; ++e) chain_prefetch(f + (size_t)(3 * BB + e) * K);
     double y[B];
+    CB_UNROLL
     for (int a = 0; a < B; ++a) {
       double s = b[a];
+      CB_UNROLL
       for (int q = 0; q < B; ++q) s -= f[(size_t)(a * B + q) * K] * w[q];
       y[a] = s;
     }
+    CB_UNROLL
     for (int a = 0; a < B; ++a) {
       double s = 0.0;
+      CB_UNROLL
       for (int q = 0; q < B; ++q) s += f[(size_t)(BB + a * B + q) * K] * y[q];
       w[a] = s;
     }
+    CB_UNROLL
     for (int a = 0; a < B; ++a) {
       double s = acc[a];
+      CB_UNROLL
       for (int q = 0; q < B; ++q) s += f[(size_t)(2 * BB + a * B + q) * K] * w[q];
       acc[a] = s;
     }
+    CB_UNROLL
     for (int a = 0; a < B; ++a) sol[((size_t)g * B + a) * ld + col] = w[a];
   }
+  CB_UNROLL
   for (int a = 0; a < B; ++a) {
     cL[((size_t)k * B + a) * ld + col] = acc[a];
     double s = 0.0;
     if (hasR)
+      CB_UNROLL
       for (int q = 0; q < B; ++q) s += UR[(size_t)k * BB + q * B + a] * w[q];  // U^T w_last
     cR[((size_t)k * B + a) * ld + col] = s;
   }
@@ -264,11 +279,13 @@ CB_HD void backward_chunk(const ChunkGeo G, int k, int col, int ld, const double
   constexpr int BB = B * B;
   const int g0 = G.first(k), L = G.interior(k), K = G.K;
   double xL[B], xn[B];
+  CB_UNROLL
   for (int a = 0; a < B; ++a) {
     xL[a] = (xsep != nullptr && G.has_left(k)) ? xsep[((size_t)(k - 1) * B + a) * ld + col] : 0.0;
     xn[a] = (xsep != nullptr && G.has_right(k)) ? xsep[((size_t)k * B + a) * ld + col] : 0.0;
   }
   if (G.has_right(k))
+    CB_UNROLL
     for (int a = 0; a < B; ++a) sol[((size_t)(g0 + L) * B + a) * ld + col] = xn[a];
   for (int j = L - 1; j >= 0; --j) {
     const int g = g0 + j;
@@ -276,12 +293,15 @@ CB_HD void backward_chunk(const ChunkGeo G, int k, int col, int ld, const double
     if (j > 0)
       for (int e = 0; e < 2 * BB; ++e) chain_prefetch(f - (size_t)(2 * BB - e) * K);
     double x[B];
+    CB_UNROLL
     for (int a = 0; a < B; ++a) {
       double s = sol[((size_t)g * B + a) * ld + col];
+      CB_UNROLL
       for (int q = 0; q < B; ++q)
         s -= f[(size_t)(a * B + q) * K] * xn[q] + f[(size_t)(BB + a * B + q) * K] * xL[q];
       x[a] = s;
     }
+    CB_UNROLL
     for (int a = 0; a < B; ++a) {
       sol[((size_t)g * B + a) * ld + col] = x[a];
       xn[a] = x[a];

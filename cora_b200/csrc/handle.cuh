@@ -101,7 +101,7 @@ struct cora_b200_handle {
   size_t prof_n = 0;
   cora_b200::DevBuf<double> d_snap;  // snapshot of the resident iterate
   // persistent TNT kernel (persistent.cuh)
-  cora_b200::DevBuf<double> d_longpart, d_ppartials, d_trace, d_lamT, d_lamS;
+  cora_b200::DevBuf<double> d_longpart, d_ppartials, d_trace, d_lamT, d_lamS, d_lmpart;
   cora_b200::DevBuf<unsigned long long> d_bar;
   cora_b200::DevBuf<int> d_cta_t0;
   cora_b200::DevBuf<unsigned char> d_tntdev;

@@ -669,6 +669,228 @@ __device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const d
   ph_end(c, MODE == QM_HESS ? PH_HESS : PH_GRAD);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// qprod_warp: the same tile pipeline and shared-memory operands as qprod_phase, but every warp takes
+// floor(32 / r) whole poses of the tile through Q x -> Riemannian epilogue -> store on its own, with
+// __syncwarp() between the steps: two block barriers per tile (acquire / release) instead of five, a
+// slow warp (spill gathers) no longer stalls the other seven, and the warp's d+1 rows x r columns x
+// PPW poses are one contiguous range of the output, stored with full coalescing.
+template <int D, int MODE>
+__device__ __forceinline__ void qprod_warp(const DevLayout &L, PCtx &c, const double *X, const double *Y, double *out,
+                                           double *out2, const double *longpart, double *lam, double *lamS,
+                                           double *acc) {
+  constexpr int D1 = D + 1;
+  constexpr int NV = (MODE == QM_HESS) ? 2 : 1;
+  const int r = c.r, TP = L.TP;
+  const Geo<D> geo(r);
+  const int RS = geo.RS;
+  const int PPW = 32 / r;                     // poses (or scalar rows) per warp step
+  const int lane = c.tid & 31, warp = c.tid >> 5, nwarps = c.nth >> 5;
+  const int lp = lane / r, cc = lane - lp * r;  // (pose within the warp step, column)
+  const bool lane_ok = lane < PPW * r;
+  const int pstride = D1 * RS + geo.PADP;
+  const double *bsrc = (MODE == QM_HESS) ? lam : nullptr;
+  ph_begin(c);
+  int buf = 0;
+  if (c.t0 < c.t1) tile_prefetch<D, true, NV>(L, c, c.t0, 0, X, Y, nullptr, bsrc);
+  for (int t = c.t0; t < c.t1; ++t) {
+    sub_begin(c);
+    tile_acquire<D, true, NV>(L, c, t, buf, X, Y, nullptr, bsrc);
+    sub_end(c, PH_Q_WAIT);
+    const TileBuf B = c.pick(buf);
+    const TileInfo T = tile_geom<D>(L, t, r);
+    const TileMeta M = tile_meta(L, c, t);
+    const double *sX = B.slot[0], *sY = (MODE == QM_HESS) ? B.slot[1] : B.slot[0];
+    double *sO = B.slot[2];
+    double *sW = c.sW;
+    const int S = B.meta[0];
+    const int winLo = max(T.row0 - D1, 0);
+    const int winHi = min(min(T.row0 + T.nR + D1, L.N), L.nPoseRows);
+    // hub sums of the tile's scalar hub rows live in the scalar-row part of sO, which this function never
+    // writes (tiles with POSE hub groups are routed to qprod_phase by the host: persistent_configure)
+    double *hub = sO + geo.soff(T.nP * D1, 0);
+    const int hs = r;
+    if (M.lq1 > M.lq0) {
+      tile_hub_sums<D>(L, c, M, longpart, hub);
+      __syncthreads();
+    }
+    // ---------------- pose blocks: PPW poses per warp step ----------------
+    for (int pg = warp * PPW; pg < T.nP; pg += nwarps * PPW) {
+      const int pl = pg + lp;
+      const bool active = lane_ok && pl < T.nP;
+      // step 1: (Q x) for (pose, column)
+      if (active) {
+        const int k0 = B.gptr[pl], k1 = B.gptr[pl + 1];
+        double xs0 = 0.0, xs1 = 0.0;
+        if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
+        if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
+        double w[D1];
+#pragma unroll
+        for (int a = 0; a < D1; ++a) w[a] = 0.0;
+        for (int s2 = 0; s2 < S; ++s2) {
+          const int jb = B.scol[s2 * TP + pl];
+          double x[D1];
+          if (jb >= winLo && jb + D1 <= winHi) {
+            const int lq = (jb - T.row0 + D1) / D1 - 1;
+            const double *xp = sX + lq * pstride + cc;
+#pragma unroll
+            for (int q = 0; q < D1; ++q) x[q] = xp[q * RS];
+          } else {
+            const double *xp = X + (size_t)jb * r + cc;
+#pragma unroll
+            for (int q = 0; q < D1; ++q) x[q] = __ldcg(xp + q * r);
+          }
+          const double *bv = B.sval + (size_t)s2 * D1 * D1 * TP + pl;
+#pragma unroll
+          for (int a = 0; a < D1; ++a)
+#pragma unroll
+            for (int q = 0; q < D1; ++q) w[a] = fma(bv[(a * D1 + q) * TP], x[q], w[a]);
+        }
+        for (int k = k0; k < k1; ++k) {
+          const unsigned pk = B.spk[k];
+          const int lr = (int)(pk >> 30);
+          const double xg = k == k0 ? xs0 : (k == k0 + 1 ? xs1 : __ldcg(X + (size_t)(pk & kColMask) * r + cc));
+          const double xv = B.spv[k] * xg;
+#pragma unroll
+          for (int a = 0; a < D1; ++a) w[a] += (lr == a) ? xv : 0.0;
+        }
+        const int o = geo.pose_base(pl) + cc;
+#pragma unroll
+        for (int a = 0; a < D1; ++a) sW[o + a * RS] = w[a];
+      }
+      __syncwarp();
+      const int np_here = min(PPW, T.nP - pg);
+      if (MODE != QM_SPMM) {
+        // step 2: tangent projection, D lanes per pose (lane e -> pose e / D, row e % D)
+        if (lane < np_here * D) {
+          const int p2 = pg + lane / D, a = lane % D;
+          const int o = geo.pose_base(p2);
+          const double *y = sY + o, *wv = sW + o;
+          double Pr[D], Pc[D];
+#pragma unroll
+          for (int b = 0; b < D; ++b) { Pr[b] = 0.0; Pc[b] = 0.0; }
+          for (int k = 0; k < r; ++k) {
+            const double ya = y[a * RS + k], wa = wv[a * RS + k];
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+              Pr[b] = fma(ya, wv[b * RS + k], Pr[b]);
+              Pc[b] = fma(y[b * RS + k], wa, Pc[b]);
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < D; ++b) Pr[b] = 0.5 * (Pr[b] + Pc[b]);
+          if (MODE == QM_GRAD) {  // diagonal block of Q - Lambda for the Hessian phases
+            double *lg = lam + M.boff + p2;
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+              const int e = (a * D1 + b) * TP;
+              lg[e] = B.sval[e + p2] - Pr[b];
+            }
+          }
+          double *o2 = sO + o + a * RS;
+          for (int k = 0; k < r; ++k) {
+            double sv = wv[a * RS + k];
+#pragma unroll
+            for (int b = 0; b < D; ++b) sv = fma(-Pr[b], y[b * RS + k], sv);
+            o2[k] = sv;
+          }
+          if (a == 0)  // translation row: Euclidean, copied through
+            for (int k = 0; k < r; ++k) sO[o + D * RS + k] = wv[D * RS + k];
+        }
+        __syncwarp();
+      }
+      // step 3: the warp's np_here poses are D1 * r * np_here contiguous outputs
+      {
+        const int nout = np_here * D1 * r;
+        const long long gbase = T.ebase + (long long)pg * D1 * r;
+        for (int i = lane; i < nout; i += 32) {
+          const int pr = i / (D1 * r), rem = i - pr * D1 * r;
+          const int a = rem / r, k = rem - a * r;
+          const int so = geo.pose_base(pg + pr) + a * RS + k;
+          if (MODE == QM_SPMM) {
+            out[gbase + i] = sW[so];
+          } else if (MODE == QM_GRAD) {
+            const double wq = sW[so], g = sO[so], xv = sX[so];
+            out2[gbase + i] = wq;
+            out[gbase + i] = g;
+            acc[0] = fma(xv, wq, acc[0]);
+            acc[1] = fma(g, g, acc[1]);
+          } else {
+            const double g = sO[so], dd = sX[so];
+            out[gbase + i] = g;
+            acc[0] = fma(dd, g, acc[0]);
+            acc[1] = fma(g, g, acc[1]);
+            acc[2] = fma(dd, dd, acc[2]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---------------- scalar rows: PPW rows per warp step ----------------
+    for (int rg = warp * PPW; rg < T.nS; rg += nwarps * PPW) {
+      const int sr = rg + lp;
+      const bool active = lane_ok && sr < T.nS;
+      const int lrow = T.nP * D1 + sr;
+      const int row = T.row0 + lrow;
+      const int sidx = row - L.nPoseRows;
+      const bool is_range = row >= L.nPoseRows + L.l;
+      const int so = geo.soff(lrow, cc);
+      double w = 0.0, xo = 0.0;
+      if (active) {
+        const int u = T.nP + sr;
+        const int k0 = B.gptr[u], k1 = B.gptr[u + 1];
+        double xs0 = 0.0, xs1 = 0.0;
+        if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
+        if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
+        xo = sX[so];
+        const double dg = (MODE == QM_HESS) ? __ldcg(lamS + sidx) : __ldg(L.sdiag + sidx);
+        w = dg * xo;
+        if (k0 < k1) w = fma(B.spv[k0], xs0, w);
+        if (k0 + 1 < k1) w = fma(B.spv[k0 + 1], xs1, w);
+        for (int k = k0 + 2; k < k1; ++k) w = fma(B.spv[k], __ldcg(X + (size_t)(B.spk[k] & kColMask) * r + cc), w);
+        for (int q = M.lq0; q < M.lq1; ++q) {
+          if (L.long_grp[q] != L.n + sidx) continue;
+          w += hub[(q - M.lq0) * hs + cc];
+        }
+        sW[so] = w;
+      }
+      __syncwarp();
+      if (active) {
+        const long long e = T.ebase + (long long)lrow * r + cc;
+        if (MODE == QM_SPMM) {
+          out[e] = w;
+        } else {
+          const double yv = (MODE == QM_GRAD) ? xo : sY[so];
+          double sdot = 0.0;
+          if (is_range) {
+            const int o0 = geo.soff(lrow, 0);
+            for (int k = 0; k < r; ++k) sdot = fma(sY[o0 + k], sW[o0 + k], sdot);  // ObliqueManifold.cpp:16-27
+          }
+          const double g = is_range ? fma(-sdot, yv, w) : w;
+          out[e] = g;
+          if (MODE == QM_GRAD) {
+            out2[e] = w;
+            if (cc == 0) lamS[sidx] = __ldg(L.sdiag + sidx) - (is_range ? sdot : 0.0);
+            acc[0] = fma(xo, w, acc[0]);
+            acc[1] = fma(g, g, acc[1]);
+          } else {
+            acc[0] = fma(xo, g, acc[0]);
+            acc[1] = fma(g, g, acc[1]);
+            acc[2] = fma(xo, xo, acc[2]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    sub_end(c, PH_Q_QX);
+    if (MODE == QM_GRAD) asm volatile("fence.proxy.async.global;" ::: "memory");
+    tile_release<D, true, NV>(L, c, t, buf, X, Y, nullptr, bsrc);
+    sub_end(c, PH_Q_STORE);
+  }
+  ph_end(c, MODE == QM_HESS ? PH_HESS : PH_GRAD);
+}
+
 // STPCG update + preconditioner closure (IterativeSolvers.h:374-386, src/CORA.cpp:89-92):
 //   AXPY: R += alpha HP (tile pipeline)         then   V = proj_Y(z), z = R*dinv | R | Z
 //   acc[0] += <R, V>, acc[1] += <V, V>.   (S += alpha P is a separate flat pass: axpy_flat)

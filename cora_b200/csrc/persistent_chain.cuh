@@ -23,7 +23,11 @@ struct ChainDev {
   const int *rinc_ptr, *rinc_k, *rend_x, *bl_ptr, *bl_row;
   const double *rinc_e, *rdinv, *rend_e, *bl_val, *W, *SLinv;
   double *u, *Y;
+  // landmark reductions split in chunks of kLmChunk entries over all CTAs: partials [l][max chunks][r]
+  int max_rinc_chunks, max_bl_chunks;
+  double *part_pre, *part_bl;
 };
+constexpr int kLmChunk = 256;
 
 // CTA-wide reduction of one landmark's sparse column: out[c] = sum_q val[q] * X[row[q]*r + c]
 __device__ __forceinline__ void cta_sparse_dot(PCtx &c, int q0, int q1, const int *idx, const double *val,
@@ -57,19 +61,23 @@ __device__ __forceinline__ void chain_apply_persistent(const ChainDev &C, PCtx &
   const long long gtid = (long long)c.b * c.nth + c.tid, gsize = (long long)c.G * c.nth;
   double *Y = C.Y;
   ph_begin(c);
-  // ---- pre: Y = V on pose and landmark rows minus the range elimination (k_chain_pre) ----
-  for (int j = c.b; j < l; j += c.G) {
-    cta_sparse_dot(c, C.rinc_ptr[n + j], C.rinc_ptr[n + j + 1], C.rinc_k, C.rinc_e, C.rdinv, V, rg0, r, c.sW + c.nth);
-    if (c.tid < r) Y[(np + j) * r + c.tid] = (j == C.pinned_landmark) ? 0.0 : V[(np + j) * r + c.tid] - c.sW[c.nth + c.tid];
+  // ---- pre: Y = V on pose rows minus the range elimination (k_chain_pre); the landmark rows' reductions
+  // over their incident ranges are split in chunks over all CTAs and combined after the border phase ----
+  for (int item = c.b; item < l * C.max_rinc_chunks; item += c.G) {
+    const int j = item / C.max_rinc_chunks, ch = item - j * C.max_rinc_chunks;
+    const int q0 = C.rinc_ptr[n + j] + ch * kLmChunk, q1 = min(C.rinc_ptr[n + j + 1], q0 + kLmChunk);
+    if (q0 >= q1) continue;  // uniform per CTA
+    cta_sparse_dot(c, q0, q1, C.rinc_k, C.rinc_e, C.rdinv, V, rg0, r, c.sW + c.nth);
+    if (c.tid < r) C.part_pre[((size_t)j * C.max_rinc_chunks + ch) * r + c.tid] = c.sW[c.nth + c.tid];
     __syncthreads();
   }
   {
-    const size_t nE = np * r;
-    for (size_t e = (size_t)gtid; e < nE; e += (size_t)gsize) {
-      const size_t row = e / r;
-      const int cc = (int)(e - row * r);
+    const unsigned nE = (unsigned)(np * r), ur = (unsigned)r;
+    for (unsigned e = (unsigned)gtid; e < nE; e += (unsigned)gsize) {
+      const unsigned row = e / ur;
+      const int cc = (int)(e - row * ur);
       double v = V[e];
-      if ((int)(row % B) == B - 1) {
+      if (row % B == B - 1) {
         const int x = (int)(row / B);
         for (int q = C.rinc_ptr[x]; q < C.rinc_ptr[x + 1]; ++q)
           v -= C.rinc_e[q] * C.rdinv[C.rinc_k[q]] * V[(rg0 + C.rinc_k[q]) * r + cc];
@@ -107,37 +115,54 @@ __device__ __forceinline__ void chain_apply_persistent(const ChainDev &C, PCtx &
       grid_sync(c);
     }
   }
-  // ---- border: u_j = y_L[j] - sum B[row, j] y[row]  (k_chain_border) ----
+  // ---- border: partial sums of sum_B B[row, j] y[row] per (landmark, chunk)  (k_chain_border) ----
   if (l > 0) {
-    for (int j = c.b; j < l; j += c.G) {
-      cta_sparse_dot(c, C.bl_ptr[j], C.bl_ptr[j + 1], C.bl_row, C.bl_val, nullptr, Y, 0, r, c.sW + c.nth);
-      if (c.tid < r) C.u[(size_t)j * r + c.tid] = Y[(np + j) * r + c.tid] - c.sW[c.nth + c.tid];
+    for (int item = c.b; item < l * C.max_bl_chunks; item += c.G) {
+      const int j = item / C.max_bl_chunks, ch = item - j * C.max_bl_chunks;
+      const int q0 = C.bl_ptr[j] + ch * kLmChunk, q1 = min(C.bl_ptr[j + 1], q0 + kLmChunk);
+      if (q0 >= q1) continue;
+      cta_sparse_dot(c, q0, q1, C.bl_row, C.bl_val, nullptr, Y, 0, r, c.sW + c.nth);
+      if (c.tid < r) C.part_bl[((size_t)j * C.max_bl_chunks + ch) * r + c.tid] = c.sW[c.nth + c.tid];
       __syncthreads();
     }
     ph_end(c, PH_CH_BORDER);
     grid_sync(c);
   }
-  // ---- z_L = S_L^-1 u, computed by every CTA into shared memory (l x r values) ----
-  double *zL = c.sW;  // l * r doubles
+  // ---- every CTA: u_j = (v_L[j] - range partials) - border partials ; z_L = S_L^-1 u  (l x r values each,
+  // fixed summation order) ----
+  double *uS = c.sW, *zL = c.sW + l * r;
   for (int i = c.tid; i < l * r; i += c.nth) {
     const int jj = i / r, cc = i - jj * r;
-    double s = 0.0;
-    for (int j2 = 0; j2 < l; ++j2) s = fma(C.SLinv[(size_t)jj * l + j2], C.u[(size_t)j2 * r + cc], s);
-    zL[i] = (jj == C.pinned_landmark) ? 0.0 : s;
+    double y = 0.0;
+    if (jj != C.pinned_landmark) {
+      y = V[(np + jj) * r + cc];
+      const int nc = (C.rinc_ptr[n + jj + 1] - C.rinc_ptr[n + jj] + kLmChunk - 1) / kLmChunk;
+      for (int ch = 0; ch < nc; ++ch) y -= C.part_pre[((size_t)jj * C.max_rinc_chunks + ch) * r + cc];
+    }
+    const int nb = (C.bl_ptr[jj + 1] - C.bl_ptr[jj] + kLmChunk - 1) / kLmChunk;
+    for (int ch = 0; ch < nb; ++ch) y -= C.part_bl[((size_t)jj * C.max_bl_chunks + ch) * r + cc];
+    uS[i] = y;
+  }
+  __syncthreads();
+  for (int i = c.tid; i < l * r; i += c.nth) {
+    const int jj = i / r, cc = i - jj * r;
+    double sacc = 0.0;
+    for (int j2 = 0; j2 < l; ++j2) sacc = fma(C.SLinv[(size_t)jj * l + j2], uS[j2 * r + cc], sacc);
+    zL[i] = (jj == C.pinned_landmark) ? 0.0 : sacc;
   }
   __syncthreads();
   // ---- post: z_P = y_P - W z_L ; z_L ; ranges back-substituted  (k_chain_post) ----
   {
-    const size_t nE = (rg0 + m) * r;
+    const unsigned nE = (unsigned)((rg0 + m) * r), ur = (unsigned)r;
     auto zpose = [&](size_t row, int cc) -> double {
       if ((int)row == C.pinned_pose_row) return 0.0;
       double s = Y[row * r + cc];
       for (int j = 0; j < l; ++j) s = fma(-C.W[row * l + j], zL[(size_t)j * r + cc], s);
       return s;
     };
-    for (size_t e = (size_t)gtid; e < nE; e += (size_t)gsize) {
-      const size_t row = e / r;
-      const int cc = (int)(e - row * r);
+    for (unsigned e = (unsigned)gtid; e < nE; e += (unsigned)gsize) {
+      const unsigned row = e / ur;
+      const int cc = (int)(e - row * ur);
       double out;
       if (row < np) {
         out = zpose(row, cc);

@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
   double fx, gnorm, pgnorm, rv_cur;
   {
     double acc[3] = {0.0, 0.0, 0.0};
-    if (A.regpath & 2) qprod_hyb<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
+    if (A.regpath & 4) qprod_warp<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
+    else if (A.regpath & 2) qprod_hyb<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
     else qprod_phase<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
     grid_reduce<3>(acc, c, &t0);
     fx = 0.5 * acc[0];
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
     grid_sync(c);
     while (cg.state == 0) {
       double acc[3] = {0.0, 0.0, 0.0};
-      if (A.regpath & 2) qprod_hyb<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
+      if (A.regpath & 4) qprod_warp<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
+      else if (A.regpath & 2) qprod_hyb<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
       else qprod_phase<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
       grid_reduce<3>(acc, c, nullptr);
       if (c.tid == 0) cg_post_hess(&cg, acc[0], acc[1], acc[2]);
@@ -274,7 +276,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
     double fxp, gnorm_p, hHh;
     {
       double a6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      if (A.regpath & 2) {
+      if (A.regpath & 4) {
+        qprod_warp<D, QM_GRAD>(L, c, v[V_XP], nullptr, v[V_GRADP], v[V_GP], lp0, lamp, lamSp, a6);
+        qprod_warp<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_HP], nullptr, lp1, lamc, lamSc, a6 + 3);
+      } else if (A.regpath & 2) {
         qprod_hyb<D, QM_GRAD>(L, c, v[V_XP], nullptr, v[V_GRADP], v[V_GP], lp0, lamp, lamSp, a6);
         qprod_hyb<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_HP], nullptr, lp1, lamc, lamSc, a6 + 3);
       } else {
@@ -417,7 +422,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_spmm_persistent(const DevLayout
       hub_phase<D>(L, c, X, 1.0, nullptr, 0.0, lp0);
       grid_sync(c);
     }
-    if (A.regpath & 2) qprod_hyb<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
+    if (A.regpath & 4) qprod_warp<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
+    else if (A.regpath & 2) qprod_hyb<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
     else qprod_phase<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
     grid_sync(c);
   }

@@ -231,6 +231,9 @@ inline void persistent_configure(H *h, int r) {
     {  // the hub-row scratch of a tile lives in one vector slot
       const HostLayout &HL = h->HL;
       const size_t vstride = ((size_t)HL.TR * (r | 1) + HL.TP) & ~(size_t)1;
+      for (size_t q = 0; q < HL.long_grp.size(); ++q)
+        if (HL.long_grp[q] < HL.n) h->persistent_regpath &= ~4;  // pose hub groups: block-synchronous products
+      if (r > 16) h->persistent_regpath &= ~4;                    // one pose per warp step would idle half the lanes
       for (int t = 0; t < HL.numTiles; ++t) {
         const int q0 = HL.tile_long_ptr[t], q1 = HL.tile_long_ptr[t + 1];
         if (q1 == q0) continue;
@@ -347,8 +350,23 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
     cd.rinc_ptr = C->rinc_ptr.p; cd.rinc_k = C->rinc_k.p; cd.rend_x = C->rend_x.p; cd.bl_ptr = C->bl_ptr.p;
     cd.bl_row = C->bl_row.p; cd.rinc_e = C->rinc_e.p; cd.rdinv = C->rdinv.p; cd.rend_e = C->rend_e.p;
     cd.bl_val = C->bl_val.p; cd.W = C->W.p; cd.SLinv = C->SLinv.p; cd.u = C->u.p; cd.Y = C->Y.p;
+    {  // chunked landmark reductions
+      const ChainFactorHost &F = C->host;
+      int mr = 1, mb = 1;
+      for (int j = 0; j < cd.l; ++j) {
+        mr = std::max(mr, (int)((F.rinc_ptr[cd.n + j + 1] - F.rinc_ptr[cd.n + j] + kLmChunk - 1) / kLmChunk));
+        mb = std::max(mb, (int)((F.bl_ptr[j + 1] - F.bl_ptr[j] + kLmChunk - 1) / kLmChunk));
+      }
+      cd.max_rinc_chunks = mr; cd.max_bl_chunks = mb;
+      const size_t need = (size_t)std::max(cd.l, 1) * (mr + mb) * h->ws_r;
+      if (h->d_lmpart.n < need) h->d_lmpart.alloc(need);
+      cd.part_pre = h->d_lmpart.p;
+      cd.part_bl = h->d_lmpart.p + (size_t)std::max(cd.l, 1) * mr * h->ws_r;
+      if ((size_t)cd.n * h->DL.D1 * r >= (1ull << 31) || ((size_t)h->DL.N * r) >= (1ull << 31))
+        throw Error(CORA_B200_ERUNTIME, "persistent chain apply: problem too large for 32-bit element indices");
+    }
     const size_t vstride = ((size_t)h->DL.TR * (r | 1) + h->DL.TP) & ~(size_t)1;
-    if ((size_t)cd.l * r > 6 * vstride)
+    if (2 * (size_t)cd.l * r > 6 * vstride)
       throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many landmarks for the shared-memory border solve");
   }
   A.lam[0] = h->d_lamT.p; A.lam[1] = h->d_lamT.p + h->d_lamT.n / 2;
