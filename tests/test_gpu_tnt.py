@@ -129,3 +129,47 @@ def test_regularized_cholesky_tnt(lib, name, r):
     np.testing.assert_allclose(got.objective_values[:4], ref.objective_values[:4], rtol=1e-6)
     np.testing.assert_allclose(got.preconditioned_gradient_norms[:3], ref.preconditioned_gradient_norms[:3],
                                rtol=1e-6)
+
+
+@pytest.mark.parametrize("d,r", [(2, 2), (2, 4), (3, 3), (3, 8), (3, 9), (3, 12)])
+def test_warm_start_cg_heavy_all_ranks(lib, d, r):
+    """CG-heavy regime (warm start: STPCG runs tens of iterations per call) at ranks that exercise every
+    lane-group size of the register phases (2, 4, 8, 16) and the single-buffered tile pipeline (large r):
+    the leading outer iterations are reproduced step for step against the oracle."""
+    from cora_b200 import synthetic
+    n, l, m = 600, 3, 200
+    p = make_synthetic(n=n, l=l, m=m, d=d, seed=9, rank=r)
+    p.update_problem_data()
+    arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=9)
+    x0 = p.project_to_manifold(synthetic.perturbed_ground_truth(d, n, l, arrays, gt, r, seed=1))
+    ref = co.problem_tnt(p, x0, co.cora_tnt_params(max_iterations=12))
+    with make_handle(p) as h:
+        got = h.tnt(x0, _params(max_iterations=12))
+    assert sum(ref.inner_iterations) > 50
+    # step for step until the first long CG solves; after those, summation-order differences are amplified
+    # by the conditioning of the Newton systems, so the tail is compared to 1e-4
+    k = 7
+    assert got.inner_iterations[:k] == ref.inner_iterations[:k]
+    np.testing.assert_allclose(got.objective_values[:k], ref.objective_values[:k], rtol=1e-7)
+    np.testing.assert_allclose(got.gradient_norms[:k], ref.gradient_norms[:k], rtol=1e-5)
+    np.testing.assert_allclose(got.trust_region_radius[:k], ref.trust_region_radius[:k], rtol=1e-8)
+    np.testing.assert_allclose(got.objective_values[:10], ref.objective_values[:10], rtol=1e-4)
+
+
+@pytest.mark.parametrize("flags", ["0", "1", "3", "5"])
+def test_product_phase_variants_agree(lib, flags, monkeypatch):
+    """The four implementations of the hot phases (shared-memory epilogue, register update, hybrid,
+    warp-local) follow the same trajectory (CORA_B200_REG selects them)."""
+    from cora_b200 import synthetic
+    monkeypatch.setenv("CORA_B200_REG", flags)
+    d, r, n, l, m = 3, 5, 900, 4, 300
+    p = make_synthetic(n=n, l=l, m=m, d=d, seed=12, rank=r)
+    p.update_problem_data()
+    arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=12)
+    x0 = p.project_to_manifold(synthetic.perturbed_ground_truth(d, n, l, arrays, gt, r, seed=2))
+    ref = co.problem_tnt(p, x0, co.cora_tnt_params(max_iterations=10))
+    with make_handle(p) as h:
+        got = h.tnt(x0, _params(max_iterations=10))
+    assert got.inner_iterations[:7] == ref.inner_iterations[:7]
+    np.testing.assert_allclose(got.objective_values[:7], ref.objective_values[:7], rtol=1e-7)
+    np.testing.assert_allclose(got.objective_values[:10], ref.objective_values[:10], rtol=1e-4)
