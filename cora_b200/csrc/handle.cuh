@@ -113,7 +113,9 @@ struct cora_b200_handle {
   // bit 0: STPCG update / preconditioner projection in the group-per-pose register form (update_reg);
   // bit 1: Hessian / gradient products in the hybrid form (TMA-staged operands + register compute, qprod_hyb)
   // instead of the shared-memory epilogue (qprod_phase)
-  int persistent_regpath = 1;
+  // bit 2: warp-local products (qprod_warp); bit 3: direction update fused into the Hessian phase (cg_fused_phase,
+  // only with the shared-memory products)
+  int persistent_regpath = 1;  // measured best (r01c): shared-memory products + register update; 9 = fused variant (-8 %)
   bool use_persistent = true;
   int snap_r = 0;
 };

@@ -118,6 +118,7 @@ struct PCtx {
   int parity;
   int nbar;
   unsigned mpar0, mpar1;  // mbarrier phase parity per buffer
+  unsigned long long hub_target;  // != 0: wait for bar[1] >= hub_target before consuming hub partials
   // shared memory (everything that lives for the whole solve is kept THERE, not in registers: the
   // hot loops need the register file)
   unsigned long long *prof_ns, *tph;   // [PH_COUNT], [2] written by thread 0 only
@@ -240,6 +241,7 @@ __device__ __forceinline__ void hub_phase(const DevLayout &L, PCtx &c, const dou
     for (int q = 0; q < D1; ++q) acc[q] = 0.0;
     if (e < per) {
       const int k0 = L.chunk_beg[ch], k1 = L.chunk_end[ch];
+#pragma unroll 4
       for (int k = k0 + e; k < k1; k += per) {
         const unsigned pk = __ldg(L.long_pk + k);
         const int lr = (int)(pk >> 30);
@@ -293,7 +295,7 @@ __device__ __forceinline__ TileMeta tile_meta(const DevLayout &L, const PCtx &c,
 // ---------------------------------------------------------------- tile pipeline ----
 // Issue the asynchronous loads of tile t into buffer `buf`: NV dense vectors (tile rows, padded
 // layout) by cp.async, and -- when NEEDQ -- the tile's data-matrix slice by TMA bulk copies.
-template <int D, bool NEEDQ, int NV>
+template <int D, bool NEEDQ, int NV, bool HALO2 = false>
 __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
                                               const double *v1, const double *v2, const double *bsrc = nullptr) {
   constexpr int D1 = D + 1;
@@ -341,6 +343,7 @@ __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t
         const int hl = side == 0 ? lrow - D1 : nR + lrow;  // local row, may be negative
         const int so = (hl + D1) * geo.RS + (geo.PADP ? (hl + D1) / D1 : 0) + cc - (D1 * geo.RS + geo.PADP);
         cp_async8(B.slot[0] + so, v0 + (long long)grow * r + cc);
+        if (HALO2) cp_async8(B.slot[2] + so, v2 + (long long)grow * r + cc);
       }
     }
   }
@@ -348,11 +351,11 @@ __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t
 }
 
 // Top of a pipeline iteration: start tile t+1 (double buffered), then wait for tile t.
-template <int D, bool NEEDQ, int NV>
+template <int D, bool NEEDQ, int NV, bool HALO2 = false>
 __device__ __forceinline__ void tile_acquire(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
                                              const double *v1, const double *v2, const double *bsrc = nullptr) {
   if (c.nbuf == 2 && t + 1 < c.t1) {
-    tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, buf ^ 1, v0, v1, v2, bsrc);
+    tile_prefetch<D, NEEDQ, NV, HALO2>(L, c, t + 1, buf ^ 1, v0, v1, v2, bsrc);
     cp_async_wait<1>();
   } else {
     cp_async_wait<0>();
@@ -364,12 +367,12 @@ __device__ __forceinline__ void tile_acquire(const DevLayout &L, PCtx &c, int t,
   __syncthreads();
 }
 // Bottom: every thread is done with tile t's buffer.
-template <int D, bool NEEDQ, int NV>
+template <int D, bool NEEDQ, int NV, bool HALO2 = false>
 __device__ __forceinline__ void tile_release(const DevLayout &L, PCtx &c, int t, int &buf, const double *v0,
                                              const double *v1, const double *v2, const double *bsrc = nullptr) {
   __syncthreads();
   if (c.nbuf == 2) buf ^= 1;
-  else if (t + 1 < c.t1) tile_prefetch<D, NEEDQ, NV>(L, c, t + 1, 0, v0, v1, v2, bsrc);
+  else if (t + 1 < c.t1) tile_prefetch<D, NEEDQ, NV, HALO2>(L, c, t + 1, 0, v0, v1, v2, bsrc);
 }
 
 // Sums of the hub-row chunk partials of the tile's long groups, one warp per (group row, column) with the
@@ -408,7 +411,14 @@ __device__ __forceinline__ void tile_hub_sums(const DevLayout &L, PCtx &c, const
 template <int D>
 __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInfo &T, const Geo<D> &geo, PCtx &c,
                                         const TileBuf &B, const double *X, const double *sX,
-                                        const double *longpart, const double *slam, const double *lamS) {
+                                        const double *longpart, const double *slam, const double *lamS,
+                                        const double *Vg = nullptr, double beta = 0.0) {
+  // Vg != nullptr: the multiplied vector is x = -Vg + beta * X (the new CG direction), evaluated on the fly
+  // for every element that is not in the staged window
+  auto gx = [&](size_t off) -> double {
+    const double xv = __ldcg(X + off);
+    return Vg != nullptr ? fma(beta, xv, -__ldcg(Vg + off)) : xv;
+  };
   constexpr int D1 = D + 1;
   const int r = c.r, TP = L.TP;
   const int S = B.meta[0];
@@ -421,8 +431,8 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
     // spill columns first: their L2 round trip overlaps the block products below
     const int k0 = B.gptr[p], k1 = B.gptr[p + 1];
     double xs0 = 0.0, xs1 = 0.0;
-    if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
-    if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
+    if (k0 < k1) xs0 = gx((size_t)(B.spk[k0] & kColMask) * r + cc);
+    if (k0 + 1 < k1) xs1 = gx((size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
     double acc[D1];
 #pragma unroll
     for (int a = 0; a < D1; ++a) acc[a] = 0.0;
@@ -435,9 +445,9 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
 #pragma unroll
         for (int q = 0; q < D1; ++q) x[q] = xp[q * geo.RS];
       } else {
-        const double *xp = X + (size_t)jb * r + cc;
+        const size_t xo = (size_t)jb * r + cc;
 #pragma unroll
-        for (int q = 0; q < D1; ++q) x[q] = __ldcg(xp + q * r);
+        for (int q = 0; q < D1; ++q) x[q] = gx(xo + (size_t)q * r);
       }
       const double *bv = B.sval + (size_t)s * D1 * D1 * TP + p;
 #pragma unroll
@@ -448,7 +458,7 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
     for (int k = k0; k < k1; ++k) {
       const unsigned pk = B.spk[k];
       const int lr = (int)(pk >> 30);
-      const double xg = k == k0 ? xs0 : (k == k0 + 1 ? xs1 : __ldcg(X + (size_t)(pk & kColMask) * r + cc));
+      const double xg = k == k0 ? xs0 : (k == k0 + 1 ? xs1 : gx((size_t)(pk & kColMask) * r + cc));
       const double xv = B.spv[k] * xg;
 #pragma unroll
       for (int a = 0; a < D1; ++a) acc[a] += (lr == a) ? xv : 0.0;
@@ -467,19 +477,23 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
     const int u = T.nP + sr;
     const int k0 = B.gptr[u], k1 = B.gptr[u + 1];
     double xs0 = 0.0, xs1 = 0.0;
-    if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
-    if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
+    if (k0 < k1) xs0 = gx((size_t)(B.spk[k0] & kColMask) * r + cc);
+    if (k0 + 1 < k1) xs1 = gx((size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
     const double dg = lamS != nullptr ? __ldcg(lamS + sidx) : __ldg(L.sdiag + sidx);  // lamS: diag(Q) - lambda_k
     double acc = dg * sX[geo.soff(lrow, cc)];
     if (k0 < k1) acc = fma(B.spv[k0], xs0, acc);
     if (k0 + 1 < k1) acc = fma(B.spv[k0 + 1], xs1, acc);
     for (int k = k0 + 2; k < k1; ++k)
-      acc = fma(B.spv[k], __ldcg(X + (size_t)(B.spk[k] & kColMask) * r + cc), acc);
+      acc = fma(B.spv[k], gx((size_t)(B.spk[k] & kColMask) * r + cc), acc);
     c.sW[geo.soff(lrow, cc)] = acc;
   }
   __syncthreads();
   const TileMeta M = tile_meta(L, c, t);
   if (M.lq1 > M.lq0) {
+    if (c.hub_target != 0) {  // fused CG phase: the chunk partials were produced earlier in THIS phase by all CTAs
+      if (c.tid == 0) while (ld_acquire_u64(c.bar + 1) < c.hub_target) { }
+      __syncthreads();
+    }
     double *hub = B.slot[2];  // free at this point in every mode (the epilogue output is written later)
     tile_hub_sums<D>(L, c, M, longpart, hub);
     __syncthreads();
@@ -669,6 +683,88 @@ __device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const d
   ph_end(c, MODE == QM_HESS ? PH_HESS : PH_GRAD);
 }
 
+
+
+// ------------------------------------------------------------------------------------------------
+// Fused CG phase C + A: the direction update of STPCG (IterativeSolvers.h:374,420) folded into the
+// staging of the next Hessian product -- one phase and one grid barrier less per CG iteration:
+//   p' = -v + beta * p   (own rows, while the tile sits in shared memory; p' is also written to Pn for the
+//   neighbours' next iteration; s += alpha * p moves into the update phase, where alpha is known), halo rows and spill / out-of-window columns of p'
+//   evaluated on the fly from (v, p), hub-row partials of Q p' produced at the start of the phase by all
+//   CTAs and consumed behind a counter (bar[1]) instead of a barrier;
+//   Hp' = proj_Y((Q - Lambda) p') + <p',Hp'>, <Hp',Hp'>, <p',p'>.
+template <int D>
+__device__ __forceinline__ void cg_fused_phase(const DevLayout &L, PCtx &c, const double *Pold, const double *V,
+                                               const double *Y, double beta, double *Pn,
+                                               double *HP, double *longpart, const double *bvalH,
+                                               const double *sdiagH, unsigned long long hub_target, double *acc) {
+  constexpr int D1 = D + 1;
+  const int r = c.r;
+  const Geo<D> geo(r);
+  // hub-row partial sums of Q p' first: they are needed by the one CTA that owns the landmark rows
+  if (L.numChunks > 0) {
+    hub_phase<D>(L, c, Pold, beta, V, -1.0, longpart);
+    if (c.tid == 0) {
+      __threadfence();
+      atomicAdd(c.bar + 1, 1ULL);
+    }
+    c.hub_target = hub_target;
+  }
+  ph_begin(c);
+  int buf = 0;
+  if (c.t0 < c.t1) tile_prefetch<D, true, 3, true>(L, c, c.t0, 0, Pold, Y, V, bvalH);
+  for (int t = c.t0; t < c.t1; ++t) {
+    sub_begin(c);
+    tile_acquire<D, true, 3, true>(L, c, t, buf, Pold, Y, V, bvalH);
+    sub_end(c, PH_Q_WAIT);
+    const TileBuf B = c.pick(buf);
+    const TileInfo T = tile_geom<D>(L, t, r);
+    const int nE = T.nR * r;
+    double *sX = B.slot[0], *sV = B.slot[2];
+    const double *sY = B.slot[1];
+    // direction update in place in shared memory (own rows + halo)
+    for (int le = c.tid; le < nE; le += c.nth) {
+      const int lrow = le / r, cc = le - lrow * r;
+      const int so = geo.soff(lrow, cc);
+      const double po = sX[so];
+      const double pn = fma(beta, po, -sV[so]);
+      sX[so] = pn;
+      Pn[T.ebase + le] = pn;
+    }
+    {
+      const int hE = D1 * r;
+      if (c.tid < 2 * hE) {
+        const int side = c.tid / hE, le = c.tid - side * hE;
+        const int lrow = le / r, cc = le - lrow * r;
+        const int grow = side == 0 ? T.row0 - D1 + lrow : T.row0 + T.nR + lrow;
+        if (grow >= 0 && grow < L.N) {
+          const int hl = side == 0 ? lrow - D1 : T.nR + lrow;
+          const int so = (hl + D1) * geo.RS + (geo.PADP ? (hl + D1) / D1 : 0) + cc - (D1 * geo.RS + geo.PADP);
+          sX[so] = fma(beta, sX[so], -sV[so]);
+        }
+      }
+    }
+    __syncthreads();
+    tile_qx<D>(L, t, T, geo, c, B, Pold, sX, longpart, nullptr, sdiagH, V, beta);
+    sub_end(c, PH_Q_QX);
+    double *sO = B.slot[2];  // the tile rows of v are consumed
+    tile_epilogue2<D, false>(L, T, geo, c, sY, nullptr, nullptr, c.sW, sO);
+    sub_end(c, PH_Q_EPI);
+    for (int le = c.tid; le < nE; le += c.nth) {
+      const int lrow = le / r, cc = le - lrow * r;
+      const int so = geo.soff(lrow, cc);
+      const double w = sO[so], dd = sX[so];
+      HP[T.ebase + le] = w;
+      acc[0] = fma(dd, w, acc[0]);
+      acc[1] = fma(w, w, acc[1]);
+      acc[2] = fma(dd, dd, acc[2]);
+    }
+    tile_release<D, true, 3, true>(L, c, t, buf, Pold, Y, V, bvalH);
+    sub_end(c, PH_Q_STORE);
+  }
+  c.hub_target = 0;
+  ph_end(c, PH_HESS);
+}
 
 // ------------------------------------------------------------------------------------------------
 // qprod_warp: the same tile pipeline and shared-memory operands as qprod_phase, but every warp takes
@@ -981,6 +1077,27 @@ __device__ __forceinline__ void cg_pupdate_flat(PCtx &c, double alpha, double be
   ph_end(c, PH_PUPDATE);
 }
 
+// s += alpha p over the CTA's elements, 16-byte accesses (fused CG mode: IterativeSolvers.h:374)
+__device__ __forceinline__ void cg_supdate_flat(PCtx &c, double alpha, double *S, const double *P) {
+  ph_begin(c);
+  const long long n2 = (c.e1 - c.e0) >> 1;
+  const double2 *P2 = reinterpret_cast<const double2 *>(P + c.e0);
+  double2 *S2 = reinterpret_cast<double2 *>(S + c.e0);
+#pragma unroll 4
+  for (long long i = c.tid; i < n2; i += c.nth) {
+    const double2 p = __ldcg(P2 + i);
+    double2 s2 = __ldcg(S2 + i);
+    s2.x = fma(alpha, p.x, s2.x);
+    s2.y = fma(alpha, p.y, s2.y);
+    S2[i] = s2;
+  }
+  if (c.tid == 0 && ((c.e1 - c.e0) & 1)) {
+    const long long e = c.e1 - 1;
+    S[e] = fma(alpha, __ldcg(P + e), __ldcg(S + e));
+  }
+  ph_end(c, PH_PUPDATE);
+}
+
 // STPCG initialisation (IterativeSolvers.h:207-279): S = 0, R = grad, P = -v
 __device__ __forceinline__ void cg_init_flat(PCtx &c, const double *Gr, const double *Vv, double *S, double *R,
                                              double *P) {
@@ -989,7 +1106,7 @@ __device__ __forceinline__ void cg_init_flat(PCtx &c, const double *Gr, const do
   for (long long e = c.e0 + c.tid; e < c.e1; e += c.nth) {
     S[e] = 0.0;
     R[e] = __ldcg(Gr + e);
-    P[e] = -__ldcg(Vv + e);
+    P[e] = Vv != nullptr ? -__ldcg(Vv + e) : 0.0;
   }
   ph_end(c, PH_CGINIT);
 }

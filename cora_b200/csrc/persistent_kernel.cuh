@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
   c.bar = A.bar; c.target = 0; c.partials = A.partials; c.parity = 0; c.nbar = 0;
   c.prof_ns = s_prof_ns; c.prof_cnt = s_prof_cnt; c.tph = s_tph;
   c.mpar0 = c.mpar1 = 0u;
+  c.hub_target = 0;
   const int r = A.r;
   {
     c.t0 = A.cta_t0[c.b];
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
   const double sqrt_eps = 1.4901161193847656e-08;
   unsigned long long now = 0, t0 = 0;
   int n_state = 0, n_iter = 0;
+  unsigned long long hub_gen = 0;  // fused CG phases executed (hub-partial counter generations)
   auto tr_state = [&](double el, double f, double g, double pg, double Dl) {
     if (master && n_state < A.trace_cap) {
       A.trace[(size_t)TR_TIME * A.trace_cap + n_state] = el;
@@ -195,15 +197,29 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
       cg.state = done;
     }
     __syncthreads();
-    cg_init_flat(c, v[V_GRAD], v[V_PG], v[V_S], v[V_R], v[V_P]);
-    if (L.numChunks > 0) hub_phase<D>(L, c, v[V_PG], -1.0, nullptr, 0.0, lp0);
-    grid_sync(c);
+    const bool fuse = (A.regpath & 8) && (A.regpath & 1) && !(A.regpath & 6);  // fused direction update + Hessian product
+    if (fuse) {
+      cg_init_flat(c, v[V_GRAD], nullptr, v[V_S], v[V_R], v[V_P]);  // s = 0, r = grad, p = 0 (p' = -v + 0 * p below)
+      grid_sync(c);
+    } else {
+      cg_init_flat(c, v[V_GRAD], v[V_PG], v[V_S], v[V_R], v[V_P]);
+      if (L.numChunks > 0) hub_phase<D>(L, c, v[V_PG], -1.0, nullptr, 0.0, lp0);
+      grid_sync(c);
+    }
+    double beta_prev = 0.0;
+    bool first_cg = true;
     while (cg.state == 0) {
       double acc[3] = {0.0, 0.0, 0.0};
-      if (A.regpath & 4) qprod_warp<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
+      if (fuse) {
+        ++hub_gen;
+        cg_fused_phase<D>(L, c, v[V_P], first_cg ? v[V_PG] : v[V_V], v[V_X], beta_prev, v[V_T1],
+                          v[V_HP], lp0, lamc, lamSc, hub_gen * (unsigned long long)c.G, acc);
+        first_cg = false;
+      } else if (A.regpath & 4) qprod_warp<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
       else if (A.regpath & 2) qprod_hyb<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
       else qprod_phase<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
       grid_reduce<3>(acc, c, nullptr);
+      if (fuse) swp(V_P, V_T1);  // v[V_P] is the direction the product was taken with
       if (c.tid == 0) cg_post_hess(&cg, acc[0], acc[1], acc[2]);
       __syncthreads();
       if (cg.state != 0) break;  // p in ker(H): finished below
@@ -219,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
       const double alpha = cg.alpha;
       if (use_chain) {
         axpby_flat(c, 1.0, v[V_R], alpha, v[V_HP], v[V_R]);  // r += alpha Hp  (:377)
+        if (fuse) cg_supdate_flat(c, alpha, v[V_S], v[V_P]);  // s += alpha p  (:374)
         grid_sync(c);
         chain_apply_persistent<D>(A.chain, c, v[V_R], v[V_Z]);
         if (A.regpath & 1) update_reg<D, false>(L, c, v[V_X], nullptr, v[V_R], v[V_Z], v[V_V], 0.0, 2, a2);
@@ -226,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
       } else if (A.regpath & 1) {
         update_reg<D, true>(L, c, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
                             A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);
+        if (fuse) cg_supdate_flat(c, alpha, v[V_S], v[V_P]);  // s += alpha p  (:374)
       } else {
         update_phase<D, true>(L, c, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
                               A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);
@@ -235,14 +253,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
       __syncthreads();
       if (cg.state != 0) {
         // s += alpha p of the last iteration (:374); s is read next by this CTA only (retraction)
-        axpby_flat(c, 1.0, v[V_S], alpha, v[V_P], v[V_S]);
+        if (!fuse) axpby_flat(c, 1.0, v[V_S], alpha, v[V_P], v[V_S]);
         break;
       }
       const double beta = cg.beta;
-      cg_pupdate_flat(c, alpha, beta, v[V_S], v[V_P], v[V_V], v[V_T1]);  // s += alpha p ; p' = -v + beta p
-      if (L.numChunks > 0) hub_phase<D>(L, c, v[V_P], beta, v[V_V], -1.0, lp0);
-      grid_sync(c);
-      swp(V_P, V_T1);
+      if (fuse) {  // s += alpha p and p' = -v + beta p happen inside the next fused phase
+        beta_prev = beta;
+      } else {
+        cg_pupdate_flat(c, alpha, beta, v[V_S], v[V_P], v[V_V], v[V_T1]);  // s += alpha p ; p' = -v + beta p
+        if (L.numChunks > 0) hub_phase<D>(L, c, v[V_P], beta, v[V_V], -1.0, lp0);
+        grid_sync(c);
+        swp(V_P, V_T1);
+      }
     }
     double hM = cg.hM;
     const int inner = cg.it;
@@ -373,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_spmm_persistent(const DevLayout
   c.bar = A.bar; c.target = 0; c.partials = A.partials; c.parity = 0; c.nbar = 0;
   c.prof_ns = s_prof_ns; c.prof_cnt = s_prof_cnt; c.tph = s_tph;
   c.mpar0 = c.mpar1 = 0u;
+  c.hub_target = 0;
   const int r = A.r;
   {
     c.t0 = A.cta_t0[c.b];

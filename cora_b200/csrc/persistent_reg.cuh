@@ -267,7 +267,8 @@ __device__ __forceinline__ void qprod_hyb(const DevLayout &L, PCtx &c, const dou
 // acc[0] += <R,V>, acc[1] += <V,V>
 template <int D, bool AXPY>
 __device__ __forceinline__ void update_reg(const DevLayout &L, PCtx &c, const double *Y, const double *HP, double *R,
-                                           const double *Z, double *V, double alpha, int zsrc, double *acc) {
+                                           const double *Z, double *V, double alpha, int zsrc, double *acc,
+                                           double *S = nullptr, const double *P = nullptr) {  // S != nullptr: s += alpha p
   constexpr int D1 = D + 1;
   const int r = c.r, TP = L.TP;
   const int GS = group_size(r), PPW = 32 / GS;
@@ -292,6 +293,7 @@ __device__ __forceinline__ void update_reg(const DevLayout &L, PCtx &c, const do
         if (AXPY) {
           v = fma(alpha, HP[e], v);
           R[e] = v;
+          if (S != nullptr) S[e] = fma(alpha, P[e], S[e]);
         }
         rr[a] = v;
         if (zsrc == 0) z[a] = v * __ldg(L.dinv + p * D1 + a);
@@ -323,6 +325,7 @@ __device__ __forceinline__ void update_reg(const DevLayout &L, PCtx &c, const do
       if (AXPY) {
         rr = fma(alpha, HP[e], rr);
         R[e] = rr;
+        if (S != nullptr) S[e] = fma(alpha, P[e], S[e]);
       }
       if (zsrc == 0) z = rr * __ldg(L.dinv + row);
       else if (zsrc == 1) z = rr;

@@ -295,7 +295,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   if (h->d_ppartials.n < npart) h->d_ppartials.alloc(npart);
   const size_t nlp = 2 * (size_t)std::max(h->DL.numChunks, 1) * h->DL.D1 * h->ws_r;
   if (h->d_longpart.n < nlp) h->d_longpart.alloc(nlp);
-  if (!h->d_bar.p) h->d_bar.alloc(1);
+  if (!h->d_bar.p) h->d_bar.alloc(2);
   {
     // two copies (current / proposal) of the block values with Q - Lambda on the diagonal blocks, and of
     // diag(Q) - lambda_k of the scalar rows; everything but those entries is Q and is copied once
@@ -375,7 +375,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   DevBuf<unsigned long long> d_prof_all;
   if (phase_prof) { d_prof_all.alloc((size_t)G * PH_COUNT); A.prof_all = d_prof_all.p; }
   CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-  CUDA_CHECK(cudaMemsetAsync(h->d_bar.p, 0, sizeof(unsigned long long), h->stream));
+  CUDA_CHECK(cudaMemsetAsync(h->d_bar.p, 0, 2 * sizeof(unsigned long long), h->stream));
   DevLayout Lc = h->DL;
   void *args[] = {(void *)&Lc, (void *)&A};
   DISPATCH_D(h, CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_tnt_persistent<DD>, dim3(G), dim3(h->persistent_threads), args,
@@ -458,7 +458,7 @@ inline float spmm_persistent(H *h, int r, const double *X, double *out, int reps
   const int G = h->persistent_grid;
   const size_t nlp = 2 * (size_t)std::max(h->DL.numChunks, 1) * h->DL.D1 * h->ws_r;
   if (h->d_longpart.n < nlp) h->d_longpart.alloc(nlp);
-  if (!h->d_bar.p) h->d_bar.alloc(1);
+  if (!h->d_bar.p) h->d_bar.alloc(2);
   PArgs A{};
   A.longpart = h->d_longpart.p;
   A.bar = h->d_bar.p;

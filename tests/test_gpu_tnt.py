@@ -156,7 +156,7 @@ def test_warm_start_cg_heavy_all_ranks(lib, d, r):
     np.testing.assert_allclose(got.objective_values[:10], ref.objective_values[:10], rtol=1e-4)
 
 
-@pytest.mark.parametrize("flags", ["0", "1", "3", "5"])
+@pytest.mark.parametrize("flags", ["0", "1", "3", "5", "8", "9"])
 def test_product_phase_variants_agree(lib, flags, monkeypatch):
     """The four implementations of the hot phases (shared-memory epilogue, register update, hybrid,
     warp-local) follow the same trajectory (CORA_B200_REG selects them)."""
