@@ -26,6 +26,8 @@ def build(force=False, verbose=False):
            "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "--use_fast_math=false",
            "-o", LIB, os.path.join(SRC, "unity.cu"), "-lcudart"]
     cmd = [c for c in cmd if c != "--use_fast_math=false"]
+    if os.environ.get("CORA_B200_NVCC_DEFS"):
+        cmd[1:1] = os.environ["CORA_B200_NVCC_DEFS"].split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -6,6 +6,11 @@
 #include "persistent_chain.cuh"
 #include "persistent_reg.cuh"
 
+#ifndef CORA_PERSIST_THREADS
+#define CORA_PERSIST_THREADS 256  // CTA size the persistent kernels are compiled for ...
+#define CORA_PERSIST_MINB 2       // ... and resident CTAs per SM (register budget = 65536 / (threads * CTAs))
+#endif
+
 namespace cora_b200 {
 
 struct PArgs {
@@ -27,7 +32,7 @@ struct PArgs {
 
 // ============================================================ k_tnt_persistent ====
 template <int D>
-__global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout L, const PArgs A) {
+__global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt_persistent(const DevLayout L, const PArgs A) {
   constexpr int D1 = D + 1;
   extern __shared__ __align__(16) double smem[];
   __shared__ CgCtrl cg;
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tnt_persistent(const DevLayout 
 // `reps` data-matrix products out = Q X through the same tile pipeline (roofline leg of bench.py /
 // scripts/sweep_1m.py; Problem::dataMatrixProduct, src/CORA_problem.cpp:742-757).
 template <int D>
-__global__ void __launch_bounds__(kThreads, 2) k_spmm_persistent(const DevLayout L, const PArgs A, const double *X,
+__global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_spmm_persistent(const DevLayout L, const PArgs A, const double *X,
                                                                  double *out, int reps) {
   constexpr int D1 = D + 1;
   extern __shared__ __align__(16) double smem[];
