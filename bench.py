@@ -370,6 +370,22 @@ def run_ours(args):
         b_outer = 2 * q + 19 * V + 8 * N
         total_bytes = its_rank0 * ab["cg_iter"] + outer_rank0 * b_outer
         ach = total_bytes / t_kernel / 1e9
+        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (one launch of a smaller slice):
+        # the measured traffic / algorithmic ratio of that capture, scaled to this run's launch
+        traffic, traffic_note = None, None
+        try:
+            import csv
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01c_persistent_ncu_raw.csv"))))
+            hdr, units, vals = rows[0], rows[1], rows[2]
+            get = lambda name: float(vals[hdr.index(name)].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[hdr.index(name)]]
+            cap = get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
+            cap_alg = 160 * ab["cg_iter"] + 2 * b_outer          # the captured launch: 2 outer iterations, 160 CG iterations
+            traffic = cap / cap_alg * total_bytes / max(1, args.steps)
+            traffic_note = ("ncu --set full of one launch with 160 CG + 2 outer iterations (profiles/r01c_persistent_ncu_raw.csv): "
+                            "%.2f GB DRAM read+write vs %.2f GB algorithmic (ratio %.3f); scaled to this launch's algorithmic bytes"
+                            % (cap / 1e9, cap_alg / 1e9, cap / cap_alg))
+        except Exception:
+            pass
         phases = {}
         for k, (us, cnt) in prof.items():
             if cnt:
@@ -395,7 +411,7 @@ def run_ours(args):
                              "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": total_bytes / max(1, args.steps),
                              "avg_launch_us": 1e6 * t_kernel / max(1, args.steps), "launches_timed": args.steps,
-                             "traffic": None, "grid": grid,
+                             "traffic": traffic, "traffic_source": traffic_note, "grid": grid,
                              "timing": "CUDA events on the launching stream around every launch of the timed steps",
                              "phases_in_kernel_globaltimer_cta0": phases}}
         if not args.no_cpu_baseline and world == 1:
