@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
     c.qstride = c.nbv + c.spcap + (c.ncol + c.TRP + c.spcap) / 2;  // doubles (int regions are multiples of 4)
     c.smem = smem;
     c.sred = smem;
-    c.sbc = smem + 64;
-    c.qbase = 80;
+    c.sbc = smem + 128;  // sred: up to 16 warps x 8 partial sums
+    c.qbase = 144;
     const int after_q = c.qbase + c.nbuf * c.qstride;
     c.sW = smem + after_q;
     c.vbase = after_q + c.vstride;
@@ -419,8 +419,8 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_spm
     c.qstride = c.nbv + c.spcap + (c.ncol + c.TRP + c.spcap) / 2;  // doubles (int regions are multiples of 4)
     c.smem = smem;
     c.sred = smem;
-    c.sbc = smem + 64;
-    c.qbase = 80;
+    c.sbc = smem + 128;  // sred: up to 16 warps x 8 partial sums
+    c.qbase = 144;
     const int after_q = c.qbase + c.nbuf * c.qstride;
     c.sW = smem + after_q;
     c.vbase = after_q + c.vstride;

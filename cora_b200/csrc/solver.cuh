@@ -208,7 +208,7 @@ inline size_t persistent_smem(const H *h, int r, int nbuf) {
   const size_t pstride = (size_t)D1 * (r | 1) + ((D1 % 2 == 0) ? 1 : 0);
   const size_t vstride = ((size_t)h->DL.TR * (r | 1) + h->DL.TP + 2 * pstride + 1) & ~(size_t)1;
   const size_t qbuf = (nbv + spcap) * sizeof(double) + (ncol + h->DL.TRP + spcap) * sizeof(int);
-  return 80 * sizeof(double) + nbuf * qbuf + (1 + 3 * (size_t)nbuf) * vstride * sizeof(double);
+  return 144 * sizeof(double) + nbuf * qbuf + (1 + 3 * (size_t)nbuf) * vstride * sizeof(double);
 }
 
 // One cooperative launch runs the whole trust-region solve on the resident iterate.
@@ -216,7 +216,7 @@ inline size_t persistent_smem(const H *h, int r, int nbuf) {
 inline void persistent_configure(H *h, int r) {
   if (h->persistent_grid_r != r) {
     if (const char *e = getenv("CORA_B200_REG")) h->persistent_regpath = atoi(e);
-    if (const char *e = getenv("CORA_B200_PTHREADS")) h->persistent_threads = std::max(64, std::min(256, atoi(e)));
+    if (const char *e = getenv("CORA_B200_PTHREADS")) h->persistent_threads = std::max(64, std::min(1024, atoi(e)));
     // double-buffered tile pipeline when two CTAs of it fit on an SM, single-buffered otherwise
     size_t smem = 0;
     int nbuf = 2;
