@@ -120,7 +120,7 @@ SYMBOLS = [
     "cora_b200_tnt_resident", "cora_b200_spmm_resident", "cora_b200_certify", "cora_b200_saddle_escape",
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
-    "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile",
+    "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
     "cora_b200_select_best", "cora_b200_nccl_unique_id", "cora_b200_nccl_init", "cora_b200_nccl_destroy",
 ]
@@ -533,6 +533,11 @@ class Handle:
                                                  C.byref(grid), C.byref(bars)))
         prof = {name: (float(tot[i]), int(cnt[i])) for i, name in enumerate(self.PHASES[: n.value])}
         return prof, grid.value, bars.value
+
+    def get_work_vector(self, which, r):
+        out = np.empty((self.N, r), order="F")
+        _check(self._lib.cora_b200_get_work_vector(self._h, C.c_int(which), C.c_int(r), _p(out)))
+        return out
 
     def spmm_resident(self, reps):
         ms = C.c_float()

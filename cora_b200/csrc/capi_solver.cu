@@ -161,6 +161,16 @@ extern "C" int cora_b200_profile_read(cora_b200_t *h, int capacity, float *ms, i
   API_END
 }
 
+extern "C" int cora_b200_get_work_vector(cora_b200_t *h, int which, int r, double *out) {
+  API_BEGIN
+  require(h && out, "NULL argument");
+  require(which == 0 || which == 1, "which must be 0 (X) or 1 (Q*X)");
+  require(r > 0 && r <= h->ws_r, "no workspace of this rank");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  export_matrix(h, h->ws[which == 0 ? V_X : V_G].p, r, out);
+  API_END
+}
+
 extern "C" int cora_b200_phase_profile(cora_b200_t *h, int capacity, double *total_us, int64_t *count,
                                        int *n_kinds, int *grid, int64_t *barriers) {
   API_BEGIN

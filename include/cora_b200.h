@@ -185,6 +185,9 @@ int cora_b200_restore_iterate(cora_b200_t *h);
  * inside STPCG): enable with max_samples > 0, read back the milliseconds of each launch */
 int cora_b200_profile_hessvec(cora_b200_t *h, int max_samples);
 int cora_b200_profile_read(cora_b200_t *h, int capacity, float *ms, int *count);
+/* test hook: copy one of the handle's N x r work vectors out (reference layout).  which: 0 = resident
+ * iterate X, 1 = Q*X as left by cora_b200_spmm_resident / the last gradient evaluation. */
+int cora_b200_get_work_vector(cora_b200_t *h, int which, int r, double *out);
 /* in-kernel phase profile of the last persistent TNT call (CTA 0's %globaltimer): for each phase
  * kind k < *n_kinds, total_us[k] and count[k].  Kinds, in order: hub, grad, hess, update, pupdate,
  * retract, precond, cginit, sync, misc, q.wait, q.qx, q.epi, q.store, ch.pre, ch.fwd, ch.bwd,

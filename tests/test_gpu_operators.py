@@ -182,3 +182,51 @@ def test_regularized_cholesky_rejects_loop_closures(lib):
     p.update_problem_data()
     with pytest.raises(capi.NotImplementedInReference):
         make_handle(p, preconditioner=capi.PRECON_REG_CHOLESKY)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,r", [(2, 3), (3, 5), (3, 7), (3, 12)])
+def test_persistent_spmm_kernel(lib, d, r):
+    """The tile-pipelined data-matrix product that scripts/sweep_1m.py times (k_spmm_persistent) against Q @ X,
+    including landmark hub rows (more than 64 couplings) and a range-row tail."""
+    from synth import make_synthetic
+    p = make_synthetic(n=1500, l=3, m=900, d=d, seed=21, rank=r)
+    p.update_problem_data()
+    X = np.asfortranarray(np.random.default_rng(5).standard_normal((p.N, r)))
+    with make_handle(p) as h:
+        h.set_iterate(X)
+        assert h.spmm_resident(2) > 0
+        got = h.get_work_vector(1, r)
+    ref = p.Q @ X
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_full_size_tnt_against_cpu_port(lib):
+    """BASELINE configs[2] at full size (100k poses): the leading trust-region iterations of the persistent kernel
+    against the C++ CPU restatement (oracle/cpu_ref.cpp), and size-independent properties of the result."""
+    import os
+    from cora_b200 import capi, synthetic
+    from oracle import cpu_ref
+    d, n, l, m, r = 3, 100_000, 10, 20_000, 5
+    arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=42)
+    Q = capi.assemble(d, n, l, arrays)
+    m = len(arrays["rg_w"])
+    x0 = synthetic.perturbed_ground_truth(d, n, l, arrays, gt, r, seed=0)
+    prm = capi.default_tnt_params(max_iterations=8, max_TPCG_iterations=10, max_computation_time=0.0)
+    with capi.Handle(d, n, m, n + l, Q, preconditioner=capi.PRECON_JACOBI) as h:
+        x0 = h.project_to_manifold(x0)
+        got = h.tnt(x0, prm)
+        f_check = h.evaluate_objective(got.x)
+    R = cpu_ref.CpuRef(d, n, m, n + l, Q, preconditioner=1, threads=os.cpu_count() or 1)
+    ref = R.tnt(x0, prm)
+    assert got.inner_iterations == ref.inner_iterations
+    np.testing.assert_allclose(got.objective_values, ref.objective_values, rtol=1e-8)
+    np.testing.assert_allclose(got.trust_region_radius, ref.trust_region_radius, rtol=1e-8)
+    ov = got.objective_values
+    assert all(ov[i + 1] <= ov[i] for i in range(len(ov) - 1))
+    assert abs(f_check - got.f) <= 1e-8 * abs(got.f)   # f = 1/2 <x, Qx> cancels terms of order 1e9 here
+    B = got.x[: d * n].reshape(n, d, r)
+    assert np.abs(np.einsum("nir,njr->nij", B, B) - np.eye(d)).max() < 1e-10     # rotations on the Stiefel manifold
+    rows = got.x[d * n: d * n + m]
+    assert np.abs(np.linalg.norm(rows, axis=1) - 1).max() < 1e-12               # range rows on the sphere
