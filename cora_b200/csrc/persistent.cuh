@@ -52,6 +52,20 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
+// Geometry of a staged tile in the persistent kernels: UNPADDED, element (local row, column) at lrow * r + c,
+// i.e. exactly the global row-major layout -- so a tile's rows (plus one pose block of halo either side) of a
+// dense vector are ONE contiguous range and arrive by a single TMA bulk copy.  (kernels.cuh's Geo pads rows
+// and poses for its thread-per-pose epilogue; the mappings used here tolerate the occasional 2-way conflict.)
+template <int D>
+struct PGeo {
+  static constexpr int D1 = D + 1;
+  static constexpr int PADP = 0;
+  int r, RS;
+  __device__ __forceinline__ PGeo(int r_) : r(r_), RS(r_) {}
+  __device__ __forceinline__ int soff(int lrow, int c) const { return lrow * RS + c; }
+  __device__ __forceinline__ int pose_base(int p) const { return p * D1 * RS; }
+};
+
 // ---------------------------------------------------------------- async copies ----
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
@@ -94,7 +108,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, unsign
 
 // One staging buffer of the tile pipeline: the tile's slice of the data matrix (block-ELL values and
 // columns, spill group pointers / entries) filled by bulk copies, and three tile-row slots of dense
-// vectors (padded layout of Geo<D>) filled by 8-byte cp.async.
+// vectors (padded layout of PGeo<D>) filled by 8-byte cp.async.
 struct TileBuf {
   double *sval, *spv, *slam, *slot[3];
   int *scol, *gptr;
@@ -130,7 +144,7 @@ struct PCtx {
   // carve-up of the dynamic shared memory in doubles from `smem`: buffer k of the data-matrix slice
   // starts at qbase + k*qstride, vector slot j of buffer k at vbase + (k*3 + j)*vstride + pstride
   double *smem;
-  int qbase, qstride, vbase, vstride, pstride, nbv, spcap, ncol, TRP, nlam;
+  int qbase, qstride, vbase, vstride, pstride, hpad, nbv, spcap, ncol, TRP, nlam;
   __device__ __forceinline__ TileBuf pick(int buf) const {
     TileBuf B;
     double *q = smem + qbase + (nbuf == 2 ? buf : 0) * qstride;
@@ -141,7 +155,7 @@ struct PCtx {
     B.scol = qi;
     B.gptr = qi + ncol;
     B.spk = (unsigned *)(qi + ncol + TRP);
-    double *vb = smem + vbase + (nbuf == 2 ? buf : 0) * 3 * vstride + pstride;
+    double *vb = smem + vbase + (nbuf == 2 ? buf : 0) * 3 * vstride + hpad;
     B.slot[0] = vb;
     B.slot[1] = vb + vstride;
     B.slot[2] = vb + 2 * vstride;
@@ -176,6 +190,8 @@ __device__ __forceinline__ void sub_end(PCtx &c, int id) {
 }
 
 __device__ __forceinline__ void grid_sync(PCtx &c) {
+  // global data written with ordinary stores in this phase is read by TMA bulk copies (async proxy) in the next
+  asm volatile("fence.proxy.async.global;" ::: "memory");
   __syncthreads();
   ph_begin(c);
   if (c.tid == 0) {
@@ -299,74 +315,51 @@ template <int D, bool NEEDQ, int NV, bool HALO2 = false>
 __device__ __forceinline__ void tile_prefetch(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
                                               const double *v1, const double *v2, const double *bsrc = nullptr) {
   constexpr int D1 = D + 1;
+  if (c.tid != 0) return;  // everything is TMA: one thread arms the mbarrier and issues the bulk copies
   const int r = c.r;
-  const Geo<D> geo(r);
   const TileBuf B = c.pick(buf);
-  if (NEEDQ && c.tid == 0) {
-    const TileMeta M = tile_meta(L, c, t);
-    const int S = M.S, nsp = M.nsp;
-    B.meta[0] = S;
-    const unsigned bq = (unsigned)S * D1 * D1 * L.TP * 8u, bc = (unsigned)S * L.TP * 4u;
-    const unsigned bg = (unsigned)L.TRP * 4u, bp = (unsigned)nsp * 4u, bv = (unsigned)nsp * 8u;
-    mbar_expect_tx(B.mbar, bq + bc + bg + bp + bv);
-    if (S > 0) {
+  // dense vectors: tile rows + one pose block of halo either side = one contiguous, 16-byte aligned range
+  const long long e_row0 = (long long)t * L.TR * r;
+  const int nR = min(L.TR, L.N - t * L.TR);
+  const long long e_lo = t > 0 ? e_row0 - c.hpad : 0;
+  long long e_hi = min(((long long)t * L.TR + nR + D1) * r, (long long)L.N * r);
+  e_hi = (e_hi + 1) & ~1LL;  // the work vectors are allocated with slack beyond N * r
+  const unsigned vbytes = (unsigned)(e_hi - e_lo) * 8u;
+  unsigned total = NV * vbytes;
+  unsigned bq = 0, bc = 0, bg = 0, bp = 0, bv = 0;
+  TileMeta M;
+  if (NEEDQ) {
+    M = tile_meta(L, c, t);
+    B.meta[0] = M.S;
+    bq = (unsigned)M.S * D1 * D1 * L.TP * 8u; bc = (unsigned)M.S * L.TP * 4u;
+    bg = (unsigned)L.TRP * 4u; bp = (unsigned)M.nsp * 4u; bv = (unsigned)M.nsp * 8u;
+    total += bq + bc + bg + bp + bv;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to the buffer vs the copies
+  mbar_expect_tx(B.mbar, total);
+  const long long doff = e_lo - e_row0;  // <= 0: the halo before the tile sits in front of the slot pointer
+  if (NV > 0) bulk_g2s(B.slot[0] + doff, v0 + e_lo, vbytes, B.mbar);
+  if (NV > 1) bulk_g2s(B.slot[1] + doff, v1 + e_lo, vbytes, B.mbar);
+  if (NV > 2) bulk_g2s(B.slot[2] + doff, v2 + e_lo, vbytes, B.mbar);
+  if (NEEDQ) {
+    if (M.S > 0) {
       bulk_g2s(B.sval, (bsrc != nullptr ? bsrc : L.bval) + M.boff, bq, B.mbar);
       bulk_g2s(B.scol, L.bcol + M.coff, bc, B.mbar);
     }
     bulk_g2s(B.gptr, L.sp_gptr + (size_t)t * L.TRP, bg, B.mbar);
-    if (nsp > 0) {
+    if (M.nsp > 0) {
       bulk_g2s(B.spk, L.sp_pk + M.spoff, bp, B.mbar);
       bulk_g2s(B.spv, L.sp_val + M.spoff, bv, B.mbar);
     }
   }
-  const int row0 = t * L.TR;
-  const int nR = min(L.TR, L.N - row0);
-  const int nE = nR * r;
-  const long long eb = (long long)row0 * r;
-  for (int le = c.tid; le < nE; le += c.nth) {
-    const int lrow = le / r, cc = le - lrow * r;
-    const int so = geo.soff(lrow, cc);
-    if (NV > 0) cp_async8(B.slot[0] + so, v0 + eb + le);
-    if (NV > 1) cp_async8(B.slot[1] + so, v1 + eb + le);
-    if (NV > 2) cp_async8(B.slot[2] + so, v2 + eb + le);
-  }
-  if (NEEDQ) {
-    // halo of the multiplied vector: one pose block before and after the tile, so that the
-    // neighbours of an odometry chain never leave shared memory (slot pointers are one pose
-    // stride into their buffers; see the carve-up in the kernel)
-    const int hE = D1 * r;
-    if (c.tid < 2 * hE) {
-      const int side = c.tid / hE, le = c.tid - side * hE;
-      const int lrow = le / r, cc = le - lrow * r;
-      const int grow = side == 0 ? row0 - D1 + lrow : row0 + nR + lrow;
-      if (grow >= 0 && grow < L.N) {
-        const int hl = side == 0 ? lrow - D1 : nR + lrow;  // local row, may be negative
-        const int so = (hl + D1) * geo.RS + (geo.PADP ? (hl + D1) / D1 : 0) + cc - (D1 * geo.RS + geo.PADP);
-        cp_async8(B.slot[0] + so, v0 + (long long)grow * r + cc);
-        if (HALO2) cp_async8(B.slot[2] + so, v2 + (long long)grow * r + cc);
-      }
-    }
-  }
-  cp_async_commit();
 }
-
-// Top of a pipeline iteration: start tile t+1 (double buffered), then wait for tile t.
 template <int D, bool NEEDQ, int NV, bool HALO2 = false>
 __device__ __forceinline__ void tile_acquire(const DevLayout &L, PCtx &c, int t, int buf, const double *v0,
                                              const double *v1, const double *v2, const double *bsrc = nullptr) {
-  if (c.nbuf == 2 && t + 1 < c.t1) {
-    tile_prefetch<D, NEEDQ, NV, HALO2>(L, c, t + 1, buf ^ 1, v0, v1, v2, bsrc);
-    cp_async_wait<1>();
-  } else {
-    cp_async_wait<0>();
-  }
-  if (NEEDQ) {
-    mbar_wait(c.mbar + buf, buf ? c.mpar1 : c.mpar0);
-    if (buf) c.mpar1 ^= 1u; else c.mpar0 ^= 1u;
-  }
-  __syncthreads();
+  if (c.nbuf == 2 && t + 1 < c.t1) tile_prefetch<D, NEEDQ, NV, HALO2>(L, c, t + 1, buf ^ 1, v0, v1, v2, bsrc);
+  mbar_wait(c.mbar + buf, buf ? c.mpar1 : c.mpar0);
+  if (buf) c.mpar1 ^= 1u; else c.mpar0 ^= 1u;
 }
-// Bottom: every thread is done with tile t's buffer.
 template <int D, bool NEEDQ, int NV, bool HALO2 = false>
 __device__ __forceinline__ void tile_release(const DevLayout &L, PCtx &c, int t, int &buf, const double *v0,
                                              const double *v1, const double *v2, const double *bsrc = nullptr) {
@@ -409,7 +402,7 @@ __device__ __forceinline__ void tile_hub_sums(const DevLayout &L, PCtx &c, const
 // sW <- (Q X)[tile]; sX holds the tile rows of X plus one pose block of halo on either side
 // (staged), X is the global vector (columns outside the staged window, spill columns).
 template <int D>
-__device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInfo &T, const Geo<D> &geo, PCtx &c,
+__device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInfo &T, const PGeo<D> &geo, PCtx &c,
                                         const TileBuf &B, const double *X, const double *sX,
                                         const double *longpart, const double *slam, const double *lamS,
                                         const double *Vg = nullptr, double beta = 0.0) {
@@ -518,7 +511,7 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
 // src/CORA_problem.cpp:782-867 / StiefelProduct.cpp:38-55 / ObliqueManifold.cpp:16-27.
 // Contains block barriers: every thread of the CTA must call it.
 template <int D, bool CURV>
-__device__ __forceinline__ void tile_epilogue2(const DevLayout &L, const TileInfo &T, const Geo<D> &geo, PCtx &c,
+__device__ __forceinline__ void tile_epilogue2(const DevLayout &L, const TileInfo &T, const PGeo<D> &geo, PCtx &c,
                                                const double *sY, const double *sG, const double *sDd, double *sW,
                                                double *sOut, double *lam_out = nullptr, double *lamS_out = nullptr,
                                                const double *sv0 = nullptr) {
@@ -628,7 +621,7 @@ __device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const d
   constexpr int NV = (MODE == QM_HESS) ? 2 : 1;
   const double *lam_in = (MODE == QM_HESS) ? lam : nullptr;
   const int r = c.r;
-  const Geo<D> geo(r);
+  const PGeo<D> geo(r);
   ph_begin(c);
   int buf = 0;
   if (c.t0 < c.t1) tile_prefetch<D, true, NV>(L, c, c.t0, 0, X, Y, nullptr, lam_in);
@@ -700,7 +693,7 @@ __device__ __forceinline__ void cg_fused_phase(const DevLayout &L, PCtx &c, cons
                                                const double *sdiagH, unsigned long long hub_target, double *acc) {
   constexpr int D1 = D + 1;
   const int r = c.r;
-  const Geo<D> geo(r);
+  const PGeo<D> geo(r);
   // hub-row partial sums of Q p' first: they are needed by the one CTA that owns the landmark rows
   if (L.numChunks > 0) {
     hub_phase<D>(L, c, Pold, beta, V, -1.0, longpart);
@@ -739,7 +732,7 @@ __device__ __forceinline__ void cg_fused_phase(const DevLayout &L, PCtx &c, cons
         const int grow = side == 0 ? T.row0 - D1 + lrow : T.row0 + T.nR + lrow;
         if (grow >= 0 && grow < L.N) {
           const int hl = side == 0 ? lrow - D1 : T.nR + lrow;
-          const int so = (hl + D1) * geo.RS + (geo.PADP ? (hl + D1) / D1 : 0) + cc - (D1 * geo.RS + geo.PADP);
+          const int so = hl * geo.RS + cc;
           sX[so] = fma(beta, sX[so], -sV[so]);
         }
       }
@@ -779,7 +772,7 @@ __device__ __forceinline__ void qprod_warp(const DevLayout &L, PCtx &c, const do
   constexpr int D1 = D + 1;
   constexpr int NV = (MODE == QM_HESS) ? 2 : 1;
   const int r = c.r, TP = L.TP;
-  const Geo<D> geo(r);
+  const PGeo<D> geo(r);
   const int RS = geo.RS;
   const int PPW = 32 / r;                     // poses (or scalar rows) per warp step
   const int lane = c.tid & 31, warp = c.tid >> 5, nwarps = c.nth >> 5;
@@ -996,7 +989,7 @@ __device__ __forceinline__ void update_phase(const DevLayout &L, PCtx &c, const 
                                              double *acc) {
   constexpr int NV = 3;
   const int r = c.r;
-  const Geo<D> geo(r);
+  const PGeo<D> geo(r);
   const double *third = AXPY ? HP : (zsrc == 2 ? Z : Y);
   ph_begin(c);
   int buf = 0;
@@ -1123,9 +1116,15 @@ __device__ __forceinline__ void retract_phase(const DevLayout &L, PCtx &c, const
                                               const double *Gr, double *XP, double *acc) {
   constexpr int NV = 3;
   const int r = c.r;
-  const Geo<D> geo(r);
+  const PGeo<D> geo(r);
   double *sW = c.sW;
   ph_begin(c);
+  // S was last written by THIS CTA with ordinary stores (s += alpha p on the way out of STPCG) and no grid barrier
+  // lies in between: make those stores visible to the TMA reads below (async proxy reads L2, it does not see the
+  // SM's in-flight stores)
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncthreads();
   int buf = 0;
   if (c.t0 < c.t1) tile_prefetch<D, false, NV>(L, c, c.t0, 0, X, S, Gr);
   for (int t = c.t0; t < c.t1; ++t) {

@@ -56,13 +56,14 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
     c.e0 = (long long)c.t0 * L.TR * r;
     c.e1 = min((long long)c.t1 * L.TR, (long long)L.N) * r;
     if (c.e0 > c.e1) c.e0 = c.e1;
-    const Geo<D> geo(r);
+    const PGeo<D> geo(r);
     c.nbv = L.maxSlots * D1 * D1 * L.TP;              // doubles
     c.ncol = (L.maxSlots * L.TP + 3) & ~3;            // ints
     c.spcap = (L.maxTileSpill + 3) & ~3;              // entries
     c.TRP = L.TRP;
-    c.pstride = D1 * geo.RS + geo.PADP;
-    c.vstride = (L.TR * geo.RS + L.TP + 2 * c.pstride + 1) & ~1;
+    c.pstride = D1 * r;
+    c.hpad = (c.pstride + 1) & ~1;                              // halo in front of the tile rows, kept 16-byte aligned
+    c.vstride = (c.hpad + L.TR * r + c.pstride + 2 + 1) & ~1;  // + halo behind, + one element of copy rounding
     c.nlam = D * D * L.TP;
     c.qstride = c.nbv + c.spcap + (c.ncol + c.TRP + c.spcap) / 2;  // doubles (int regions are multiples of 4)
     c.smem = smem;
@@ -408,13 +409,14 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_spm
     c.e0 = (long long)c.t0 * L.TR * r;
     c.e1 = min((long long)c.t1 * L.TR, (long long)L.N) * r;
     if (c.e0 > c.e1) c.e0 = c.e1;
-    const Geo<D> geo(r);
+    const PGeo<D> geo(r);
     c.nbv = L.maxSlots * D1 * D1 * L.TP;              // doubles
     c.ncol = (L.maxSlots * L.TP + 3) & ~3;            // ints
     c.spcap = (L.maxTileSpill + 3) & ~3;              // entries
     c.TRP = L.TRP;
-    c.pstride = D1 * geo.RS + geo.PADP;
-    c.vstride = (L.TR * geo.RS + L.TP + 2 * c.pstride + 1) & ~1;
+    c.pstride = D1 * r;
+    c.hpad = (c.pstride + 1) & ~1;                              // halo in front of the tile rows, kept 16-byte aligned
+    c.vstride = (c.hpad + L.TR * r + c.pstride + 2 + 1) & ~1;  // + halo behind, + one element of copy rounding
     c.nlam = D * D * L.TP;
     c.qstride = c.nbv + c.spcap + (c.ncol + c.TRP + c.spcap) / 2;  // doubles (int regions are multiples of 4)
     c.smem = smem;

@@ -71,7 +71,7 @@ __device__ __forceinline__ void qprod_hyb(const DevLayout &L, PCtx &c, const dou
   constexpr int D1 = D + 1;
   constexpr int NV = (MODE == QM_HESS) ? 2 : 1;
   const int r = c.r, TP = L.TP;
-  const Geo<D> geo(r);
+  const PGeo<D> geo(r);
   const int GS = group_size(r), PPW = 32 / GS;
   const int lane = c.tid & 31, warp = c.tid >> 5, nwarps = c.nth >> 5;
   const int sub = lane / GS, cc = lane - sub * GS;

@@ -205,8 +205,8 @@ inline size_t persistent_smem(const H *h, int r, int nbuf) {
   const size_t nbv = (size_t)h->DL.maxSlots * D1 * D1 * h->DL.TP;
   const size_t ncol = ((size_t)h->DL.maxSlots * h->DL.TP + 3) & ~(size_t)3;
   const size_t spcap = ((size_t)h->DL.maxTileSpill + 3) & ~(size_t)3;
-  const size_t pstride = (size_t)D1 * (r | 1) + ((D1 % 2 == 0) ? 1 : 0);
-  const size_t vstride = ((size_t)h->DL.TR * (r | 1) + h->DL.TP + 2 * pstride + 1) & ~(size_t)1;
+  const size_t pstride = (size_t)D1 * r, hpad = (pstride + 1) & ~(size_t)1;
+  const size_t vstride = (hpad + (size_t)h->DL.TR * r + pstride + 2 + 1) & ~(size_t)1;
   const size_t qbuf = (nbv + spcap) * sizeof(double) + (ncol + h->DL.TRP + spcap) * sizeof(int);
   return 144 * sizeof(double) + nbuf * qbuf + (1 + 3 * (size_t)nbuf) * vstride * sizeof(double);
 }
@@ -230,7 +230,7 @@ inline void persistent_configure(H *h, int r) {
     h->persistent_smem = smem;
     {  // the hub-row scratch of a tile lives in one vector slot
       const HostLayout &HL = h->HL;
-      const size_t vstride = ((size_t)HL.TR * (r | 1) + HL.TP) & ~(size_t)1;
+      const size_t vstride = (size_t)HL.TR * r;
       for (size_t q = 0; q < HL.long_grp.size(); ++q)
         if (HL.long_grp[q] < HL.n) h->persistent_regpath &= ~4;  // pose hub groups: block-synchronous products
       if (r > 16) h->persistent_regpath &= ~4;                    // one pose per warp step would idle half the lanes
@@ -365,7 +365,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
       if ((size_t)cd.n * h->DL.D1 * r >= (1ull << 31) || ((size_t)h->DL.N * r) >= (1ull << 31))
         throw Error(CORA_B200_ERUNTIME, "persistent chain apply: problem too large for 32-bit element indices");
     }
-    const size_t vstride = ((size_t)h->DL.TR * (r | 1) + h->DL.TP) & ~(size_t)1;
+    const size_t vstride = (size_t)h->DL.TR * r;
     if (2 * (size_t)cd.l * r > 6 * vstride)
       throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many landmarks for the shared-memory border solve");
   }
