@@ -17,6 +17,13 @@
 #pragma once
 #include "persistent.cuh"
 
+#ifndef CORA_UPDATE_UNROLL
+#define CORA_UPDATE_UNROLL 2  // pose groups per warp step of update_reg
+#endif
+#ifndef CORA_UPDATE_UNROLL_SCALAR
+#define CORA_UPDATE_UNROLL_SCALAR 4  // scalar-row groups per warp step of update_reg
+#endif
+
 namespace cora_b200 {
 
 __device__ __forceinline__ double group_sum(double v, int GS) {
@@ -277,67 +284,106 @@ __device__ __forceinline__ void update_reg(const DevLayout &L, PCtx &c, const do
   const bool col_ok = cc < r;
   ph_begin(c);
   const int P0 = min(c.t0 * TP, L.n), P1 = min(c.t1 * TP, L.n);
-  for (int pb = P0 + warp * PPW; pb < P1; pb += nwarps * PPW) {
-    const int p = pb + sub;
-    const bool active = col_ok && p < P1;
-    double rr[D1], z[D1], y[D];
+  // U pose groups per warp step: all loads of the U groups are issued before the first dependent shuffle / store, which
+  // doubles the bytes in flight per warp (the phase is latency bound at 2 CTAs/SM).  The dot accumulation order per
+  // thread is unchanged (group 0 rows, then group 1 rows = the order of the one-group loop).
+  constexpr int U = CORA_UPDATE_UNROLL;
+  const int step = nwarps * PPW;
+  for (int pb = P0 + warp * PPW; pb < P1; pb += U * step) {
+    double rr[U][D1], z[U][D1], y[U][D], hp[U][D1], dv[U][D1];
+    bool act[U];
 #pragma unroll
-    for (int a = 0; a < D1; ++a) { rr[a] = 0.0; z[a] = 0.0; }
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * step + sub;
+      act[u] = col_ok && p < P1;
 #pragma unroll
-    for (int a = 0; a < D; ++a) y[a] = 0.0;
-    if (active) {
+      for (int a = 0; a < D1; ++a) { rr[u][a] = 0.0; z[u][a] = 0.0; hp[u][a] = 0.0; dv[u][a] = 0.0; }
 #pragma unroll
-      for (int a = 0; a < D1; ++a) {
-        const size_t e = ((size_t)p * D1 + a) * r + cc;
-        double v = R[e];
-        if (AXPY) {
-          v = fma(alpha, HP[e], v);
-          R[e] = v;
-          if (S != nullptr) S[e] = fma(alpha, P[e], S[e]);
+      for (int a = 0; a < D; ++a) y[u][a] = 0.0;
+      if (act[u]) {
+#pragma unroll
+        for (int a = 0; a < D1; ++a) {
+          const size_t e = ((size_t)p * D1 + a) * r + cc;
+          rr[u][a] = R[e];
+          if (AXPY) hp[u][a] = HP[e];
+          if (zsrc == 0) dv[u][a] = __ldg(L.dinv + p * D1 + a);
+          else if (zsrc == 2) z[u][a] = Z[e];
+          if (a < D) y[u][a] = Y[e];
         }
-        rr[a] = v;
-        if (zsrc == 0) z[a] = v * __ldg(L.dinv + p * D1 + a);
-        else if (zsrc == 1) z[a] = v;
-        else z[a] = Z[e];
-        if (a < D) y[a] = Y[e];
       }
     }
-    double Sm[D * D];
-    group_tangent<D>(y, z, GS, active, Sm);
-    if (active) {
 #pragma unroll
-      for (int a = 0; a < D1; ++a) {
-        V[((size_t)p * D1 + a) * r + cc] = z[a];
-        acc[0] = fma(rr[a], z[a], acc[0]);
-        acc[1] = fma(z[a], z[a], acc[1]);
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * step + sub;
+      if (act[u]) {
+#pragma unroll
+        for (int a = 0; a < D1; ++a) {
+          const size_t e = ((size_t)p * D1 + a) * r + cc;
+          double v = rr[u][a];
+          if (AXPY) {
+            v = fma(alpha, hp[u][a], v);
+            R[e] = v;
+            if (S != nullptr) S[e] = fma(alpha, P[e], S[e]);
+          }
+          rr[u][a] = v;
+          if (zsrc == 0) z[u][a] = v * dv[u][a];
+          else if (zsrc == 1) z[u][a] = v;
+        }
+      }
+      double Sm[D * D];
+      group_tangent<D>(y[u], z[u], GS, act[u], Sm);
+      if (act[u]) {
+#pragma unroll
+        for (int a = 0; a < D1; ++a) {
+          V[((size_t)p * D1 + a) * r + cc] = z[u][a];
+          acc[0] = fma(rr[u][a], z[u][a], acc[0]);
+          acc[1] = fma(z[u][a], z[u][a], acc[1]);
+        }
       }
     }
   }
   const int R0 = max(c.t0 * L.TR, L.nPoseRows), R1 = min(c.t1 * L.TR, L.N);
-  for (int rb = R0 + warp * PPW; rb < R1; rb += nwarps * PPW) {
-    const int row = rb + sub;
-    const bool active = col_ok && row < R1;
-    const bool is_range = row >= L.nPoseRows + L.l;
-    double rr = 0.0, z = 0.0, yv = 0.0;
-    if (active) {
-      const size_t e = (size_t)row * r + cc;
-      rr = R[e];
-      if (AXPY) {
-        rr = fma(alpha, HP[e], rr);
-        R[e] = rr;
-        if (S != nullptr) S[e] = fma(alpha, P[e], S[e]);
+  // scalar rows (landmark + range rows): 4 loads per row only, so US row groups per warp step keep enough bytes in
+  // flight; the CTAs that own these rows were the stragglers of the phase (40 us against a median of 25 us)
+  constexpr int US = CORA_UPDATE_UNROLL_SCALAR;
+  for (int rb = R0 + warp * PPW; rb < R1; rb += US * step) {
+    double rr[US], z[US], yv[US], hp[US], dv[US];
+    bool act[US];
+#pragma unroll
+    for (int u = 0; u < US; ++u) {
+      const int row = rb + u * step + sub;
+      act[u] = col_ok && row < R1;
+      rr[u] = 0.0; z[u] = 0.0; yv[u] = 0.0; hp[u] = 0.0; dv[u] = 0.0;
+      if (act[u]) {
+        const size_t e = (size_t)row * r + cc;
+        rr[u] = R[e];
+        if (AXPY) hp[u] = HP[e];
+        if (zsrc == 0) dv[u] = __ldg(L.dinv + row);
+        else if (zsrc == 2) z[u] = Z[e];
+        yv[u] = Y[e];
       }
-      if (zsrc == 0) z = rr * __ldg(L.dinv + row);
-      else if (zsrc == 1) z = rr;
-      else z = Z[e];
-      yv = Y[e];
     }
-    const double s = group_sum((active && is_range) ? yv * z : 0.0, GS);
-    if (active) {
-      if (is_range) z = fma(-s, yv, z);
-      V[(size_t)row * r + cc] = z;
-      acc[0] = fma(rr, z, acc[0]);
-      acc[1] = fma(z, z, acc[1]);
+#pragma unroll
+    for (int u = 0; u < US; ++u) {
+      const int row = rb + u * step + sub;
+      const bool is_range = row >= L.nPoseRows + L.l;
+      const size_t e = (size_t)row * r + cc;
+      if (act[u]) {
+        if (AXPY) {
+          rr[u] = fma(alpha, hp[u], rr[u]);
+          R[e] = rr[u];
+          if (S != nullptr) S[e] = fma(alpha, P[e], S[e]);
+        }
+        if (zsrc == 0) z[u] = rr[u] * dv[u];
+        else if (zsrc == 1) z[u] = rr[u];
+      }
+      const double sd = group_sum((act[u] && is_range) ? yv[u] * z[u] : 0.0, GS);
+      if (act[u]) {
+        if (is_range) z[u] = fma(-sd, yv[u], z[u]);
+        V[e] = z[u];
+        acc[0] = fma(rr[u], z[u], acc[0]);
+        acc[1] = fma(z[u], z[u], acc[1]);
+      }
     }
   }
   ph_end(c, AXPY ? PH_UPDATE : PH_PRECOND);
