@@ -460,25 +460,50 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
 #pragma unroll
     for (int a = 0; a < D1; ++a) c.sW[o + a * geo.RS] = acc[a];
   }
-  // scalar rows (landmarks, ranges): diagonal + spill; two gathers in flight per item
+  // scalar rows (landmarks, ranges): diagonal + spill.  The gathers of UQ items (2 each) are issued before the first
+  // dependent use and before any store to sW (a shared-memory store between the items would pin the order of the
+  // next item's shared loads), so a 192-row scalar tile is one L2 round trip instead of two or more.
   const int nSI = T.nS * r;
-#pragma unroll 2
-  for (int j = c.tid; j < nSI; j += c.nth) {
-    const int sr = j / r, cc = j - sr * r;
-    const int lrow = T.nP * D1 + sr;
-    const int sidx = T.row0 + lrow - L.nPoseRows;
-    const int u = T.nP + sr;
-    const int k0 = B.gptr[u], k1 = B.gptr[u + 1];
-    double xs0 = 0.0, xs1 = 0.0;
-    if (k0 < k1) xs0 = gx((size_t)(B.spk[k0] & kColMask) * r + cc);
-    if (k0 + 1 < k1) xs1 = gx((size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
-    const double dg = lamS != nullptr ? __ldcg(lamS + sidx) : __ldg(L.sdiag + sidx);  // lamS: diag(Q) - lambda_k
-    double acc = dg * sX[geo.soff(lrow, cc)];
-    if (k0 < k1) acc = fma(B.spv[k0], xs0, acc);
-    if (k0 + 1 < k1) acc = fma(B.spv[k0 + 1], xs1, acc);
-    for (int k = k0 + 2; k < k1; ++k)
-      acc = fma(B.spv[k], gx((size_t)(B.spk[k] & kColMask) * r + cc), acc);
-    c.sW[geo.soff(lrow, cc)] = acc;
+  constexpr int UQ = 4;
+  for (int j0 = c.tid; j0 < nSI; j0 += UQ * c.nth) {
+    int k0v[UQ], k1v[UQ], off[UQ];
+    double xs0[UQ], xs1[UQ], dgv[UQ], xd[UQ];
+#pragma unroll
+    for (int q = 0; q < UQ; ++q) {
+      const int j = j0 + q * c.nth;
+      k0v[q] = 0; k1v[q] = -1; off[q] = 0;
+      xs0[q] = 0.0; xs1[q] = 0.0; dgv[q] = 0.0; xd[q] = 0.0;
+      if (j < nSI) {
+        const int sr = j / r, cc = j - sr * r;
+        const int lrow = T.nP * D1 + sr;
+        const int sidx = T.row0 + lrow - L.nPoseRows;
+        const int u = T.nP + sr;
+        const int k0 = B.gptr[u], k1 = B.gptr[u + 1];
+        k0v[q] = k0; k1v[q] = k1;
+        if (k0 < k1) xs0[q] = gx((size_t)(B.spk[k0] & kColMask) * r + cc);
+        if (k0 + 1 < k1) xs1[q] = gx((size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
+        dgv[q] = lamS != nullptr ? __ldcg(lamS + sidx) : __ldg(L.sdiag + sidx);  // lamS: diag(Q) - lambda_k
+        off[q] = geo.soff(lrow, cc);
+        xd[q] = sX[off[q]];
+      }
+    }
+    double accq[UQ];
+#pragma unroll
+    for (int q = 0; q < UQ; ++q) {
+      const int k0 = k0v[q], k1 = k1v[q];
+      double acc = dgv[q] * xd[q];
+      if (k0 < k1) acc = fma(B.spv[k0], xs0[q], acc);
+      if (k0 + 1 < k1) acc = fma(B.spv[k0 + 1], xs1[q], acc);
+      if (k0 + 2 < k1) {
+        const int cc = (j0 + q * c.nth) % r;
+        for (int k = k0 + 2; k < k1; ++k)
+          acc = fma(B.spv[k], gx((size_t)(B.spk[k] & kColMask) * r + cc), acc);
+      }
+      accq[q] = acc;
+    }
+#pragma unroll
+    for (int q = 0; q < UQ; ++q)
+      if (j0 + q * c.nth < nSI) c.sW[off[q]] = accq[q];
   }
   __syncthreads();
   const TileMeta M = tile_meta(L, c, t);
