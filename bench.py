@@ -375,13 +375,13 @@ def run_ours(args):
         traffic, traffic_note = None, None
         try:
             import csv
-            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01e_persistent_ncu_raw.csv"))))
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01f_persistent_ncu_raw.csv"))))
             hdr, units, vals = rows[0], rows[1], rows[2]
             get = lambda name: float(vals[hdr.index(name)].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[hdr.index(name)]]
             cap = get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
             cap_alg = 160 * ab["cg_iter"] + 2 * b_outer          # the captured launch: 2 outer iterations, 160 CG iterations
             traffic = cap / cap_alg * total_bytes / max(1, args.steps)
-            traffic_note = ("ncu --set full of one launch with 160 CG + 2 outer iterations (profiles/r01e_persistent_ncu_raw.csv): "
+            traffic_note = ("ncu --set full of one launch with 160 CG + 2 outer iterations (profiles/r01f_persistent_ncu_raw.csv): "
                             "%.2f GB DRAM read+write vs %.2f GB algorithmic (ratio %.3f); scaled to this launch's algorithmic bytes"
                             % (cap / 1e9, cap_alg / 1e9, cap / cap_alg))
         except Exception:
