@@ -119,6 +119,7 @@ SYMBOLS = [
     "cora_b200_tnt_default_params", "cora_b200_tnt", "cora_b200_set_iterate", "cora_b200_get_iterate",
     "cora_b200_tnt_resident", "cora_b200_spmm_resident", "cora_b200_certify", "cora_b200_saddle_escape",
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
+    "cora_b200_strip_layout_roundtrip",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
     "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
@@ -213,8 +214,8 @@ def _p(a):
     return a.ctypes.data_as(_PD)
 
 
-def layout_roundtrip(d, n, m, nt, Q):
-    """Test hook: CSR -> internal layout -> CSR on the host (no GPU)."""
+def layout_roundtrip(d, n, m, nt, Q, strips=False):
+    """Test hook: CSR -> internal layout (-> strip layout of the streaming kernels) -> CSR on the host (no GPU)."""
     import scipy.sparse as sp
     Q = sp.csr_matrix(Q)
     rp = np.ascontiguousarray(Q.indptr, dtype=np.int32)
@@ -226,7 +227,8 @@ def layout_roundtrip(d, n, m, nt, Q):
     ova = np.zeros(max(nnz, 1), dtype=np.float64)
     stats = np.zeros(8, dtype=np.int64)
     i32 = C.POINTER(C.c_int32)
-    _check(load().cora_b200_layout_roundtrip(
+    fn = load().cora_b200_strip_layout_roundtrip if strips else load().cora_b200_layout_roundtrip
+    _check(fn(
         C.c_int(d), C.c_int(n), C.c_int(m), C.c_int(nt), rp.ctypes.data_as(i32), ci.ctypes.data_as(i32),
         _p(va), C.c_int64(nnz), orp.ctypes.data_as(i32), oci.ctypes.data_as(i32), _p(ova),
         stats.ctypes.data_as(C.POINTER(C.c_int64))))

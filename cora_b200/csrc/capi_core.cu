@@ -132,10 +132,30 @@ extern "C" int cora_b200_create(cora_b200_t **out, int device, void *stream, int
     h->d_sp_pk.upload(L.sp_pk, s); h->d_sp_val.upload(L.sp_val, s);
     if (const char *e = getenv("CORA_B200_TNT_PATH")) h->use_persistent = std::string(e) != "launch";
     h->d_diag.upload(L.diag, s);
-    { std::vector<double> inv(L.diag.size());
-      for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1.0 / L.diag[i];  // src/CORA_problem.cpp:616-618
+    { std::vector<double> inv(L.diag.size() + 2, 0.0);  // + slack: 16-byte bulk copies of odd row ranges
+      for (size_t i = 0; i < L.diag.size(); ++i) inv[i] = 1.0 / L.diag[i];  // src/CORA_problem.cpp:616-618
       h->d_dinv.upload(inv, s);
       CUDA_CHECK(cudaStreamSynchronize(s)); }
+    {  // strip layout for the streaming kernels (two copies of the diagonal slots: current / proposal point)
+      build_stream_layout(L, h->SH);
+      const StreamHost &S = h->SH;
+      h->d_rec_off.upload(S.rec_off, s);
+      h->d_rec.upload(S.rec, s);
+      h->d_diagQ.upload(S.diagQ, s);
+      h->d_sdiagP.upload(S.sdiagP, s);
+      h->d_diagL.alloc(2 * S.diagQ.size());
+      h->d_sdiagL.alloc(2 * S.sdiagP.size());
+      for (int k = 0; k < 2; ++k) {
+        CUDA_CHECK(cudaMemcpyAsync(h->d_diagL.p + k * S.diagQ.size(), S.diagQ.data(), S.diagQ.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(h->d_sdiagL.p + k * S.sdiagP.size(), S.sdiagP.data(), S.sdiagP.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+      }
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      std::vector<unsigned char>().swap(h->SH.rec);
+      std::vector<double>().swap(h->SH.diagQ);
+      if (const char *e = getenv("CORA_B200_STREAM")) h->allow_stream = atoi(e) != 0;
+      if (const char *e = getenv("CORA_B200_STREAM_STAGES")) h->stream_stages = std::max(2, std::min(kStreamMaxStages, atoi(e)));
+      if (const char *e = getenv("CORA_B200_STREAM_SCALAR_WEIGHT")) h->stream_scalar_weight = atof(e);
+    }
     h->d_partials.alloc((size_t)std::max(L.numTiles, h->sm_count * 8) * kNPart);
     h->d_scal.alloc(SC_COUNT);
     h->d_counter.alloc(4);
@@ -371,10 +391,10 @@ extern "C" int cora_b200_certificate_product(cora_b200_t *h, int r, const double
   API_END
 }
 
-extern "C" int cora_b200_layout_roundtrip(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
-                                          const int32_t *col, const double *val, int64_t nnz,
-                                          int32_t *out_rowptr, int32_t *out_col, double *out_val,
-                                          int64_t *stats) {
+namespace {
+int layout_roundtrip_impl(bool strips, int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
+                          const int32_t *col, const double *val, int64_t nnz, int32_t *out_rowptr,
+                          int32_t *out_col, double *out_val, int64_t *stats) {
   API_BEGIN
   require(rowptr && out_rowptr && stats, "NULL argument");
   HostLayout L;
@@ -383,7 +403,13 @@ extern "C" int cora_b200_layout_roundtrip(int d, int n_poses, int n_ranges, int 
   build_layout(L, d, n_poses, n_ranges, n_trans, rowptr, col, val, nnz, TR);
   std::vector<int32_t> rp, ci;
   std::vector<double> v;
-  layout_to_csr(L, rp, ci, v);
+  if (strips) {  // through the strip layout of the streaming kernels as well
+    StreamHost SH;
+    build_stream_layout(L, SH);
+    stream_to_csr(L, SH, rp, ci, v);
+  } else {
+    layout_to_csr(L, rp, ci, v);
+  }
   if ((int64_t)ci.size() > nnz) throw Error(CORA_B200_ERUNTIME, "layout round trip produced more entries than the input");
   std::memcpy(out_rowptr, rp.data(), rp.size() * sizeof(int32_t));
   if (!ci.empty()) {
@@ -394,6 +420,23 @@ extern "C" int cora_b200_layout_roundtrip(int d, int n_poses, int n_ranges, int 
   stats[4] = L.nnz_long; stats[5] = (int64_t)L.long_grp.size(); stats[6] = (int64_t)L.bval.size();
   stats[7] = (int64_t)ci.size();
   API_END
+}
+}  // namespace
+
+extern "C" int cora_b200_layout_roundtrip(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
+                                          const int32_t *col, const double *val, int64_t nnz,
+                                          int32_t *out_rowptr, int32_t *out_col, double *out_val,
+                                          int64_t *stats) {
+  return layout_roundtrip_impl(false, d, n_poses, n_ranges, n_trans, rowptr, col, val, nnz, out_rowptr, out_col,
+                               out_val, stats);
+}
+
+extern "C" int cora_b200_strip_layout_roundtrip(int d, int n_poses, int n_ranges, int n_trans,
+                                                const int32_t *rowptr, const int32_t *col, const double *val,
+                                                int64_t nnz, int32_t *out_rowptr, int32_t *out_col,
+                                                double *out_val, int64_t *stats) {
+  return layout_roundtrip_impl(true, d, n_poses, n_ranges, n_trans, rowptr, col, val, nnz, out_rowptr, out_col,
+                               out_val, stats);
 }
 
 // ------------------------------------------------------------------ assembly ----

@@ -164,10 +164,11 @@ extern "C" int cora_b200_profile_read(cora_b200_t *h, int capacity, float *ms, i
 extern "C" int cora_b200_get_work_vector(cora_b200_t *h, int which, int r, double *out) {
   API_BEGIN
   require(h && out, "NULL argument");
-  require(which == 0 || which == 1, "which must be 0 (X) or 1 (Q*X)");
+  require(which == 0 || which == 1 || (which >= 100 && which < 100 + V_COUNT),
+          "which must be 0 (X), 1 (Q*X) or 100 + work vector index (test hook)");
   require(r > 0 && r <= h->ws_r, "no workspace of this rank");
   CUDA_CHECK(cudaSetDevice(h->device));
-  export_matrix(h, h->ws[which == 0 ? V_X : V_G].p, r, out);
+  export_matrix(h, h->ws[which >= 100 ? which - 100 : (which == 0 ? V_X : V_G)].p, r, out);
   API_END
 }
 

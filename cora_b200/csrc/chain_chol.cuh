@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(128) k_chain_backward(const ChunkGeo G, int ld
 // Step 1 of the apply: Y = V on pose and landmark rows, minus the range elimination on the
 // translation rows; pinned rows zeroed.  Blocks [0, l) reduce one landmark each; the rest
 // cover the pose-section elements (flat).
-__global__ void __launch_bounds__(kThreads) k_chain_pre(int n, int l, int D1, int r, const double *__restrict__ V,
+static __global__ void __launch_bounds__(kThreads) k_chain_pre(int n, int l, int D1, int r, const double *__restrict__ V,
                                                         double *__restrict__ Y, const int *rinc_ptr,
                                                         const int *rinc_k, const double *rinc_e,
                                                         const double *rdinv, int pinned_pose_row,
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(kThreads) k_chain_pre(int n, int l, int D1, in
 
 // Step 3: u_j = y_L[j] - sum_B B[row, j] y[row]  (one CTA per landmark), then the last CTA
 // applies S_L^-1 (l x l) and writes z_L.
-__global__ void __launch_bounds__(kThreads) k_chain_border(int n, int l, int D1, int r, const double *__restrict__ Y,
+static __global__ void __launch_bounds__(kThreads) k_chain_border(int n, int l, int D1, int r, const double *__restrict__ Y,
                                                            const int *bl_ptr, const int *bl_row,
                                                            const double *bl_val, const double *SLinv, double *u,
                                                            double *zL, unsigned *counter, int pinned_landmark,
@@ -829,7 +829,7 @@ __global__ void __launch_bounds__(kThreads) k_chain_border(int n, int l, int D1,
 }
 
 // Step 4: z_P = y_P - W z_L ; z_L ; ranges back-substituted.
-__global__ void __launch_bounds__(kThreads) k_chain_post(int n, int l, int m, int D1, int r,
+static __global__ void __launch_bounds__(kThreads) k_chain_post(int n, int l, int m, int D1, int r,
                                                          const double *__restrict__ V, const double *__restrict__ Y,
                                                          const double *__restrict__ W, const double *__restrict__ zL,
                                                          const int *rend_x, const double *rend_e,

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "internal.cuh"
+#include "stream_layout.hpp"
 
 namespace cora_b200 {
 
@@ -110,12 +111,18 @@ struct cora_b200_handle {
   int trace_cap = 0;
   int persistent_grid = 0, persistent_grid_r = -1, persistent_nbuf = 0, persistent_threads = 256;
   size_t persistent_smem = 0;
-  // bit 0: STPCG update / preconditioner projection in the group-per-pose register form (update_reg);
-  // bit 1: Hessian / gradient products in the hybrid form (TMA-staged operands + register compute, qprod_hyb)
-  // instead of the shared-memory epilogue (qprod_phase)
-  // bit 2: warp-local products (qprod_warp); bit 3: direction update fused into the Hessian phase (cg_fused_phase,
-  // only with the shared-memory products)
-  int persistent_regpath = 1;  // measured best (r01c): shared-memory products + register update; 9 = fused variant (-8 %)
+  // strip layout of the data matrix (stream_layout.hpp) for the rank-specialised streaming kernels
+  cora_b200::StreamHost SH;
+  cora_b200::DevBuf<unsigned> d_rec_off;
+  cora_b200::DevBuf<unsigned char> d_rec;
+  cora_b200::DevBuf<double> d_diagQ, d_sdiagP, d_diagL, d_sdiagL;
+  cora_b200::DevBuf<int> d_warp_strip;
+  bool persistent_stream = false;   // the configured rank runs on a streaming kernel
+  int stream_stages = 2;            // ring depth per warp
+  int stream_stage_doubles = 0, stream_xw = 0, stream_yw = 0;
+  double stream_scalar_weight = 1.0;
+  bool allow_stream = true;
+  void *persistent_kfn = nullptr, *persistent_spmm_kfn = nullptr;
   bool use_persistent = true;
   int snap_r = 0;
 };

@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(const DevLayout L, const
 }
 
 // p = -v + beta p  (IterativeSolvers.h:420)
-__global__ void __launch_bounds__(kThreads) k_cg_pupdate(const CgCtrl *ctrl, const double *__restrict__ V,
+static __global__ void __launch_bounds__(kThreads) k_cg_pupdate(const CgCtrl *ctrl, const double *__restrict__ V,
                                                          double *__restrict__ P, long long nE) {
   if (*((volatile const int *)&ctrl->state) != 0) return;
   const double beta = ctrl->beta;
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_pupdate(const CgCtrl *ctrl, con
 // STPCG initialisation (IterativeSolvers.h:207-279): s = 0, r = g, p = -v and the
 // scalar state; v = P(g) and <g, v> were produced by the caller (TNT.h:383-392
 // computes the same preconditioned gradient for its stopping test).
-__global__ void __launch_bounds__(kThreads) k_cg_init(CgCtrl *ctrl, const double *scal, int rv_slot,
+static __global__ void __launch_bounds__(kThreads) k_cg_init(CgCtrl *ctrl, const double *scal, int rv_slot,
                                                       double Delta, int max_it, double kappa_fgr,
                                                       double theta, double eps,
                                                       const double *__restrict__ Gr,
@@ -995,7 +995,7 @@ __global__ void __launch_bounds__(kThreads) k_patch_certificate(const DevLayout 
 
 // ------------------------------------------------------------- layout changes ---
 // reference column-major N x r  ->  internal row-major (row permuted)
-__global__ void __launch_bounds__(kThreads) k_import(const int *__restrict__ int2ref, const double *__restrict__ src,
+static __global__ void __launch_bounds__(kThreads) k_import(const int *__restrict__ int2ref, const double *__restrict__ src,
                                                      double *__restrict__ dst, int N, int r, int src_cols) {
   const long long nE = (long long)N * r;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nE;
@@ -1004,7 +1004,7 @@ __global__ void __launch_bounds__(kThreads) k_import(const int *__restrict__ int
     dst[e] = c < src_cols ? src[(size_t)c * N + int2ref[row]] : 0.0;
   }
 }
-__global__ void __launch_bounds__(kThreads) k_export(const int *__restrict__ int2ref, const double *__restrict__ src,
+static __global__ void __launch_bounds__(kThreads) k_export(const int *__restrict__ int2ref, const double *__restrict__ src,
                                                      double *__restrict__ dst, int N, int r) {
   const long long nE = (long long)N * r;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nE;
@@ -1015,14 +1015,14 @@ __global__ void __launch_bounds__(kThreads) k_export(const int *__restrict__ int
 }
 
 // out = a*x + b*y (flat)
-__global__ void __launch_bounds__(kThreads) k_axpby(double a, const double *__restrict__ x, double b,
+static __global__ void __launch_bounds__(kThreads) k_axpby(double a, const double *__restrict__ x, double b,
                                                     const double *__restrict__ y, double *out, long long nE) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nE;
        e += (long long)gridDim.x * blockDim.x)
     out[e] = a * x[e] + (y != nullptr ? b * y[e] : 0.0);
 }
 // z = V * dinv  (Jacobi, src/CORA_problem.cpp:888-889)
-__global__ void __launch_bounds__(kThreads) k_jacobi(const double *__restrict__ dinv, const double *__restrict__ V,
+static __global__ void __launch_bounds__(kThreads) k_jacobi(const double *__restrict__ dinv, const double *__restrict__ V,
                                                      double *out, int r, long long nE) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nE;
        e += (long long)gridDim.x * blockDim.x)
@@ -1030,7 +1030,7 @@ __global__ void __launch_bounds__(kThreads) k_jacobi(const double *__restrict__ 
 }
 
 // Deterministic flat inner products: up to 2 pairs, one partial per CTA.
-__global__ void __launch_bounds__(kThreads) k_dot2(const double *__restrict__ a0, const double *__restrict__ b0,
+static __global__ void __launch_bounds__(kThreads) k_dot2(const double *__restrict__ a0, const double *__restrict__ b0,
                                                    const double *__restrict__ a1, const double *__restrict__ b1,
                                                    long long nE, double *partials, unsigned *counter,
                                                    double *scal, int slot) {

@@ -38,7 +38,7 @@ struct TntDev {  // results of one persistent TNT call (device -> host)
   unsigned long long prof_ns[24];  // CTA 0's time per phase kind (PhaseId)
   unsigned int prof_cnt[24];
 };
-enum PhaseId { PH_HUB = 0, PH_GRAD, PH_HESS, PH_UPDATE, PH_PUPDATE, PH_RETRACT, PH_PRECOND, PH_CGINIT, PH_SYNC, PH_MISC, PH_Q_WAIT, PH_Q_QX, PH_Q_EPI, PH_Q_STORE, PH_CH_PRE, PH_CH_FWD, PH_CH_BWD, PH_CH_BORDER, PH_CH_POST, PH_COUNT };
+enum PhaseId { PH_HUB = 0, PH_GRAD, PH_HESS, PH_UPDATE, PH_PUPDATE, PH_RETRACT, PH_PRECOND, PH_CGINIT, PH_SYNC, PH_MISC, PH_Q_WAIT, PH_Q_QX, PH_Q_EPI, PH_Q_STORE, PH_CH_PRE, PH_CH_FWD, PH_CH_BWD, PH_CH_BORDER, PH_CH_POST, PH_SMID, PH_COUNT };
 
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
@@ -132,7 +132,6 @@ struct PCtx {
   int parity;
   int nbar;
   unsigned mpar0, mpar1;  // mbarrier phase parity per buffer
-  unsigned long long hub_target;  // != 0: wait for bar[1] >= hub_target before consuming hub partials
   // shared memory (everything that lives for the whole solve is kept THERE, not in registers: the
   // hot loops need the register file)
   unsigned long long *prof_ns, *tph;   // [PH_COUNT], [2] written by thread 0 only
@@ -404,14 +403,8 @@ __device__ __forceinline__ void tile_hub_sums(const DevLayout &L, PCtx &c, const
 template <int D>
 __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInfo &T, const PGeo<D> &geo, PCtx &c,
                                         const TileBuf &B, const double *X, const double *sX,
-                                        const double *longpart, const double *slam, const double *lamS,
-                                        const double *Vg = nullptr, double beta = 0.0) {
-  // Vg != nullptr: the multiplied vector is x = -Vg + beta * X (the new CG direction), evaluated on the fly
-  // for every element that is not in the staged window
-  auto gx = [&](size_t off) -> double {
-    const double xv = __ldcg(X + off);
-    return Vg != nullptr ? fma(beta, xv, -__ldcg(Vg + off)) : xv;
-  };
+                                        const double *longpart, const double *slam, const double *lamS) {
+  auto gx = [&](size_t off) -> double { return __ldcg(X + off); };
   constexpr int D1 = D + 1;
   const int r = c.r, TP = L.TP;
   const int S = B.meta[0];
@@ -508,10 +501,6 @@ __device__ __forceinline__ void tile_qx(const DevLayout &L, int t, const TileInf
   __syncthreads();
   const TileMeta M = tile_meta(L, c, t);
   if (M.lq1 > M.lq0) {
-    if (c.hub_target != 0) {  // fused CG phase: the chunk partials were produced earlier in THIS phase by all CTAs
-      if (c.tid == 0) while (ld_acquire_u64(c.bar + 1) < c.hub_target) { }
-      __syncthreads();
-    }
     double *hub = B.slot[2];  // free at this point in every mode (the epilogue output is written later)
     tile_hub_sums<D>(L, c, M, longpart, hub);
     __syncthreads();
@@ -703,359 +692,6 @@ __device__ __forceinline__ void qprod_phase(const DevLayout &L, PCtx &c, const d
 
 
 
-// ------------------------------------------------------------------------------------------------
-// Fused CG phase C + A: the direction update of STPCG (IterativeSolvers.h:374,420) folded into the
-// staging of the next Hessian product -- one phase and one grid barrier less per CG iteration:
-//   p' = -v + beta * p   (own rows, while the tile sits in shared memory; p' is also written to Pn for the
-//   neighbours' next iteration; s += alpha * p moves into the update phase, where alpha is known), halo rows and spill / out-of-window columns of p'
-//   evaluated on the fly from (v, p), hub-row partials of Q p' produced at the start of the phase by all
-//   CTAs and consumed behind a counter (bar[1]) instead of a barrier;
-//   Hp' = proj_Y((Q - Lambda) p') + <p',Hp'>, <Hp',Hp'>, <p',p'>.
-template <int D>
-__device__ __forceinline__ void cg_fused_phase(const DevLayout &L, PCtx &c, const double *Pold, const double *V,
-                                               const double *Y, double beta, double *Pn,
-                                               double *HP, double *longpart, const double *bvalH,
-                                               const double *sdiagH, unsigned long long hub_target, double *acc) {
-  constexpr int D1 = D + 1;
-  const int r = c.r;
-  const PGeo<D> geo(r);
-  // hub-row partial sums of Q p' first: they are needed by the one CTA that owns the landmark rows
-  if (L.numChunks > 0) {
-    hub_phase<D>(L, c, Pold, beta, V, -1.0, longpart);
-    if (c.tid == 0) {
-      __threadfence();
-      atomicAdd(c.bar + 1, 1ULL);
-    }
-    c.hub_target = hub_target;
-  }
-  ph_begin(c);
-  int buf = 0;
-  if (c.t0 < c.t1) tile_prefetch<D, true, 3, true>(L, c, c.t0, 0, Pold, Y, V, bvalH);
-  for (int t = c.t0; t < c.t1; ++t) {
-    sub_begin(c);
-    tile_acquire<D, true, 3, true>(L, c, t, buf, Pold, Y, V, bvalH);
-    sub_end(c, PH_Q_WAIT);
-    const TileBuf B = c.pick(buf);
-    const TileInfo T = tile_geom<D>(L, t, r);
-    const int nE = T.nR * r;
-    double *sX = B.slot[0], *sV = B.slot[2];
-    const double *sY = B.slot[1];
-    // direction update in place in shared memory (own rows + halo)
-    for (int le = c.tid; le < nE; le += c.nth) {
-      const int lrow = le / r, cc = le - lrow * r;
-      const int so = geo.soff(lrow, cc);
-      const double po = sX[so];
-      const double pn = fma(beta, po, -sV[so]);
-      sX[so] = pn;
-      Pn[T.ebase + le] = pn;
-    }
-    {
-      const int hE = D1 * r;
-      if (c.tid < 2 * hE) {
-        const int side = c.tid / hE, le = c.tid - side * hE;
-        const int lrow = le / r, cc = le - lrow * r;
-        const int grow = side == 0 ? T.row0 - D1 + lrow : T.row0 + T.nR + lrow;
-        if (grow >= 0 && grow < L.N) {
-          const int hl = side == 0 ? lrow - D1 : T.nR + lrow;
-          const int so = hl * geo.RS + cc;
-          sX[so] = fma(beta, sX[so], -sV[so]);
-        }
-      }
-    }
-    __syncthreads();
-    tile_qx<D>(L, t, T, geo, c, B, Pold, sX, longpart, nullptr, sdiagH, V, beta);
-    sub_end(c, PH_Q_QX);
-    double *sO = B.slot[2];  // the tile rows of v are consumed
-    tile_epilogue2<D, false>(L, T, geo, c, sY, nullptr, nullptr, c.sW, sO);
-    sub_end(c, PH_Q_EPI);
-    for (int le = c.tid; le < nE; le += c.nth) {
-      const int lrow = le / r, cc = le - lrow * r;
-      const int so = geo.soff(lrow, cc);
-      const double w = sO[so], dd = sX[so];
-      HP[T.ebase + le] = w;
-      acc[0] = fma(dd, w, acc[0]);
-      acc[1] = fma(w, w, acc[1]);
-      acc[2] = fma(dd, dd, acc[2]);
-    }
-    tile_release<D, true, 3, true>(L, c, t, buf, Pold, Y, V, bvalH);
-    sub_end(c, PH_Q_STORE);
-  }
-  c.hub_target = 0;
-  ph_end(c, PH_HESS);
-}
-
-// ------------------------------------------------------------------------------------------------
-// qprod_warp: the same tile pipeline and shared-memory operands as qprod_phase, but every warp takes
-// floor(32 / r) whole poses of the tile through Q x -> Riemannian epilogue -> store on its own, with
-// __syncwarp() between the steps: two block barriers per tile (acquire / release) instead of five, a
-// slow warp (spill gathers) no longer stalls the other seven, and the warp's d+1 rows x r columns x
-// PPW poses are one contiguous range of the output, stored with full coalescing.
-template <int D, int MODE>
-__device__ __forceinline__ void qprod_warp(const DevLayout &L, PCtx &c, const double *X, const double *Y, double *out,
-                                           double *out2, const double *longpart, double *lam, double *lamS,
-                                           double *acc) {
-  constexpr int D1 = D + 1;
-  constexpr int NV = (MODE == QM_HESS) ? 2 : 1;
-  const int r = c.r, TP = L.TP;
-  const PGeo<D> geo(r);
-  const int RS = geo.RS;
-  const int PPW = 32 / r;                     // poses (or scalar rows) per warp step
-  const int lane = c.tid & 31, warp = c.tid >> 5, nwarps = c.nth >> 5;
-  const int lp = lane / r, cc = lane - lp * r;  // (pose within the warp step, column)
-  const bool lane_ok = lane < PPW * r;
-  const int pstride = D1 * RS + geo.PADP;
-  const double *bsrc = (MODE == QM_HESS) ? lam : nullptr;
-  ph_begin(c);
-  int buf = 0;
-  if (c.t0 < c.t1) tile_prefetch<D, true, NV>(L, c, c.t0, 0, X, Y, nullptr, bsrc);
-  for (int t = c.t0; t < c.t1; ++t) {
-    sub_begin(c);
-    tile_acquire<D, true, NV>(L, c, t, buf, X, Y, nullptr, bsrc);
-    sub_end(c, PH_Q_WAIT);
-    const TileBuf B = c.pick(buf);
-    const TileInfo T = tile_geom<D>(L, t, r);
-    const TileMeta M = tile_meta(L, c, t);
-    const double *sX = B.slot[0], *sY = (MODE == QM_HESS) ? B.slot[1] : B.slot[0];
-    double *sO = B.slot[2];
-    double *sW = c.sW;
-    const int S = B.meta[0];
-    const int winLo = max(T.row0 - D1, 0);
-    const int winHi = min(min(T.row0 + T.nR + D1, L.N), L.nPoseRows);
-    // hub sums of the tile's scalar hub rows live in the scalar-row part of sO, which this function never
-    // writes (tiles with POSE hub groups are routed to qprod_phase by the host: persistent_configure)
-    double *hub = sO + geo.soff(T.nP * D1, 0);
-    const int hs = r;
-    if (M.lq1 > M.lq0) {
-      tile_hub_sums<D>(L, c, M, longpart, hub);
-      __syncthreads();
-    }
-    // ---------------- pose blocks: PPW poses per warp step ----------------
-    for (int pg = warp * PPW; pg < T.nP; pg += nwarps * PPW) {
-      const int pl = pg + lp;
-      const bool active = lane_ok && pl < T.nP;
-      // step 1: (Q x) for (pose, column)
-      if (active) {
-        const int k0 = B.gptr[pl], k1 = B.gptr[pl + 1];
-        double xs0 = 0.0, xs1 = 0.0;
-        if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
-        if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
-        double w[D1];
-#pragma unroll
-        for (int a = 0; a < D1; ++a) w[a] = 0.0;
-        for (int s2 = 0; s2 < S; ++s2) {
-          const int jb = B.scol[s2 * TP + pl];
-          double x[D1];
-          if (jb >= winLo && jb + D1 <= winHi) {
-            const int lq = (jb - T.row0 + D1) / D1 - 1;
-            const double *xp = sX + lq * pstride + cc;
-#pragma unroll
-            for (int q = 0; q < D1; ++q) x[q] = xp[q * RS];
-          } else {
-            const double *xp = X + (size_t)jb * r + cc;
-#pragma unroll
-            for (int q = 0; q < D1; ++q) x[q] = __ldcg(xp + q * r);
-          }
-          const double *bv = B.sval + (size_t)s2 * D1 * D1 * TP + pl;
-#pragma unroll
-          for (int a = 0; a < D1; ++a)
-#pragma unroll
-            for (int q = 0; q < D1; ++q) w[a] = fma(bv[(a * D1 + q) * TP], x[q], w[a]);
-        }
-        for (int k = k0; k < k1; ++k) {
-          const unsigned pk = B.spk[k];
-          const int lr = (int)(pk >> 30);
-          const double xg = k == k0 ? xs0 : (k == k0 + 1 ? xs1 : __ldcg(X + (size_t)(pk & kColMask) * r + cc));
-          const double xv = B.spv[k] * xg;
-#pragma unroll
-          for (int a = 0; a < D1; ++a) w[a] += (lr == a) ? xv : 0.0;
-        }
-        const int o = geo.pose_base(pl) + cc;
-#pragma unroll
-        for (int a = 0; a < D1; ++a) sW[o + a * RS] = w[a];
-      }
-      __syncwarp();
-      const int np_here = min(PPW, T.nP - pg);
-      if (MODE != QM_SPMM) {
-        // step 2: tangent projection, D lanes per pose (lane e -> pose e / D, row e % D)
-        if (lane < np_here * D) {
-          const int p2 = pg + lane / D, a = lane % D;
-          const int o = geo.pose_base(p2);
-          const double *y = sY + o, *wv = sW + o;
-          double Pr[D], Pc[D];
-#pragma unroll
-          for (int b = 0; b < D; ++b) { Pr[b] = 0.0; Pc[b] = 0.0; }
-          for (int k = 0; k < r; ++k) {
-            const double ya = y[a * RS + k], wa = wv[a * RS + k];
-#pragma unroll
-            for (int b = 0; b < D; ++b) {
-              Pr[b] = fma(ya, wv[b * RS + k], Pr[b]);
-              Pc[b] = fma(y[b * RS + k], wa, Pc[b]);
-            }
-          }
-#pragma unroll
-          for (int b = 0; b < D; ++b) Pr[b] = 0.5 * (Pr[b] + Pc[b]);
-          if (MODE == QM_GRAD) {  // diagonal block of Q - Lambda for the Hessian phases
-            double *lg = lam + M.boff + p2;
-#pragma unroll
-            for (int b = 0; b < D; ++b) {
-              const int e = (a * D1 + b) * TP;
-              lg[e] = B.sval[e + p2] - Pr[b];
-            }
-          }
-          double *o2 = sO + o + a * RS;
-          for (int k = 0; k < r; ++k) {
-            double sv = wv[a * RS + k];
-#pragma unroll
-            for (int b = 0; b < D; ++b) sv = fma(-Pr[b], y[b * RS + k], sv);
-            o2[k] = sv;
-          }
-          if (a == 0)  // translation row: Euclidean, copied through
-            for (int k = 0; k < r; ++k) sO[o + D * RS + k] = wv[D * RS + k];
-        }
-        __syncwarp();
-      }
-      // step 3: the warp's np_here poses are D1 * r * np_here contiguous outputs
-      {
-        const int nout = np_here * D1 * r;
-        const long long gbase = T.ebase + (long long)pg * D1 * r;
-        for (int i = lane; i < nout; i += 32) {
-          const int pr = i / (D1 * r), rem = i - pr * D1 * r;
-          const int a = rem / r, k = rem - a * r;
-          const int so = geo.pose_base(pg + pr) + a * RS + k;
-          if (MODE == QM_SPMM) {
-            out[gbase + i] = sW[so];
-          } else if (MODE == QM_GRAD) {
-            const double wq = sW[so], g = sO[so], xv = sX[so];
-            out2[gbase + i] = wq;
-            out[gbase + i] = g;
-            acc[0] = fma(xv, wq, acc[0]);
-            acc[1] = fma(g, g, acc[1]);
-          } else {
-            const double g = sO[so], dd = sX[so];
-            out[gbase + i] = g;
-            acc[0] = fma(dd, g, acc[0]);
-            acc[1] = fma(g, g, acc[1]);
-            acc[2] = fma(dd, dd, acc[2]);
-          }
-        }
-      }
-      __syncwarp();
-    }
-    // ---------------- scalar rows: PPW rows per warp step ----------------
-    for (int rg = warp * PPW; rg < T.nS; rg += nwarps * PPW) {
-      const int sr = rg + lp;
-      const bool active = lane_ok && sr < T.nS;
-      const int lrow = T.nP * D1 + sr;
-      const int row = T.row0 + lrow;
-      const int sidx = row - L.nPoseRows;
-      const bool is_range = row >= L.nPoseRows + L.l;
-      const int so = geo.soff(lrow, cc);
-      double w = 0.0, xo = 0.0;
-      if (active) {
-        const int u = T.nP + sr;
-        const int k0 = B.gptr[u], k1 = B.gptr[u + 1];
-        double xs0 = 0.0, xs1 = 0.0;
-        if (k0 < k1) xs0 = __ldcg(X + (size_t)(B.spk[k0] & kColMask) * r + cc);
-        if (k0 + 1 < k1) xs1 = __ldcg(X + (size_t)(B.spk[k0 + 1] & kColMask) * r + cc);
-        xo = sX[so];
-        const double dg = (MODE == QM_HESS) ? __ldcg(lamS + sidx) : __ldg(L.sdiag + sidx);
-        w = dg * xo;
-        if (k0 < k1) w = fma(B.spv[k0], xs0, w);
-        if (k0 + 1 < k1) w = fma(B.spv[k0 + 1], xs1, w);
-        for (int k = k0 + 2; k < k1; ++k) w = fma(B.spv[k], __ldcg(X + (size_t)(B.spk[k] & kColMask) * r + cc), w);
-        for (int q = M.lq0; q < M.lq1; ++q) {
-          if (L.long_grp[q] != L.n + sidx) continue;
-          w += hub[(q - M.lq0) * hs + cc];
-        }
-        sW[so] = w;
-      }
-      __syncwarp();
-      if (active) {
-        const long long e = T.ebase + (long long)lrow * r + cc;
-        if (MODE == QM_SPMM) {
-          out[e] = w;
-        } else {
-          const double yv = (MODE == QM_GRAD) ? xo : sY[so];
-          double sdot = 0.0;
-          if (is_range) {
-            const int o0 = geo.soff(lrow, 0);
-            for (int k = 0; k < r; ++k) sdot = fma(sY[o0 + k], sW[o0 + k], sdot);  // ObliqueManifold.cpp:16-27
-          }
-          const double g = is_range ? fma(-sdot, yv, w) : w;
-          out[e] = g;
-          if (MODE == QM_GRAD) {
-            out2[e] = w;
-            if (cc == 0) lamS[sidx] = __ldg(L.sdiag + sidx) - (is_range ? sdot : 0.0);
-            acc[0] = fma(xo, w, acc[0]);
-            acc[1] = fma(g, g, acc[1]);
-          } else {
-            acc[0] = fma(xo, g, acc[0]);
-            acc[1] = fma(g, g, acc[1]);
-            acc[2] = fma(xo, xo, acc[2]);
-          }
-        }
-      }
-      __syncwarp();
-    }
-    sub_end(c, PH_Q_QX);
-    if (MODE == QM_GRAD) asm volatile("fence.proxy.async.global;" ::: "memory");
-    tile_release<D, true, NV>(L, c, t, buf, X, Y, nullptr, bsrc);
-    sub_end(c, PH_Q_STORE);
-  }
-  ph_end(c, MODE == QM_HESS ? PH_HESS : PH_GRAD);
-}
-
-// STPCG update + preconditioner closure (IterativeSolvers.h:374-386, src/CORA.cpp:89-92):
-//   AXPY: R += alpha HP (tile pipeline)         then   V = proj_Y(z), z = R*dinv | R | Z
-//   acc[0] += <R, V>, acc[1] += <V, V>.   (S += alpha P is a separate flat pass: axpy_flat)
-template <int D, bool AXPY>
-__device__ __forceinline__ void update_phase(const DevLayout &L, PCtx &c, const double *Y, const double *HP,
-                                             double *R, const double *Z, double *V, double alpha, int zsrc,
-                                             double *acc) {
-  constexpr int NV = 3;
-  const int r = c.r;
-  const PGeo<D> geo(r);
-  const double *third = AXPY ? HP : (zsrc == 2 ? Z : Y);
-  ph_begin(c);
-  int buf = 0;
-  if (c.t0 < c.t1) tile_prefetch<D, false, NV>(L, c, c.t0, 0, R, Y, third);
-  for (int t = c.t0; t < c.t1; ++t) {
-    tile_acquire<D, false, NV>(L, c, t, buf, R, Y, third);
-    const TileBuf B = c.pick(buf);
-    const TileInfo T = tile_geom<D>(L, t, r);
-    const int nE = T.nR * r;
-    double *sR = B.slot[0], *sY = B.slot[1], *s3 = B.slot[2];
-    double *sZ = c.sW;
-    for (int le = c.tid; le < nE; le += c.nth) {
-      const int lrow = le / r, cc = le - lrow * r;
-      const int so = geo.soff(lrow, cc);
-      double rr = sR[so];
-      if (AXPY) {
-        rr = fma(alpha, s3[so], rr);
-        R[T.ebase + le] = rr;
-        sR[so] = rr;
-      }
-      double z;
-      if (zsrc == 0) z = rr * __ldg(L.dinv + T.row0 + lrow);
-      else if (zsrc == 1) z = rr;
-      else z = s3[so];
-      sZ[so] = z;
-    }
-    __syncthreads();
-    tile_epilogue2<D, false>(L, T, geo, c, sY, nullptr, nullptr, sZ, s3);  // slot 2 is consumed: reuse as output
-    for (int le = c.tid; le < nE; le += c.nth) {
-      const int lrow = le / r, cc = le - lrow * r;
-      const int so = geo.soff(lrow, cc);
-      const double v = s3[so];
-      V[T.ebase + le] = v;
-      acc[0] = fma(sR[so], v, acc[0]);
-      acc[1] = fma(v, v, acc[1]);
-    }
-    tile_release<D, false, NV>(L, c, t, buf, R, Y, third);
-  }
-  ph_end(c, AXPY ? PH_UPDATE : PH_PRECOND);
-}
-
 // out = a*X + b*Y over the CTA's contiguous element range (Y may be nullptr); flat and unrolled
 __device__ __forceinline__ void axpby_flat(PCtx &c, double a, const double *X, double bcoef, const double *Y,
                                            double *out) {
@@ -1091,27 +727,6 @@ __device__ __forceinline__ void cg_pupdate_flat(PCtx &c, double alpha, double be
     const double p = __ldcg(P + e);
     S[e] = fma(alpha, p, __ldcg(S + e));
     Pn[e] = fma(beta, p, -__ldcg(V + e));
-  }
-  ph_end(c, PH_PUPDATE);
-}
-
-// s += alpha p over the CTA's elements, 16-byte accesses (fused CG mode: IterativeSolvers.h:374)
-__device__ __forceinline__ void cg_supdate_flat(PCtx &c, double alpha, double *S, const double *P) {
-  ph_begin(c);
-  const long long n2 = (c.e1 - c.e0) >> 1;
-  const double2 *P2 = reinterpret_cast<const double2 *>(P + c.e0);
-  double2 *S2 = reinterpret_cast<double2 *>(S + c.e0);
-#pragma unroll 4
-  for (long long i = c.tid; i < n2; i += c.nth) {
-    const double2 p = __ldcg(P2 + i);
-    double2 s2 = __ldcg(S2 + i);
-    s2.x = fma(alpha, p.x, s2.x);
-    s2.y = fma(alpha, p.y, s2.y);
-    S2[i] = s2;
-  }
-  if (c.tid == 0 && ((c.e1 - c.e0) & 1)) {
-    const long long e = c.e1 - 1;
-    S[e] = fma(alpha, __ldcg(P + e), __ldcg(S + e));
   }
   ph_end(c, PH_PUPDATE);
 }

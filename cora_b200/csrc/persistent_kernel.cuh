@@ -5,6 +5,7 @@
 #include "persistent.cuh"
 #include "persistent_chain.cuh"
 #include "persistent_reg.cuh"
+#include "stream.cuh"
 
 #ifndef CORA_PERSIST_THREADS
 #define CORA_PERSIST_THREADS 256  // CTA size the persistent kernels are compiled for ...
@@ -26,19 +27,77 @@ struct PArgs {
   double *lamS[2];               // lambda_k = (QY)_k . y_k per scalar row (0 for landmark rows)
   cora_b200_tnt_params p;
   int r, trace_cap, precond, nbuf;
-  int regpath;                   // 1: register/shuffle phases (persistent_reg.cuh), 0: shared-memory tile pipeline
+  StreamDev sd;                  // strip layout + ring geometry (kernels compiled for a fixed rank, R > 0)
   ChainDev chain;                // RegularizedCholesky factor (precond == CORA_B200_PRECON_REG_CHOLESKY)
 };
 
+// Set-up shared by the persistent kernels: contiguous tile range of the CTA, carve-up of the dynamic shared
+// memory (tile pipeline of persistent.cuh; with STREAM the data-matrix slice buffers are not needed: the
+// products run on the strip rings), per-warp ring of the streaming phases.
+template <int D, bool STREAM>
+__device__ __forceinline__ void persistent_setup(const DevLayout &L, const PArgs &A, PCtx &c, double *smem,
+                                                 TileMeta *s_tmeta, unsigned long long *s_mbar,
+                                                 unsigned long long *s_rbar, Ring &rg) {
+  constexpr int D1 = D + 1;
+  const int r = A.r;
+  c.t0 = A.cta_t0[c.b];
+  c.t1 = A.cta_t0[c.b + 1];
+  c.e0 = (long long)c.t0 * L.TR * r;
+  c.e1 = min((long long)c.t1 * L.TR, (long long)L.N) * r;
+  if (c.e0 > c.e1) c.e0 = c.e1;
+  c.nbv = STREAM ? 0 : L.maxSlots * D1 * D1 * L.TP;              // doubles
+  c.ncol = STREAM ? 0 : (L.maxSlots * L.TP + 3) & ~3;            // ints
+  c.spcap = STREAM ? 0 : (L.maxTileSpill + 3) & ~3;              // entries
+  c.TRP = STREAM ? 0 : L.TRP;
+  c.pstride = D1 * r;
+  c.hpad = (c.pstride + 1) & ~1;                              // halo in front of the tile rows, kept 16-byte aligned
+  c.vstride = (c.hpad + L.TR * r + c.pstride + 2 + 1) & ~1;  // + halo behind, + one element of copy rounding
+  c.nlam = D * D * L.TP;
+  c.qstride = c.nbv + c.spcap + (c.ncol + c.TRP + c.spcap) / 2;  // doubles (int regions are multiples of 4)
+  c.smem = smem;
+  c.sred = smem;
+  c.sbc = smem + 128;  // sred: up to 16 warps x 8 partial sums
+  c.qbase = 144;
+  const int after_q = c.qbase + c.nbuf * c.qstride;
+  c.sW = smem + after_q;
+  c.vbase = after_q + c.vstride;
+  c.tmeta = s_tmeta;
+  c.mbar = s_mbar;
+  if (!STREAM)
+    for (int i = c.tid; i < min(c.t1 - c.t0, kMaxTilesPerCta); i += c.nth) {
+      const int t = c.t0 + i;
+      TileMeta M;
+      M.boff = L.tile_boff[t]; M.coff = L.tile_coff[t]; M.spoff = L.tile_sp_off[t];
+      M.S = L.tile_slots[t]; M.nsp = L.tile_sp_cnt[t];
+      M.lq0 = L.tile_long_ptr[t]; M.lq1 = L.tile_long_ptr[t + 1];
+      s_tmeta[i] = M;
+    }
+  if (c.tid == 0) {
+    mbar_init(&s_mbar[0], 1);
+    mbar_init(&s_mbar[1], 1);
+    if (STREAM)
+      for (int i = 0; i < kStreamMaxWarps * kStreamMaxStages; ++i) mbar_init(&s_rbar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int warp = c.tid >> 5;
+  rg.base = smem + A.sd.ring_base + (size_t)warp * A.sd.nstage * A.sd.stage_doubles;
+  rg.bar = s_rbar + warp * kStreamMaxStages;
+  rg.par = 0u;
+}
+
 // ============================================================ k_tnt_persistent ====
-template <int D>
+// R > 0: the kernel is compiled for rank R and the data-matrix products and the preconditioned update run as
+// warp-autonomous streaming phases (stream.cuh); R == 0: any rank, tile pipeline of persistent.cuh.
+template <int D, int R>
 __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt_persistent(const DevLayout L, const PArgs A) {
   constexpr int D1 = D + 1;
+  constexpr bool STREAM = R > 0;
   extern __shared__ __align__(16) double smem[];
   __shared__ CgCtrl cg;
   __shared__ __align__(8) unsigned long long s_mbar[2];
+  __shared__ __align__(8) unsigned long long s_rbar[STREAM ? kStreamMaxWarps * kStreamMaxStages : 1];
   __shared__ int s_meta[2][4];
-  __shared__ TileMeta s_tmeta[kMaxTilesPerCta];
+  __shared__ TileMeta s_tmeta[STREAM ? 1 : kMaxTilesPerCta];
   __shared__ unsigned long long s_prof_ns[PH_COUNT], s_tph[2];
   __shared__ unsigned int s_prof_cnt[PH_COUNT];
   __shared__ double *s_v[V_COUNT];  // the work vectors by role; rotated by thread 0 (swp)
@@ -48,50 +107,14 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
   c.bar = A.bar; c.target = 0; c.partials = A.partials; c.parity = 0; c.nbar = 0;
   c.prof_ns = s_prof_ns; c.prof_cnt = s_prof_cnt; c.tph = s_tph;
   c.mpar0 = c.mpar1 = 0u;
-  c.hub_target = 0;
-  const int r = A.r;
+  const int r = STREAM ? R : A.r;
+  Ring rg;
   {
-    c.t0 = A.cta_t0[c.b];
-    c.t1 = A.cta_t0[c.b + 1];
-    c.e0 = (long long)c.t0 * L.TR * r;
-    c.e1 = min((long long)c.t1 * L.TR, (long long)L.N) * r;
-    if (c.e0 > c.e1) c.e0 = c.e1;
-    const PGeo<D> geo(r);
-    c.nbv = L.maxSlots * D1 * D1 * L.TP;              // doubles
-    c.ncol = (L.maxSlots * L.TP + 3) & ~3;            // ints
-    c.spcap = (L.maxTileSpill + 3) & ~3;              // entries
-    c.TRP = L.TRP;
-    c.pstride = D1 * r;
-    c.hpad = (c.pstride + 1) & ~1;                              // halo in front of the tile rows, kept 16-byte aligned
-    c.vstride = (c.hpad + L.TR * r + c.pstride + 2 + 1) & ~1;  // + halo behind, + one element of copy rounding
-    c.nlam = D * D * L.TP;
-    c.qstride = c.nbv + c.spcap + (c.ncol + c.TRP + c.spcap) / 2;  // doubles (int regions are multiples of 4)
-    c.smem = smem;
-    c.sred = smem;
-    c.sbc = smem + 128;  // sred: up to 16 warps x 8 partial sums
-    c.qbase = 144;
-    const int after_q = c.qbase + c.nbuf * c.qstride;
-    c.sW = smem + after_q;
-    c.vbase = after_q + c.vstride;
-    c.mbar = s_mbar;
     c.meta = &s_meta[0][0];
-    c.tmeta = s_tmeta;
-    for (int i = c.tid; i < min(c.t1 - c.t0, kMaxTilesPerCta); i += c.nth) {
-      const int t = c.t0 + i;
-      TileMeta M;
-      M.boff = L.tile_boff[t]; M.coff = L.tile_coff[t]; M.spoff = L.tile_sp_off[t];
-      M.S = L.tile_slots[t]; M.nsp = L.tile_sp_cnt[t];
-      M.lq0 = L.tile_long_ptr[t]; M.lq1 = L.tile_long_ptr[t + 1];
-      s_tmeta[i] = M;
-    }
+    persistent_setup<D, STREAM>(L, A, c, smem, s_tmeta, s_mbar, s_rbar, rg);
     if (c.tid < PH_COUNT) { s_prof_ns[c.tid] = 0; s_prof_cnt[c.tid] = 0; }
     if (c.tid < V_COUNT) { s_v[c.tid] = A.v[c.tid]; s_perm[c.tid] = c.tid; }
-    if (c.tid == 0) {
-      s_tph[0] = s_tph[1] = 0;
-      mbar_init(&s_mbar[0], 1);
-      mbar_init(&s_mbar[1], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (c.tid == 0) s_tph[0] = s_tph[1] = 0;
     __syncthreads();
   }
   double *const *v = s_v;
@@ -107,12 +130,27 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
   const cora_b200_tnt_params &P = A.p;
   const size_t lpstride = (size_t)max(L.numChunks, 1) * D1 * r;
   double *lp0 = A.longpart, *lp1 = A.longpart + lpstride;
-  double *lamc = A.lam[0], *lamp = A.lam[1], *lamSc = A.lamS[0], *lamSp = A.lamS[1];
+  int lcur = 0;  // which copy of Q - Lambda belongs to the current iterate (the other one: the proposal)
+  // gradient phase at X: out = grad, out2 = Q X, writes copy `wl` of Q - Lambda;  acc: <X,QX>, <grad,grad>
+  auto grad_product = [&](const double *X, double *out, double *out2, const double *lp, int wl, double *acc) {
+    if constexpr (STREAM)
+      stream_qprod<D, R, QM_GRAD>(L, A.sd, c, rg, X, nullptr, out, out2, lp, nullptr, nullptr, A.sd.diagL[wl],
+                                  A.sd.sdiagL[wl], acc);
+    else
+      qprod_phase<D, QM_GRAD>(L, c, X, nullptr, out, out2, lp, A.lam[wl], A.lamS[wl], acc);
+  };
+  // Hessian product at base point Y with copy `wl` of Q - Lambda;  acc: <X,HX>, <HX,HX>, <X,X>
+  auto hess_product = [&](const double *X, const double *Y, double *out, const double *lp, int wl, double *acc) {
+    if constexpr (STREAM)
+      stream_qprod<D, R, QM_HESS>(L, A.sd, c, rg, X, Y, out, nullptr, lp, A.sd.diagL[wl], A.sd.sdiagL[wl], nullptr,
+                                  nullptr, acc);
+    else
+      qprod_phase<D, QM_HESS>(L, c, X, Y, out, nullptr, lp, A.lam[wl], A.lamS[wl], acc);
+  };
   const bool master = (c.b == 0 && c.tid == 0);
   const double sqrt_eps = 1.4901161193847656e-08;
   unsigned long long now = 0, t0 = 0;
   int n_state = 0, n_iter = 0;
-  unsigned long long hub_gen = 0;  // fused CG phases executed (hub-partial counter generations)
   auto tr_state = [&](double el, double f, double g, double pg, double Dl) {
     if (master && n_state < A.trace_cap) {
       A.trace[(size_t)TR_TIME * A.trace_cap + n_state] = el;
@@ -143,8 +181,8 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
       Zin = v[V_Z];
       zsrc = 2;
     }
-    if (A.regpath & 1) update_reg<D, false>(L, c, Y, nullptr, Rin, Zin, Vout, 0.0, zsrc, acc2);
-    else update_phase<D, false>(L, c, Y, nullptr, Rin, Zin, Vout, 0.0, zsrc, acc2);
+    if constexpr (STREAM) stream_update<D, R, false>(L, A.sd, c, rg, Y, nullptr, Rin, Zin, Vout, 0.0, zsrc, acc2);
+    else update_reg<D, false>(L, c, Y, nullptr, Rin, Zin, Vout, 0.0, zsrc, acc2);
   };
 
   if (A.prof_all != nullptr) {  // barrier latency calibration (profiling runs only)
@@ -160,9 +198,7 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
   double fx, gnorm, pgnorm, rv_cur;
   {
     double acc[3] = {0.0, 0.0, 0.0};
-    if (A.regpath & 4) qprod_warp<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
-    else if (A.regpath & 2) qprod_hyb<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
-    else qprod_phase<D, QM_GRAD>(L, c, v[V_X], nullptr, v[V_GRAD], v[V_G], lp0, lamc, lamSc, acc);
+    grad_product(v[V_X], v[V_GRAD], v[V_G], lp0, lcur, acc);
     grid_reduce<3>(acc, c, &t0);
     fx = 0.5 * acc[0];
     gnorm = sqrt(acc[1]);
@@ -203,29 +239,13 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
       cg.state = done;
     }
     __syncthreads();
-    const bool fuse = (A.regpath & 8) && (A.regpath & 1) && !(A.regpath & 6);  // fused direction update + Hessian product
-    if (fuse) {
-      cg_init_flat(c, v[V_GRAD], nullptr, v[V_S], v[V_R], v[V_P]);  // s = 0, r = grad, p = 0 (p' = -v + 0 * p below)
-      grid_sync(c);
-    } else {
-      cg_init_flat(c, v[V_GRAD], v[V_PG], v[V_S], v[V_R], v[V_P]);
-      if (L.numChunks > 0) hub_phase<D>(L, c, v[V_PG], -1.0, nullptr, 0.0, lp0);
-      grid_sync(c);
-    }
-    double beta_prev = 0.0;
-    bool first_cg = true;
+    cg_init_flat(c, v[V_GRAD], v[V_PG], v[V_S], v[V_R], v[V_P]);
+    if (L.numChunks > 0) hub_phase<D>(L, c, v[V_PG], -1.0, nullptr, 0.0, lp0);
+    grid_sync(c);
     while (cg.state == 0) {
       double acc[3] = {0.0, 0.0, 0.0};
-      if (fuse) {
-        ++hub_gen;
-        cg_fused_phase<D>(L, c, v[V_P], first_cg ? v[V_PG] : v[V_V], v[V_X], beta_prev, v[V_T1],
-                          v[V_HP], lp0, lamc, lamSc, hub_gen * (unsigned long long)c.G, acc);
-        first_cg = false;
-      } else if (A.regpath & 4) qprod_warp<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
-      else if (A.regpath & 2) qprod_hyb<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
-      else qprod_phase<D, QM_HESS>(L, c, v[V_P], v[V_X], v[V_HP], nullptr, lp0, lamc, lamSc, acc);
+      hess_product(v[V_P], v[V_X], v[V_HP], lp0, lcur, acc);
       grid_reduce<3>(acc, c, nullptr);
-      if (fuse) swp(V_P, V_T1);  // v[V_P] is the direction the product was taken with
       if (c.tid == 0) cg_post_hess(&cg, acc[0], acc[1], acc[2]);
       __syncthreads();
       if (cg.state != 0) break;  // p in ker(H): finished below
@@ -241,36 +261,28 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
       const double alpha = cg.alpha;
       if (use_chain) {
         axpby_flat(c, 1.0, v[V_R], alpha, v[V_HP], v[V_R]);  // r += alpha Hp  (:377)
-        if (fuse) cg_supdate_flat(c, alpha, v[V_S], v[V_P]);  // s += alpha p  (:374)
         grid_sync(c);
-        chain_apply_persistent<D>(A.chain, c, v[V_R], v[V_Z]);
-        if (A.regpath & 1) update_reg<D, false>(L, c, v[V_X], nullptr, v[V_R], v[V_Z], v[V_V], 0.0, 2, a2);
-        else update_phase<D, false>(L, c, v[V_X], nullptr, v[V_R], v[V_Z], v[V_V], 0.0, 2, a2);
-      } else if (A.regpath & 1) {
+        precond_project(v[V_X], v[V_R], v[V_V], a2);
+      } else if constexpr (STREAM) {
+        stream_update<D, R, true>(L, A.sd, c, rg, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
+                                  A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);
+      } else {
         update_reg<D, true>(L, c, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
                             A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);
-        if (fuse) cg_supdate_flat(c, alpha, v[V_S], v[V_P]);  // s += alpha p  (:374)
-      } else {
-        update_phase<D, true>(L, c, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
-                              A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);
       }
       grid_reduce<2>(a2, c, nullptr);
       if (c.tid == 0) cg_post_update(&cg, a2[0]);
       __syncthreads();
       if (cg.state != 0) {
         // s += alpha p of the last iteration (:374); s is read next by this CTA only (retraction)
-        if (!fuse) axpby_flat(c, 1.0, v[V_S], alpha, v[V_P], v[V_S]);
+        axpby_flat(c, 1.0, v[V_S], alpha, v[V_P], v[V_S]);
         break;
       }
       const double beta = cg.beta;
-      if (fuse) {  // s += alpha p and p' = -v + beta p happen inside the next fused phase
-        beta_prev = beta;
-      } else {
-        cg_pupdate_flat(c, alpha, beta, v[V_S], v[V_P], v[V_V], v[V_T1]);  // s += alpha p ; p' = -v + beta p
-        if (L.numChunks > 0) hub_phase<D>(L, c, v[V_P], beta, v[V_V], -1.0, lp0);
-        grid_sync(c);
-        swp(V_P, V_T1);
-      }
+      cg_pupdate_flat(c, alpha, beta, v[V_S], v[V_P], v[V_V], v[V_T1]);  // s += alpha p ; p' = -v + beta p
+      if (L.numChunks > 0) hub_phase<D>(L, c, v[V_P], beta, v[V_V], -1.0, lp0);
+      grid_sync(c);
+      swp(V_P, V_T1);
     }
     double hM = cg.hM;
     const int inner = cg.it;
@@ -304,16 +316,8 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
     double fxp, gnorm_p, hHh;
     {
       double a6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      if (A.regpath & 4) {
-        qprod_warp<D, QM_GRAD>(L, c, v[V_XP], nullptr, v[V_GRADP], v[V_GP], lp0, lamp, lamSp, a6);
-        qprod_warp<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_HP], nullptr, lp1, lamc, lamSc, a6 + 3);
-      } else if (A.regpath & 2) {
-        qprod_hyb<D, QM_GRAD>(L, c, v[V_XP], nullptr, v[V_GRADP], v[V_GP], lp0, lamp, lamSp, a6);
-        qprod_hyb<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_HP], nullptr, lp1, lamc, lamSc, a6 + 3);
-      } else {
-        qprod_phase<D, QM_GRAD>(L, c, v[V_XP], nullptr, v[V_GRADP], v[V_GP], lp0, lamp, lamSp, a6);
-        qprod_phase<D, QM_HESS>(L, c, v[V_S], v[V_X], v[V_HP], nullptr, lp1, lamc, lamSc, a6 + 3);
-      }
+      grad_product(v[V_XP], v[V_GRADP], v[V_GP], lp0, lcur ^ 1, a6);
+      hess_product(v[V_S], v[V_X], v[V_HP], lp1, lcur, a6 + 3);
       grid_reduce<6>(a6, c, nullptr);
       fxp = 0.5 * a6[0];
       gnorm_p = sqrt(a6[1]);
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
       }
       swp(V_G, V_GP);
       swp(V_GRAD, V_GRADP);
-      { double *tq = lamc; lamc = lamp; lamp = tq; tq = lamSc; lamSc = lamSp; lamSp = tq; }
+      lcur ^= 1;
       swp(V_PG, V_T0);
       rv_cur = rv_prop;
       gnorm = gnorm_p;
@@ -367,9 +371,13 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
   }
   el = (double)((master ? global_timer_ns() : now) - t0) * 1e-9;
   tr_state(el, fx, gnorm, pgnorm, Delta);
-  if (A.prof_all != nullptr && c.tid == 0)
+  if (A.prof_all != nullptr && c.tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_prof_ns[PH_SMID] = smid;
 #pragma unroll
     for (int i = 0; i < PH_COUNT; ++i) A.prof_all[(size_t)c.b * PH_COUNT + i] = s_prof_ns[i];
+  }
   if (master) {
     TntDev *o = A.out;
     o->f = fx; o->gnorm = gnorm; o->pgnorm = pgnorm; o->Delta = Delta; o->elapsed = el;
@@ -384,16 +392,17 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
 
 
 // ============================================================ k_spmm_persistent ====
-// `reps` data-matrix products out = Q X through the same tile pipeline (roofline leg of bench.py /
-// scripts/sweep_1m.py; Problem::dataMatrixProduct, src/CORA_problem.cpp:742-757).
-template <int D>
+// `reps` data-matrix products out = Q X through the same phases (roofline leg of bench.py;
+// Problem::dataMatrixProduct, src/CORA_problem.cpp:742-757).
+template <int D, int R>
 __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_spmm_persistent(const DevLayout L, const PArgs A, const double *X,
                                                                  double *out, int reps) {
-  constexpr int D1 = D + 1;
+  constexpr bool STREAM = R > 0;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) unsigned long long s_mbar[2];
+  __shared__ __align__(8) unsigned long long s_rbar[STREAM ? kStreamMaxWarps * kStreamMaxStages : 1];
   __shared__ int s_meta[2][4];
-  __shared__ TileMeta s_tmeta[kMaxTilesPerCta];
+  __shared__ TileMeta s_tmeta[STREAM ? 1 : kMaxTilesPerCta];
   __shared__ unsigned long long s_prof_ns[PH_COUNT], s_tph[2];
   __shared__ unsigned int s_prof_cnt[PH_COUNT];
   PCtx c;
@@ -401,62 +410,28 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_spm
   c.bar = A.bar; c.target = 0; c.partials = A.partials; c.parity = 0; c.nbar = 0;
   c.prof_ns = s_prof_ns; c.prof_cnt = s_prof_cnt; c.tph = s_tph;
   c.mpar0 = c.mpar1 = 0u;
-  c.hub_target = 0;
-  const int r = A.r;
-  {
-    c.t0 = A.cta_t0[c.b];
-    c.t1 = A.cta_t0[c.b + 1];
-    c.e0 = (long long)c.t0 * L.TR * r;
-    c.e1 = min((long long)c.t1 * L.TR, (long long)L.N) * r;
-    if (c.e0 > c.e1) c.e0 = c.e1;
-    const PGeo<D> geo(r);
-    c.nbv = L.maxSlots * D1 * D1 * L.TP;              // doubles
-    c.ncol = (L.maxSlots * L.TP + 3) & ~3;            // ints
-    c.spcap = (L.maxTileSpill + 3) & ~3;              // entries
-    c.TRP = L.TRP;
-    c.pstride = D1 * r;
-    c.hpad = (c.pstride + 1) & ~1;                              // halo in front of the tile rows, kept 16-byte aligned
-    c.vstride = (c.hpad + L.TR * r + c.pstride + 2 + 1) & ~1;  // + halo behind, + one element of copy rounding
-    c.nlam = D * D * L.TP;
-    c.qstride = c.nbv + c.spcap + (c.ncol + c.TRP + c.spcap) / 2;  // doubles (int regions are multiples of 4)
-    c.smem = smem;
-    c.sred = smem;
-    c.sbc = smem + 128;  // sred: up to 16 warps x 8 partial sums
-    c.qbase = 144;
-    const int after_q = c.qbase + c.nbuf * c.qstride;
-    c.sW = smem + after_q;
-    c.vbase = after_q + c.vstride;
-    c.mbar = s_mbar;
-    c.meta = &s_meta[0][0];
-    c.tmeta = s_tmeta;
-    for (int i = c.tid; i < min(c.t1 - c.t0, kMaxTilesPerCta); i += c.nth) {
-      const int t = c.t0 + i;
-      TileMeta M;
-      M.boff = L.tile_boff[t]; M.coff = L.tile_coff[t]; M.spoff = L.tile_sp_off[t];
-      M.S = L.tile_slots[t]; M.nsp = L.tile_sp_cnt[t];
-      M.lq0 = L.tile_long_ptr[t]; M.lq1 = L.tile_long_ptr[t + 1];
-      s_tmeta[i] = M;
-    }
-    if (c.tid < PH_COUNT) { s_prof_ns[c.tid] = 0; s_prof_cnt[c.tid] = 0; }
-    if (c.tid == 0) {
-      s_tph[0] = s_tph[1] = 0;
-      mbar_init(&s_mbar[0], 1);
-      mbar_init(&s_mbar[1], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-  }
+  Ring rg;
+  c.meta = &s_meta[0][0];
+  persistent_setup<D, STREAM>(L, A, c, smem, s_tmeta, s_mbar, s_rbar, rg);
+  if (c.tid < PH_COUNT) { s_prof_ns[c.tid] = 0; s_prof_cnt[c.tid] = 0; }
+  if (c.tid == 0) s_tph[0] = s_tph[1] = 0;
+  __syncthreads();
   double *lp0 = A.longpart;
   for (int rep = 0; rep < reps; ++rep) {
     if (L.numChunks > 0) {
       hub_phase<D>(L, c, X, 1.0, nullptr, 0.0, lp0);
       grid_sync(c);
     }
-    if (A.regpath & 4) qprod_warp<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
-    else if (A.regpath & 2) qprod_hyb<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
-    else qprod_phase<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
+    if constexpr (STREAM)
+      stream_qprod<D, R, QM_SPMM>(L, A.sd, c, rg, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    else
+      qprod_phase<D, QM_SPMM>(L, c, X, nullptr, out, nullptr, lp0, nullptr, nullptr, nullptr);
     grid_sync(c);
   }
 }
+
+// Kernel entry points by (d, rank), one instantiation per translation unit (pk_*.cu); nullptr: not compiled
+void *persistent_tnt_kernel(int d, int R);
+void *persistent_spmm_kernel(int d, int R);
 
 }  // namespace cora_b200

@@ -1,5 +1,5 @@
-// persistent_reg.cuh -- register / warp-shuffle formulation of the two hot phases of a CG iteration
-// (the Hessian product and the preconditioned update) for the persistent TNT kernel.
+// persistent_reg.cuh -- register / warp-shuffle formulation of the preconditioned update phase of a CG
+// iteration for the persistent TNT kernel at ranks without a compiled streaming path (stream.cuh).
 //
 // The shared-memory tile pipeline (persistent.cuh) is latency bound at two CTAs per SM: four block
 // barriers per tile and a thread-per-pose epilogue leave the LSU idle (ncu: issue active 24 %, 0.34
@@ -63,211 +63,6 @@ __device__ __forceinline__ void group_tangent(const double (&y)[D], double (&w)[
   }
 #pragma unroll
   for (int a = 0; a < D; ++a) w[a] = t[a];
-}
-
-// ------------------------------------------------------------------------------------------------
-// Hybrid: the operands arrive through the double-buffered tile pipeline of persistent.cuh (TMA bulk
-// copies of the data-matrix slice, cp.async of the dense tile rows + halo: many bytes in flight at no
-// register cost), the compute is the group-per-pose register formulation above reading from the staged
-// buffers.  Two block barriers per tile (acquire / release) instead of five, every warp busy through
-// the epilogue, results stored straight from registers.
-template <int D, int MODE>
-__device__ __forceinline__ void qprod_hyb(const DevLayout &L, PCtx &c, const double *X, const double *Y, double *out,
-                                          double *out2, const double *longpart, double *lam, double *lamS,
-                                          double *acc) {
-  constexpr int D1 = D + 1;
-  constexpr int NV = (MODE == QM_HESS) ? 2 : 1;
-  const int r = c.r, TP = L.TP;
-  const PGeo<D> geo(r);
-  const int GS = group_size(r), PPW = 32 / GS;
-  const int lane = c.tid & 31, warp = c.tid >> 5, nwarps = c.nth >> 5;
-  const int sub = lane / GS, cc = lane - sub * GS;
-  const bool col_ok = cc < r;
-  const int pstride = D1 * geo.RS + geo.PADP;
-  ph_begin(c);
-  int buf = 0;
-  const double *bsrc = (MODE == QM_HESS) ? lam : nullptr;
-  if (c.t0 < c.t1) tile_prefetch<D, true, NV>(L, c, c.t0, 0, X, Y, nullptr, bsrc);
-  for (int t = c.t0; t < c.t1; ++t) {
-    sub_begin(c);
-    tile_acquire<D, true, NV>(L, c, t, buf, X, Y, nullptr, bsrc);
-    sub_end(c, PH_Q_WAIT);
-    const TileBuf B = c.pick(buf);
-    const TileInfo T = tile_geom<D>(L, t, r);
-    const TileMeta M = tile_meta(L, c, t);
-    const double *sX = B.slot[0], *sY = B.slot[1];
-    const int S = B.meta[0];
-    const int winLo = max(T.row0 - D1, 0);
-    const int winHi = min(min(T.row0 + T.nR + D1, L.N), L.nPoseRows);
-    double *hub = c.sW;
-    const int hs = hub_stride<D>(L, M, r);
-    if (M.lq1 > M.lq0) {
-      tile_hub_sums<D>(L, c, M, longpart, hub);
-      __syncthreads();
-    }
-    // ---------------- pose blocks of the tile ----------------
-    for (int pb = warp * PPW; pb < T.nP; pb += nwarps * PPW) {
-      const int pl = pb + sub;
-      const bool active = col_ok && pl < T.nP;
-      const int p = t * TP + pl;
-      double w[D1], xo[D1];
-#pragma unroll
-      for (int a = 0; a < D1; ++a) { w[a] = 0.0; xo[a] = 0.0; }
-      if (active) {
-        // spill columns first: their L2 round trip overlaps the block products
-        const int k0 = B.gptr[pl], k1 = B.gptr[pl + 1];
-        double xs0 = 0.0, xs1 = 0.0;
-        if (k0 < k1) xs0 = X[(size_t)(B.spk[k0] & kColMask) * r + cc];
-        if (k0 + 1 < k1) xs1 = X[(size_t)(B.spk[k0 + 1] & kColMask) * r + cc];
-        const double *xop = sX + pl * pstride + cc;
-#pragma unroll
-        for (int q = 0; q < D1; ++q) xo[q] = xop[q * geo.RS];
-        for (int s = 0; s < S; ++s) {
-          const int jb = B.scol[s * TP + pl];
-          double x[D1];
-          if (jb >= winLo && jb + D1 <= winHi) {
-            const int lp = (jb - T.row0 + D1) / D1 - 1;
-            const double *xp = sX + lp * pstride + cc;
-#pragma unroll
-            for (int q = 0; q < D1; ++q) x[q] = xp[q * geo.RS];
-          } else {
-            const double *xp = X + (size_t)jb * r + cc;
-#pragma unroll
-            for (int q = 0; q < D1; ++q) x[q] = xp[(size_t)q * r];
-          }
-          const double *bv = B.sval + (size_t)s * D1 * D1 * TP + pl;
-#pragma unroll
-          for (int a = 0; a < D1; ++a)
-#pragma unroll
-            for (int q = 0; q < D1; ++q) w[a] = fma(bv[(a * D1 + q) * TP], x[q], w[a]);
-        }
-        for (int k = k0; k < k1; ++k) {
-          const unsigned pk = B.spk[k];
-          const int lr = (int)(pk >> 30);
-          const double xg = k == k0 ? xs0 : (k == k0 + 1 ? xs1 : X[(size_t)(pk & kColMask) * r + cc]);
-          const double xv = B.spv[k] * xg;
-#pragma unroll
-          for (int a = 0; a < D1; ++a) w[a] += (lr == a) ? xv : 0.0;
-        }
-        for (int q = M.lq0; q < M.lq1; ++q) {
-          if (L.long_grp[q] != p) continue;
-#pragma unroll
-          for (int a = 0; a < D1; ++a) w[a] += hub[(q - M.lq0) * hs + a * r + cc];
-        }
-      }
-      if (MODE == QM_SPMM) {
-        if (active)
-#pragma unroll
-          for (int a = 0; a < D1; ++a) out[((size_t)p * D1 + a) * r + cc] = w[a];
-        continue;
-      }
-      double y[D];
-#pragma unroll
-      for (int a = 0; a < D; ++a) y[a] = 0.0;
-      if (active) {
-        if (MODE == QM_GRAD) {
-#pragma unroll
-          for (int a = 0; a < D; ++a) y[a] = xo[a];
-#pragma unroll
-          for (int a = 0; a < D1; ++a) {
-            out2[((size_t)p * D1 + a) * r + cc] = w[a];
-            acc[0] = fma(xo[a], w[a], acc[0]);
-          }
-        } else {
-          const double *yp = sY + pl * pstride + cc;
-#pragma unroll
-          for (int a = 0; a < D; ++a) y[a] = yp[a * geo.RS];
-        }
-      }
-      double Sm[D * D];
-      group_tangent<D>(y, w, GS, active, Sm);
-      if (active) {
-        if (MODE == QM_GRAD) {
-          if (cc < D) {  // lane cc writes row cc of the diagonal block of Q - Lambda
-            double *lg = lam + M.boff + pl;
-#pragma unroll
-            for (int b = 0; b < D; ++b) {
-              double v = Sm[b];
-#pragma unroll
-              for (int a = 1; a < D; ++a) v = (cc == a) ? Sm[a * D + b] : v;
-              lg[(cc * D1 + b) * TP] = B.sval[(cc * D1 + b) * TP + pl] - v;
-            }
-          }
-#pragma unroll
-          for (int a = 0; a < D1; ++a) {
-            out[((size_t)p * D1 + a) * r + cc] = w[a];
-            acc[1] = fma(w[a], w[a], acc[1]);
-          }
-        } else {
-#pragma unroll
-          for (int a = 0; a < D1; ++a) {
-            out[((size_t)p * D1 + a) * r + cc] = w[a];
-            acc[0] = fma(xo[a], w[a], acc[0]);
-            acc[1] = fma(w[a], w[a], acc[1]);
-            acc[2] = fma(xo[a], xo[a], acc[2]);
-          }
-        }
-      }
-    }
-    // ---------------- scalar rows of the tile ----------------
-    for (int rb = warp * PPW; rb < T.nS; rb += nwarps * PPW) {
-      const int sr = rb + sub;
-      const bool active = col_ok && sr < T.nS;
-      const int lrow = T.nP * D1 + sr;
-      const int row = T.row0 + lrow;
-      const int sidx = row - L.nPoseRows;
-      const bool is_range = row >= L.nPoseRows + L.l;
-      double w = 0.0, xo = 0.0, yv = 0.0;
-      if (active) {
-        const int u = T.nP + sr;
-        const int k0 = B.gptr[u], k1 = B.gptr[u + 1];
-        double xs0 = 0.0, xs1 = 0.0;
-        if (k0 < k1) xs0 = X[(size_t)(B.spk[k0] & kColMask) * r + cc];
-        if (k0 + 1 < k1) xs1 = X[(size_t)(B.spk[k0 + 1] & kColMask) * r + cc];
-        xo = sX[geo.soff(lrow, cc)];
-        const double dg = (MODE == QM_HESS) ? lamS[sidx] : __ldg(L.sdiag + sidx);
-        w = dg * xo;
-        if (k0 < k1) w = fma(B.spv[k0], xs0, w);
-        if (k0 + 1 < k1) w = fma(B.spv[k0 + 1], xs1, w);
-        for (int k = k0 + 2; k < k1; ++k) w = fma(B.spv[k], X[(size_t)(B.spk[k] & kColMask) * r + cc], w);
-        for (int q = M.lq0; q < M.lq1; ++q) {
-          if (L.long_grp[q] != L.n + sidx) continue;
-          w += hub[(q - M.lq0) * hs + cc];
-        }
-      }
-      if (MODE == QM_SPMM) {
-        if (active) out[(size_t)row * r + cc] = w;
-        continue;
-      }
-      if (active) {
-        if (MODE == QM_GRAD) {
-          yv = xo;
-          out2[(size_t)row * r + cc] = w;
-          acc[0] = fma(xo, w, acc[0]);
-        } else {
-          yv = sY[geo.soff(lrow, cc)];
-        }
-      }
-      const double s = group_sum((active && is_range) ? yv * w : 0.0, GS);
-      if (active) {
-        if (is_range) w = fma(-s, yv, w);
-        out[(size_t)row * r + cc] = w;
-        if (MODE == QM_GRAD) {
-          if (cc == 0) lamS[sidx] = __ldg(L.sdiag + sidx) - (is_range ? s : 0.0);
-          acc[1] = fma(w, w, acc[1]);
-        } else {
-          acc[0] = fma(xo, w, acc[0]);
-          acc[1] = fma(w, w, acc[1]);
-          acc[2] = fma(xo, xo, acc[2]);
-        }
-      }
-    }
-    sub_end(c, PH_Q_QX);
-    if (MODE == QM_GRAD) asm volatile("fence.proxy.async.global;" ::: "memory");
-    tile_release<D, true, NV>(L, c, t, buf, X, Y, nullptr, bsrc);
-    sub_end(c, PH_Q_STORE);
-  }
-  ph_end(c, MODE == QM_HESS ? PH_HESS : PH_GRAD);
 }
 
 // STPCG update + preconditioner closure: R += alpha HP (AXPY) ; V = proj_Y(z), z = R*dinv | R | Z

@@ -199,89 +199,125 @@ inline void swap_vec(H *h, int a, int b) {
 }
 
 // ------------------------------------------------------- persistent TNT (host) ---
+// dynamic shared memory of the tile pipeline (persistent.cuh); with_q = false: only the dense-vector slots
+// (retraction, hub scratch, chain apply), the data-matrix slice buffers are not needed
 template <int D>
-inline size_t persistent_smem(const H *h, int r, int nbuf) {
+inline size_t persistent_smem(const H *h, int r, int nbuf, bool with_q) {
   const int D1 = D + 1;
   const size_t nbv = (size_t)h->DL.maxSlots * D1 * D1 * h->DL.TP;
   const size_t ncol = ((size_t)h->DL.maxSlots * h->DL.TP + 3) & ~(size_t)3;
   const size_t spcap = ((size_t)h->DL.maxTileSpill + 3) & ~(size_t)3;
   const size_t pstride = (size_t)D1 * r, hpad = (pstride + 1) & ~(size_t)1;
   const size_t vstride = (hpad + (size_t)h->DL.TR * r + pstride + 2 + 1) & ~(size_t)1;
-  const size_t qbuf = (nbv + spcap) * sizeof(double) + (ncol + h->DL.TRP + spcap) * sizeof(int);
+  const size_t qbuf = with_q ? (nbv + spcap) * sizeof(double) + (ncol + h->DL.TRP + spcap) * sizeof(int) : 0;
   return 144 * sizeof(double) + nbuf * qbuf + (1 + 3 * (size_t)nbuf) * vstride * sizeof(double);
 }
 
-// One cooperative launch runs the whole trust-region solve on the resident iterate.
-// grid / shared-memory configuration of the persistent kernels at rank r (cached per rank)
+// grid / shared-memory configuration of the persistent kernels at rank r (cached per rank).  Ranks with a
+// compiled streaming kernel (build.py: PK_LIST) run the data-matrix products and the preconditioned update on
+// per-warp strip rings (stream.cuh), every other rank on the any-rank tile pipeline.
 inline void persistent_configure(H *h, int r) {
-  if (h->persistent_grid_r != r) {
-    if (const char *e = getenv("CORA_B200_REG")) h->persistent_regpath = atoi(e);
-    if (const char *e = getenv("CORA_B200_PTHREADS")) h->persistent_threads = std::max(64, std::min(1024, atoi(e)));
+  if (h->persistent_grid_r == r) return;
+  const int d = h->DL.d, D1 = h->DL.D1;
+  const int threads = h->persistent_threads, warps = threads / 32;
+  void *kfn = h->allow_stream ? persistent_tnt_kernel(d, r) : nullptr;
+  bool stream = kfn != nullptr && warps <= kStreamMaxWarps;
+  size_t smem = 0;
+  int nbuf = 2;
+  int stage = 0, xw = 0, yw = 0;
+  if (stream) {
+    const StreamHost &S = h->SH;
+    xw = ((S.SP + 2) * D1 * r + 2 + 1) & ~1;
+    yw = 32 * r + 2;
+    stage = xw + yw + 128 + (S.max_rec_bytes + 7) / 8;
+    stage = std::max(stage, 3 * yw + 36);
+    stage = (stage + 1) & ~1;
+    const size_t ring = (size_t)warps * h->stream_stages * stage * sizeof(double);
+    size_t vec = 0;
+    DISPATCH_D(h, vec = persistent_smem<DD>(h, r, 2, false));
+    smem = std::max(vec, 144 * sizeof(double) + ring);
+    if (smem > 227 * 1024) stream = false;  // very large ranks / records: tile pipeline
+  }
+  if (!stream) {
+    kfn = persistent_tnt_kernel(d, 0);
+    if (!kfn) throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel not compiled for this dimension");
     // double-buffered tile pipeline when two CTAs of it fit on an SM, single-buffered otherwise
-    size_t smem = 0;
-    int nbuf = 2;
-    DISPATCH_D(h, smem = persistent_smem<DD>(h, r, 2));
-    if (const char *e = getenv("CORA_B200_NBUF")) nbuf = atoi(e) == 1 ? 1 : 2;
-    if (smem > 113 * 1024 && !getenv("CORA_B200_NBUF")) nbuf = 1;
-    DISPATCH_D(h, smem = persistent_smem<DD>(h, r, nbuf));
+    DISPATCH_D(h, smem = persistent_smem<DD>(h, r, 2, true));
+    if (smem > 113 * 1024) nbuf = 1;
+    DISPATCH_D(h, smem = persistent_smem<DD>(h, r, nbuf, true));
     if (smem > 227 * 1024)
       throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: tile working set exceeds shared memory at this rank");
-    h->persistent_nbuf = nbuf;
-    h->persistent_smem = smem;
-    {  // the hub-row scratch of a tile lives in one vector slot
-      const HostLayout &HL = h->HL;
-      const size_t vstride = (size_t)HL.TR * r;
-      for (size_t q = 0; q < HL.long_grp.size(); ++q)
-        if (HL.long_grp[q] < HL.n) h->persistent_regpath &= ~4;  // pose hub groups: block-synchronous products
-      if (r > 16) h->persistent_regpath &= ~4;                    // one pose per warp step would idle half the lanes
-      for (int t = 0; t < HL.numTiles; ++t) {
-        const int q0 = HL.tile_long_ptr[t], q1 = HL.tile_long_ptr[t + 1];
-        if (q1 == q0) continue;
-        const size_t hs = HL.long_grp[q0] < HL.n ? (size_t)HL.D1 * r : (size_t)r;
-        if ((size_t)(q1 - q0) * hs > vstride)
-          throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many hub rows in one tile for the shared-memory scratch");
-      }
-    }
-    int per_sm = 0;
-    DISPATCH_D(h, {
-      CUDA_CHECK(cudaFuncSetAttribute(k_tnt_persistent<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tnt_persistent<DD>, h->persistent_threads, smem));
-    });
-    if (per_sm < 1) throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel does not fit on an SM at this rank");
-    if (const char *e = getenv("CORA_B200_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
-    int G0 = std::max(1, std::min(h->sm_count * per_sm, h->DL.numTiles));
-    h->persistent_grid = G0;
-    h->persistent_grid_r = r;
-    {  // cost-balanced contiguous partition: scalar-row tiles (two L2 gathers per element) weigh more
-      double ws = 0.4;
-      if (const char *e = getenv("CORA_B200_SCALAR_TILE_WEIGHT")) ws = atof(e);
-      const HostLayout &HL = h->HL;
-      std::vector<double> cost(HL.numTiles);
-      double total = 0.0;
-      for (int t = 0; t < HL.numTiles; ++t) {
-        const int64_t row0 = (int64_t)t * HL.TR;
-        const int nR = (int)std::min<int64_t>(HL.TR, HL.N - row0);
-        const int nP = (int)std::max<int64_t>(0, std::min<int64_t>(HL.TP, (int64_t)HL.n - (int64_t)t * HL.TP));
-        const int nS = nR - nP * HL.D1;
-        cost[t] = 1.0 + ws * (double)nS / HL.TR;
-        total += cost[t];
-      }
-      std::vector<int> t0(G0 + 1, HL.numTiles);
-      t0[0] = 0;
-      double accum = 0.0;
-      int b = 1;
-      for (int t = 0; t < HL.numTiles && b < G0; ++t) {
-        accum += cost[t];
-        while (b < G0 && accum >= total * b / G0) t0[b++] = t + 1;
-      }
-      for (int i = 1; i <= G0; ++i) {
-        t0[i] = std::max(t0[i], t0[i - 1]);
-      }
-      t0[G0] = HL.numTiles;
-      h->d_cta_t0.upload(t0, h->stream);
-      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    // the hub-row scratch of a tile lives in one vector slot
+    const HostLayout &HL = h->HL;
+    const size_t vstride = (size_t)HL.TR * r;
+    for (int t = 0; t < HL.numTiles; ++t) {
+      const int q0 = HL.tile_long_ptr[t], q1 = HL.tile_long_ptr[t + 1];
+      if (q1 == q0) continue;
+      const size_t hs = HL.long_grp[q0] < HL.n ? (size_t)HL.D1 * r : (size_t)r;
+      if ((size_t)(q1 - q0) * hs > vstride)
+        throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many hub rows in one tile for the shared-memory scratch");
     }
   }
+  h->persistent_stream = stream;
+  h->persistent_kfn = kfn;
+  h->persistent_spmm_kfn = persistent_spmm_kernel(d, stream ? r : 0);
+  h->persistent_nbuf = nbuf;
+  h->persistent_smem = smem;
+  h->stream_stage_doubles = stage; h->stream_xw = xw; h->stream_yw = yw;
+  int per_sm = 0;
+  CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
+  if (per_sm < 1) throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel does not fit on an SM at this rank");
+  if (const char *e = getenv("CORA_B200_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+  const int G0 = std::max(1, std::min(h->sm_count * per_sm, h->DL.numTiles));
+  h->persistent_grid = G0;
+  h->persistent_grid_r = r;
+  {  // cost-balanced contiguous partition of the tiles: scalar-row tiles (two L2 gathers per element) weigh more
+    const double ws = 0.4;
+    const HostLayout &HL = h->HL;
+    std::vector<double> cost(HL.numTiles);
+    double total = 0.0;
+    for (int t = 0; t < HL.numTiles; ++t) {
+      const int64_t row0 = (int64_t)t * HL.TR;
+      const int nR = (int)std::min<int64_t>(HL.TR, HL.N - row0);
+      const int nP = (int)std::max<int64_t>(0, std::min<int64_t>(HL.TP, (int64_t)HL.n - (int64_t)t * HL.TP));
+      const int nS = nR - nP * HL.D1;
+      cost[t] = 1.0 + ws * (double)nS / HL.TR;
+      total += cost[t];
+    }
+    std::vector<int> t0(G0 + 1, HL.numTiles);
+    t0[0] = 0;
+    double accum = 0.0;
+    int b = 1;
+    for (int t = 0; t < HL.numTiles && b < G0; ++t) {
+      accum += cost[t];
+      while (b < G0 && accum >= total * b / G0) t0[b++] = t + 1;
+    }
+    for (int i = 1; i <= G0; ++i) t0[i] = std::max(t0[i], t0[i - 1]);
+    t0[G0] = HL.numTiles;
+    h->d_cta_t0.upload(t0, h->stream);
+    if (stream) {
+      std::vector<int32_t> ws0;
+      partition_strips(h->SH, G0 * warps, h->stream_scalar_weight, ws0);
+      std::vector<int> wsi(ws0.begin(), ws0.end());
+      h->d_warp_strip.upload(wsi, h->stream);  // cudaMalloc: 256-byte aligned, read as int4
+    }
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+}
+
+inline void fill_stream_args(const H *h, StreamDev &sd) {
+  const StreamHost &S = h->SH;
+  sd.SP = S.SP; sd.CP = S.CP; sd.GP = S.GP; sd.nPS = S.nPS; sd.nSS = S.nSS; sd.nStrips = S.nStrips;
+  sd.nstage = h->stream_stages;
+  sd.stage_doubles = h->stream_stage_doubles;
+  sd.xw_off = 0; sd.yw_off = h->stream_xw; sd.dg_off = h->stream_xw + h->stream_yw; sd.rc_off = sd.dg_off + 128;
+  sd.ring_base = 144;
+  sd.rec_off = h->d_rec_off.p; sd.rec = h->d_rec.p;
+  sd.diagQ = h->d_diagQ.p; sd.sdiagP = h->d_sdiagP.p;
+  sd.diagL[0] = h->d_diagL.p; sd.diagL[1] = h->d_diagL.p + h->d_diagL.n / 2;
+  sd.sdiagL[0] = h->d_sdiagL.p; sd.sdiagL[1] = h->d_sdiagL.p + h->d_sdiagL.n / 2;
+  sd.warp_strip = reinterpret_cast<const int4 *>(h->d_warp_strip.p);
 }
 
 inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200_tnt_result *res) {
@@ -296,7 +332,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   const size_t nlp = 2 * (size_t)std::max(h->DL.numChunks, 1) * h->DL.D1 * h->ws_r;
   if (h->d_longpart.n < nlp) h->d_longpart.alloc(nlp);
   if (!h->d_bar.p) h->d_bar.alloc(2);
-  {
+  if (!h->persistent_stream) {
     // two copies (current / proposal) of the block values with Q - Lambda on the diagonal blocks, and of
     // diag(Q) - lambda_k of the scalar rows; everything but those entries is Q and is copied once
     const size_t nl = std::max<size_t>((size_t)h->HL.tile_boff[h->HL.numTiles], 1), ns = (size_t)h->DL.l + h->DL.m + 1;
@@ -331,8 +367,8 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   A.trace_cap = h->trace_cap;
   A.precond = h->precond;
   A.nbuf = h->persistent_nbuf;
-  A.regpath = h->persistent_regpath;
   A.cta_t0 = h->d_cta_t0.p;
+  if (h->persistent_stream) fill_stream_args(h, A.sd);
   if (h->precond == CORA_B200_PRECON_REG_CHOLESKY) {
     ChainChol *C = h->chol;
     if (!C) throw Error(CORA_B200_ERUNTIME, "RegularizedCholesky factor missing");
@@ -369,8 +405,10 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
     if (2 * (size_t)cd.l * r > 6 * vstride)
       throw Error(CORA_B200_ERUNTIME, "persistent TNT kernel: too many landmarks for the shared-memory border solve");
   }
-  A.lam[0] = h->d_lamT.p; A.lam[1] = h->d_lamT.p + h->d_lamT.n / 2;
-  A.lamS[0] = h->d_lamS.p; A.lamS[1] = h->d_lamS.p + h->d_lamS.n / 2;
+  if (!h->persistent_stream) {
+    A.lam[0] = h->d_lamT.p; A.lam[1] = h->d_lamT.p + h->d_lamT.n / 2;
+    A.lamS[0] = h->d_lamS.p; A.lamS[1] = h->d_lamS.p + h->d_lamS.n / 2;
+  }
   const bool phase_prof = getenv("CORA_B200_PHASE_PROFILE") != nullptr;
   DevBuf<unsigned long long> d_prof_all;
   if (phase_prof) { d_prof_all.alloc((size_t)G * PH_COUNT); A.prof_all = d_prof_all.p; }
@@ -378,8 +416,9 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   CUDA_CHECK(cudaMemsetAsync(h->d_bar.p, 0, 2 * sizeof(unsigned long long), h->stream));
   DevLayout Lc = h->DL;
   void *args[] = {(void *)&Lc, (void *)&A};
-  DISPATCH_D(h, CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_tnt_persistent<DD>, dim3(G), dim3(h->persistent_threads), args,
-                                                       smem, h->stream)));
+  // the attribute belongs to the function, not to this handle: set it before every launch
+  CUDA_CHECK(cudaFuncSetAttribute(h->persistent_kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_CHECK(cudaLaunchCooperativeKernel(h->persistent_kfn, dim3(G), dim3(h->persistent_threads), args, smem, h->stream));
   check_launch(h);
   CUDA_CHECK(cudaMemcpyAsync(h->h_tntdev, h->d_tntdev.p, sizeof(TntDev), cudaMemcpyDeviceToHost, h->stream));
   CUDA_CHECK(cudaMemcpyAsync(h->h_trace.data(), h->d_trace.p, (size_t)TR_ROWS * h->trace_cap * sizeof(double),
@@ -423,8 +462,8 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
     std::printf("\n");
   }
   if (getenv("CORA_B200_PHASE_PROFILE")) {
-    static const char *names[PH_COUNT] = {"hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc", "q.wait", "q.qx", "q.epi", "q.store", "ch.pre", "ch.fwd", "ch.bwd", "ch.border", "ch.post"};
-    std::printf("[persistent] grid %d, nbuf %d, smem %zu, barriers %lld, outer %d, CG %lld, device %.3f ms\n", G, h->persistent_nbuf, smem, o.barriers, o.num_outer, o.total_inner, ms);
+    static const char *names[PH_COUNT] = {"hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc", "q.wait", "q.qx", "q.epi", "q.store", "ch.pre", "ch.fwd", "ch.bwd", "ch.border", "ch.post", "smid"};
+    std::printf("[persistent] %s grid %d, nbuf %d, smem %zu, barriers %lld, outer %d, CG %lld, device %.3f ms\n", h->persistent_stream ? "stream" : "tile", G, h->persistent_nbuf, smem, o.barriers, o.num_outer, o.total_inner, ms);
     for (int i = 0; i < PH_COUNT; ++i)
       if (o.prof_cnt[i]) std::printf("  %-8s n=%6u total %9.1f us  avg %8.2f us\n", names[i], o.prof_cnt[i], o.prof_ns[i] * 1e-3, o.prof_ns[i] * 1e-3 / o.prof_cnt[i]);
     std::vector<unsigned long long> pa((size_t)G * PH_COUNT);
@@ -438,6 +477,11 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
       int amax = 0;
       for (int b = 0; b < G; ++b) if (col[b] > col[amax]) amax = b;
       std::printf("  per-CTA avg %-8s min %7.2f  med %7.2f  p90 %7.2f  max %7.2f (cta %d)  last-cta %7.2f\n", names[i], srt[0], srt[G / 2], srt[(G * 9) / 10], srt[G - 1], amax, col[G - 1]);
+      if (atoi(getenv("CORA_B200_PHASE_PROFILE")) >= 2 && (i == PH_HESS || i == PH_UPDATE)) {
+        std::printf("    all CTAs (time@sm):");
+        for (int b = 0; b < G; ++b) std::printf("%s%.1f@%d", b % 12 == 0 ? "\n     " : " ", col[b], (int)pa[(size_t)b * PH_COUNT + PH_SMID]);
+        std::printf("\n");
+      }
     }
   }
   res->f = o.f;
@@ -464,17 +508,15 @@ inline float spmm_persistent(H *h, int r, const double *X, double *out, int reps
   A.bar = h->d_bar.p;
   A.r = r;
   A.nbuf = h->persistent_nbuf;
-  A.regpath = h->persistent_regpath;
   A.cta_t0 = h->d_cta_t0.p;
+  if (h->persistent_stream) fill_stream_args(h, A.sd);
   CUDA_CHECK(cudaMemsetAsync(h->d_bar.p, 0, sizeof(unsigned long long), h->stream));
   DevLayout Lc = h->DL;
   void *args[] = {(void *)&Lc, (void *)&A, (void *)&X, (void *)&out, (void *)&reps};
-  DISPATCH_D(h, CUDA_CHECK(cudaFuncSetAttribute(k_spmm_persistent<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)h->persistent_smem)));
+  CUDA_CHECK(cudaFuncSetAttribute(h->persistent_spmm_kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->persistent_smem));
   CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-  DISPATCH_D(h, CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_spmm_persistent<DD>, dim3(G),
-                                                       dim3(h->persistent_threads), args, h->persistent_smem,
-                                                       h->stream)));
+  CUDA_CHECK(cudaLaunchCooperativeKernel(h->persistent_spmm_kfn, dim3(G), dim3(h->persistent_threads), args,
+                                         h->persistent_smem, h->stream));
   check_launch(h);
   CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   CUDA_CHECK(cudaEventSynchronize(h->ev1));

@@ -305,6 +305,12 @@ int cora_b200_layout_roundtrip(int d, int n_poses, int n_ranges, int n_trans,
                                const int32_t *rowptr, const int32_t *col, const double *val,
                                int64_t nnz, int32_t *out_rowptr, int32_t *out_col,
                                double *out_val, int64_t *stats /* 8 entries */);
+/* Same, through the STRIP layout (per-warp records of cora_b200/csrc/stream_layout.hpp) that the
+ * rank-specialised streaming kernels consume. */
+int cora_b200_strip_layout_roundtrip(int d, int n_poses, int n_ranges, int n_trans,
+                                     const int32_t *rowptr, const int32_t *col, const double *val,
+                                     int64_t nnz, int32_t *out_rowptr, int32_t *out_col,
+                                     double *out_val, int64_t *stats /* 8 entries */);
 
 /* Test hook (CPU only, no GPU): chain factorisation of (Q + shift I) [last row pinned when
  * pin_last] and M^-1 V executed on the host through the same per-chunk routines the device

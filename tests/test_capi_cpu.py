@@ -50,13 +50,15 @@ def _roundtrip(p, tile_rows=None):
         os.environ["CORA_B200_TILE_ROWS"] = str(tile_rows)
     try:
         out, stats = capi.layout_roundtrip(p.d, p.n, p.m, p.n + p.l, p.Q)
+        out_s, _ = capi.layout_roundtrip(p.d, p.n, p.m, p.n + p.l, p.Q, strips=True)
     finally:
         os.environ.pop("CORA_B200_TILE_ROWS", None)
     ref = sp.csr_matrix(p.Q); ref.eliminate_zeros(); ref.sort_indices()
-    out.eliminate_zeros(); out.sort_indices()
-    assert np.array_equal(ref.indptr, out.indptr)
-    assert np.array_equal(ref.indices, out.indices)      # integer indexing bit-exact
-    assert np.array_equal(ref.data, out.data)            # values are moved, never recomputed
+    for o in (out, out_s):  # tile layout, and the strip records of the streaming kernels built from it
+        o.eliminate_zeros(); o.sort_indices()
+        assert np.array_equal(ref.indptr, o.indptr)
+        assert np.array_equal(ref.indices, o.indices)      # integer indexing bit-exact
+        assert np.array_equal(ref.data, o.data)            # values are moved, never recomputed
     return stats
 
 

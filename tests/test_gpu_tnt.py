@@ -165,13 +165,15 @@ def test_warm_start_cg_heavy_all_ranks(lib, d, r):
     np.testing.assert_allclose(got.objective_values[:10], ref.objective_values[:10], rtol=1e-4)
 
 
-@pytest.mark.parametrize("flags", ["0", "1", "3", "5", "8", "9"])
-def test_product_phase_variants_agree(lib, flags, monkeypatch):
-    """The four implementations of the hot phases (shared-memory epilogue, register update, hybrid,
-    warp-local) follow the same trajectory (CORA_B200_REG selects them)."""
+@pytest.mark.parametrize("stream", ["1", "0"])
+@pytest.mark.parametrize("d,r", [(3, 5), (3, 7), (3, 11), (2, 3), (2, 4)])
+def test_streaming_and_tile_kernels_agree(lib, stream, d, r, monkeypatch):
+    """The rank-specialised streaming kernel (per-warp strip rings, stream.cuh) and the any-rank tile-pipeline
+    kernel follow the oracle's trajectory (CORA_B200_STREAM=0 forces the tile pipeline; rank 11 has no
+    streaming kernel and runs the tile pipeline either way)."""
     from cora_b200 import synthetic
-    monkeypatch.setenv("CORA_B200_REG", flags)
-    d, r, n, l, m = 3, 5, 900, 4, 300
+    monkeypatch.setenv("CORA_B200_STREAM", stream)
+    n, l, m = 900, 4, 300
     p = make_synthetic(n=n, l=l, m=m, d=d, seed=12, rank=r)
     p.update_problem_data()
     arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=12)
