@@ -14,7 +14,7 @@ from typing import List, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcora_b200.so")
+LIB_PATH = os.environ.get("CORA_B200_LIB") or os.path.join(_HERE, "lib", "libcora_b200.so")  # (override: development builds)
 
 PRECON_NONE, PRECON_JACOBI, PRECON_BLOCK_CHOLESKY, PRECON_REG_CHOLESKY = 0, 1, 2, 3
 TNT_STATUS = ["Gradient", "PreconditionedGradient", "RelativeDecrease", "Stepsize", "TrustRegion",

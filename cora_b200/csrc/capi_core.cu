@@ -139,7 +139,7 @@ extern "C" int cora_b200_create(cora_b200_t **out, int device, void *stream, int
     {  // strip layout for the streaming kernels (two copies of the diagonal slots: current / proposal point)
       build_stream_layout(L, h->SH);
       const StreamHost &S = h->SH;
-      h->d_rec_off.upload(S.rec_off, s);
+      h->d_rec_off.upload(S.info, s);  // per strip {record offset, size, range window start, rows}: read as uint4
       h->d_rec.upload(S.rec, s);
       h->d_diagQ.upload(S.diagQ, s);
       h->d_sdiagP.upload(S.sdiagP, s);
@@ -155,6 +155,7 @@ extern "C" int cora_b200_create(cora_b200_t **out, int device, void *stream, int
       if (const char *e = getenv("CORA_B200_STREAM")) h->allow_stream = atoi(e) != 0;
       if (const char *e = getenv("CORA_B200_STREAM_STAGES")) h->stream_stages = std::max(2, std::min(kStreamMaxStages, atoi(e)));
       if (const char *e = getenv("CORA_B200_STREAM_SCALAR_WEIGHT")) h->stream_scalar_weight = atof(e);
+      if (const char *e = getenv("CORA_B200_STREAM_INTERLEAVE")) h->stream_interleave = atoi(e) != 0;
     }
     h->d_partials.alloc((size_t)std::max(L.numTiles, h->sm_count * 8) * kNPart);
     h->d_scal.alloc(SC_COUNT);
@@ -371,8 +372,10 @@ extern "C" int cora_b200_lambda_blocks(cora_b200_t *h, int r, const double *Y, d
   compute_lambda(h, T.v(V_X), r);
   const size_t ns = (size_t)h->DL.n * h->DL.d * h->DL.d;
   if (ns) CUDA_CHECK(cudaMemcpyAsync(lam_st, h->d_lam_st.p, ns * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (h->DL.m) CUDA_CHECK(cudaMemcpyAsync(lam_ob, h->d_lam_ob.p, (size_t)h->DL.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<double> ob((size_t)h->DL.m);
+  if (h->DL.m) CUDA_CHECK(cudaMemcpyAsync(ob.data(), h->d_lam_ob.p, (size_t)h->DL.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < h->DL.m; ++k) lam_ob[k] = ob[h->HL.range_pos[k]];  // internal range order -> reference order
   API_END
 }
 

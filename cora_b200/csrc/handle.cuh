@@ -122,6 +122,7 @@ struct cora_b200_handle {
   int stream_stage_doubles = 0, stream_xw = 0, stream_yw = 0;
   double stream_scalar_weight = 1.0;
   bool allow_stream = true;
+  bool stream_interleave = false;   // warps of a CTA take the CTA's strips round-robin
   void *persistent_kfn = nullptr, *persistent_spmm_kfn = nullptr;
   bool use_persistent = true;
   int snap_r = 0;

@@ -42,6 +42,7 @@ struct HostLayout {
   int64_t nPoseRows = 0;  // D1*n
   int64_t G = 0;          // groups = n + l + m
   std::vector<int32_t> int2ref, ref2int;
+  std::vector<int32_t> range_pos;  // internal position (0..m-1) of reference range row k: ranges sorted by their pose
   std::vector<int32_t> tile_slots;
   std::vector<int64_t> tile_boff, tile_coff;
   std::vector<double> bval;
@@ -68,7 +69,7 @@ struct HostLayout {
   inline int64_t ref_to_int(int64_t rr) const {
     const int64_t dn = (int64_t)d * n;
     if (rr < dn) return (rr / d) * D1 + (rr % d);
-    if (rr < dn + m) return nPoseRows + l + (rr - dn);
+    if (rr < dn + m) return nPoseRows + l + (range_pos.empty() ? rr - dn : (int64_t)range_pos[rr - dn]);
     const int64_t t = rr - dn - m;
     if (t < n) return t * D1 + d;
     return nPoseRows + (t - n);
@@ -84,13 +85,38 @@ inline void build_layout(HostLayout &L, int d, int n, int m, int nt, const int32
   L.d = d; L.n = n; L.m = m; L.l = nt - n; L.D1 = D1;
   L.N = (int64_t)d * n + m + nt;
   if (L.N >= (int64_t)kColMask) throw std::invalid_argument("problem too large for int32 packed columns");
-  if (rowptr[L.N] != nnz) throw std::invalid_argument("rowptr[N] != nnz");
+  if (rowptr[L.N] != nnz || rowptr[0] != 0) throw std::invalid_argument("rowptr[0] != 0 or rowptr[N] != nnz");
+  for (int64_t i = 0; i < L.N; ++i)
+    if (rowptr[i + 1] < rowptr[i]) throw std::invalid_argument("rowptr is not monotone");
+  for (int64_t k = 0; k < nnz; ++k)
+    if (col[k] < 0 || col[k] >= L.N) throw std::invalid_argument("column index out of range");
   L.TR = TR; L.TP = TR / D1;
   L.numTiles = (int)((L.N + TR - 1) / TR);
   L.nPoseRows = (int64_t)D1 * n;
   L.G = (int64_t)n + L.l + m;
   L.nnz_in = nnz;
   const int64_t N = L.N;
+  {
+    // Range rows are ordered by the (first) pose they are attached to, ties in reference order: the range rows
+    // coupled to a run of consecutive poses are then one contiguous block of every N x r vector, which the
+    // streaming kernels stage with a single bulk copy instead of gathering them row by row from L2.
+    const int64_t dn = (int64_t)d * n;
+    std::vector<int64_t> key((size_t)m);
+    for (int64_t k = 0; k < m; ++k) {
+      int64_t best = (int64_t)n + k;  // no pose among the columns (landmark-landmark range): after all poses
+      for (int64_t q = rowptr[dn + k]; q < rowptr[dn + k + 1]; ++q) {
+        if (col[q] < 0 || col[q] >= N) throw std::invalid_argument("column index out of range");
+        const int64_t t = (int64_t)col[q] - dn - m;
+        if (t >= 0 && t < n) best = std::min(best, t);
+      }
+      key[k] = best;
+    }
+    std::vector<int32_t> order((size_t)m);
+    for (int64_t k = 0; k < m; ++k) order[k] = (int32_t)k;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    L.range_pos.assign((size_t)m, 0);
+    for (int64_t pos = 0; pos < m; ++pos) L.range_pos[order[pos]] = (int32_t)pos;
+  }
   L.int2ref.resize(N); L.ref2int.resize(N);
   for (int64_t rr = 0; rr < N; ++rr) {
     const int64_t ii = L.ref_to_int(rr);

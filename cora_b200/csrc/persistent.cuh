@@ -132,6 +132,8 @@ struct PCtx {
   int parity;
   int nbar;
   unsigned mpar0, mpar1;  // mbarrier phase parity per buffer
+  unsigned long long *lmbar;  // mbarrier of the landmark cache (streaming phases)
+  unsigned lm_par;
   // shared memory (everything that lives for the whole solve is kept THERE, not in registers: the
   // hot loops need the register file)
   unsigned long long *prof_ns, *tph;   // [PH_COUNT], [2] written by thread 0 only

@@ -76,13 +76,17 @@ __device__ __forceinline__ void persistent_setup(const DevLayout &L, const PArgs
     mbar_init(&s_mbar[0], 1);
     mbar_init(&s_mbar[1], 1);
     if (STREAM)
-      for (int i = 0; i < kStreamMaxWarps * kStreamMaxStages; ++i) mbar_init(&s_rbar[i], 1);
+      for (int i = 0; i < kStreamMaxWarps * kStreamMaxStages + 1; ++i) mbar_init(&s_rbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const int warp = c.tid >> 5;
   rg.base = smem + A.sd.ring_base + (size_t)warp * A.sd.nstage * A.sd.stage_doubles;
   rg.bar = s_rbar + warp * kStreamMaxStages;
   rg.par = 0u;
+  rg.inf = make_uint4(0u, 0u, 0u, 0u);
+  rg.ro_batch = -1;
+  c.lmbar = s_rbar + (STREAM ? kStreamMaxWarps * kStreamMaxStages : 0);
+  c.lm_par = 0u;
 }
 
 // ============================================================ k_tnt_persistent ====
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
   extern __shared__ __align__(16) double smem[];
   __shared__ CgCtrl cg;
   __shared__ __align__(8) unsigned long long s_mbar[2];
-  __shared__ __align__(8) unsigned long long s_rbar[STREAM ? kStreamMaxWarps * kStreamMaxStages : 1];
+  __shared__ __align__(8) unsigned long long s_rbar[STREAM ? kStreamMaxWarps * kStreamMaxStages + 1 : 1];
   __shared__ int s_meta[2][4];
   __shared__ TileMeta s_tmeta[STREAM ? 1 : kMaxTilesPerCta];
   __shared__ unsigned long long s_prof_ns[PH_COUNT], s_tph[2];
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_spm
   constexpr bool STREAM = R > 0;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) unsigned long long s_mbar[2];
-  __shared__ __align__(8) unsigned long long s_rbar[STREAM ? kStreamMaxWarps * kStreamMaxStages : 1];
+  __shared__ __align__(8) unsigned long long s_rbar[STREAM ? kStreamMaxWarps * kStreamMaxStages + 1 : 1];
   __shared__ int s_meta[2][4];
   __shared__ TileMeta s_tmeta[STREAM ? 1 : kMaxTilesPerCta];
   __shared__ unsigned long long s_prof_ns[PH_COUNT], s_tph[2];

@@ -229,13 +229,15 @@ inline void persistent_configure(H *h, int r) {
     const StreamHost &S = h->SH;
     xw = ((S.SP + 2) * D1 * r + 2 + 1) & ~1;
     yw = 32 * r + 2;
-    stage = xw + yw + 128 + (S.max_rec_bytes + 7) / 8;
+    const int recd = ((S.max_rec_bytes + 15) / 16) * 2;
+    stage = xw + yw + 128 + recd + (kRangeWindow * r + 2);
     stage = std::max(stage, 3 * yw + 36);
     stage = (stage + 1) & ~1;
     const size_t ring = (size_t)warps * h->stream_stages * stage * sizeof(double);
+    const size_t lmc = S.lm_cache ? ((size_t)h->DL.l * r + 4) * sizeof(double) : 0;  // landmark cache behind the ring
     size_t vec = 0;
     DISPATCH_D(h, vec = persistent_smem<DD>(h, r, 2, false));
-    smem = std::max(vec, 144 * sizeof(double) + ring);
+    smem = std::max(vec, 144 * sizeof(double) + ring + lmc);
     if (smem > 227 * 1024) stream = false;  // very large ranks / records: tile pipeline
   }
   if (!stream) {
@@ -298,7 +300,7 @@ inline void persistent_configure(H *h, int r) {
     h->d_cta_t0.upload(t0, h->stream);
     if (stream) {
       std::vector<int32_t> ws0;
-      partition_strips(h->SH, G0 * warps, h->stream_scalar_weight, ws0);
+      partition_strips(h->SH, h->stream_interleave ? G0 : G0 * warps, h->stream_scalar_weight, ws0);
       std::vector<int> wsi(ws0.begin(), ws0.end());
       h->d_warp_strip.upload(wsi, h->stream);  // cudaMalloc: 256-byte aligned, read as int4
     }
@@ -310,10 +312,14 @@ inline void fill_stream_args(const H *h, StreamDev &sd) {
   const StreamHost &S = h->SH;
   sd.SP = S.SP; sd.CP = S.CP; sd.GP = S.GP; sd.nPS = S.nPS; sd.nSS = S.nSS; sd.nStrips = S.nStrips;
   sd.nstage = h->stream_stages;
+  sd.interleave = h->stream_interleave ? 1 : 0;
   sd.stage_doubles = h->stream_stage_doubles;
   sd.xw_off = 0; sd.yw_off = h->stream_xw; sd.dg_off = h->stream_xw + h->stream_yw; sd.rc_off = sd.dg_off + 128;
+  sd.gw_off = sd.rc_off + ((S.max_rec_bytes + 15) / 16) * 2;
   sd.ring_base = 144;
-  sd.rec_off = h->d_rec_off.p; sd.rec = h->d_rec.p;
+  sd.lm_rows = S.lm_cache ? h->DL.l : 0;
+  sd.lm_base = 144 + (h->persistent_threads / 32) * h->stream_stages * h->stream_stage_doubles;
+  sd.info = reinterpret_cast<const uint4 *>(h->d_rec_off.p); sd.rec = h->d_rec.p;
   sd.diagQ = h->d_diagQ.p; sd.sdiagP = h->d_sdiagP.p;
   sd.diagL[0] = h->d_diagL.p; sd.diagL[1] = h->d_diagL.p + h->d_diagL.n / 2;
   sd.sdiagL[0] = h->d_sdiagL.p; sd.sdiagL[1] = h->d_sdiagL.p + h->d_sdiagL.n / 2;

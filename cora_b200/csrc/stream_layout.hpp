@@ -7,11 +7,13 @@
 // aligned RECORD, so that it arrives with a single TMA bulk copy into the warp's private shared-memory ring:
 //
 //   pose strip record                                  scalar strip record
-//     int  hdr[4]  = {S, nsp, nlong, 0}                  int  hdr[4] = {0, nsp, nlong, 0}
+//     int  hdr[4]  = {S, nsp, nlong, rw0}                int  hdr[4] = {0, nsp, nlong, 0}
 //     int  cols[S][CP]    base row of the column pose    int  gptr[36]   spill pointers (33 used)
-//     int  gptr[GP]       spill pointers per pose        int  lq[32]     hub (long-group) index or -1
+//     int  gptr[36]       spill pointers per (pose, row) int  lq[32]     hub (long-group) index or -1
 //     int  lq[CP]         hub group of the pose or -1    uint pk[nsp4], double val[nsp2]
-//     uint pk[nsp4]       (row-in-pose << 30 | column row)
+//     uint pk[nsp4]       kind << 30 | index: a global row to gather, a row of the strip's staged range
+//                         window (the range rows attached to the strip's poses are contiguous: layout.hpp),
+//                         or a row of the CTA's landmark cache
 //     double val[nsp2]
 //     double qv[S-1][2][32][2]   off-diagonal block slots: lane (p, a) reads its row a of the
 //                                (d+1) x (d+1) block as two conflict-free 16-byte loads ([half][lane][2])
@@ -31,6 +33,12 @@ namespace cora_b200 {
 constexpr int kStripScalarRows = 32;
 constexpr int kStreamMaxWarps = 16;  // warps per CTA the ring bookkeeping of the kernels is sized for
 constexpr int kStreamMaxStages = 4;
+constexpr int kRangeWindow = 8;     // range rows of x staged per pose strip (rows attached to the strip's poses)
+constexpr int kLmCacheMax = 128;    // landmark rows of x cached in shared memory per CTA (all of them, or none)
+// packed spill entry: kind << 30 | index
+constexpr uint32_t kSpGlobal = 0u;  // index = internal row: gathered from global memory (L2)
+constexpr uint32_t kSpRange = 1u;   // index = row within the strip's staged range window
+constexpr uint32_t kSpLandmark = 2u;  // index = landmark: row of the CTA's landmark cache
 
 struct StreamHost {
   int D1 = 0, SP = 0, CP = 0, GP = 0;
@@ -39,6 +47,9 @@ struct StreamHost {
   int max_slots = 1;
   bool has_pose_hubs = false;
   std::vector<uint32_t> rec_off;  // nStrips + 1, in 16-byte units
+  std::vector<uint32_t> info;     // nStrips x 4: {record offset, record size (16-byte units), first scalar index of the
+                                  // staged range window, rows of the window}
+  bool lm_cache = false;          // landmark entries are encoded as rows of the landmark cache
   std::vector<unsigned char> rec;
   std::vector<double> diagQ;   // nPS x 128: diagonal block slot, [half][lane][2]
   std::vector<double> sdiagP;  // nSS x 32: diagonal of the scalar rows, zero padded
@@ -58,6 +69,8 @@ inline void build_stream_layout(const HostLayout &L, StreamHost &S) {
   S.nSS = (nScal + kStripScalarRows - 1) / kStripScalarRows;
   S.nStrips = S.nPS + S.nSS;
   S.rec_off.assign((size_t)S.nStrips + 1, 0);
+  S.info.assign((size_t)std::max(S.nStrips, 1) * 4, 0u);
+  S.lm_cache = L.l > 0 && L.l <= kLmCacheMax;
   S.rec.clear();
   S.diagQ.assign((size_t)std::max(S.nPS, 1) * 128, 0.0);
   S.sdiagP.assign((size_t)std::max(S.nSS, 1) * kStripScalarRows, 0.0);
@@ -100,17 +113,44 @@ inline void build_stream_layout(const HostLayout &L, StreamHost &S) {
       }
       S.max_slots = std::max(S.max_slots, Smax);
       int nlong = 0;
-      std::vector<int32_t> gptr((size_t)S.GP, 0), lq((size_t)S.CP, -1), cols((size_t)Smax * S.CP, 0);
+      std::vector<int32_t> gptr(36, 0), lq((size_t)S.CP, -1), cols((size_t)Smax * S.CP, 0);
+      // range window of the strip: the first kRangeWindow range rows among its spill columns
+      const int64_t rgrow0 = L.nPoseRows + L.l;
+      int64_t rw0 = -1;
+      for (int p = 0; p < np; ++p)
+        for (int32_t k = L.grp_ptr[i0 + p]; k < L.grp_ptr[i0 + p + 1]; ++k) {
+          const int64_t ci = L.rem_pk[k] & kColMask;
+          if (ci >= rgrow0 && (rw0 < 0 || ci < rw0)) rw0 = ci;
+        }
+      int rwn = 0;
+      // spill pointers per lane = (pose, row of the pose block); the entries of a pose are stored by row
       for (int p = 0; p < SP; ++p) {
-        gptr[p] = (int32_t)pk.size();
-        if (p >= np) continue;
-        const int i = i0 + p;
-        for (int32_t k = L.grp_ptr[i]; k < L.grp_ptr[i + 1]; ++k) { pk.push_back(L.rem_pk[k]); val.push_back(L.rem_val[k]); }
-        lq[p] = long_of[i];
-        if (lq[p] >= 0) ++nlong;
+        if (p < np) {
+          const int i = i0 + p;
+          lq[p] = long_of[i];
+          if (lq[p] >= 0) ++nlong;
+        }
+        for (int a = 0; a < D1; ++a) {
+          gptr[p * D1 + a] = (int32_t)pk.size();
+          if (p >= np) continue;
+          const int i = i0 + p;
+          for (int32_t k = L.grp_ptr[i]; k < L.grp_ptr[i + 1]; ++k) {
+            if ((int)(L.rem_pk[k] >> 30) != a) continue;
+            const int64_t ci = L.rem_pk[k] & kColMask;
+            uint32_t e = (kSpGlobal << 30) | (uint32_t)ci;
+            if (ci >= rgrow0 && ci - rw0 < kRangeWindow) {
+              e = (kSpRange << 30) | (uint32_t)(ci - rw0);
+              rwn = std::max(rwn, (int)(ci - rw0) + 1);
+            } else if (S.lm_cache && ci >= L.nPoseRows && ci < rgrow0) {
+              e = (kSpLandmark << 30) | (uint32_t)(ci - L.nPoseRows);
+            }
+            pk.push_back(e); val.push_back(L.rem_val[k]);
+          }
+        }
       }
-      for (int p = SP; p < S.GP; ++p) gptr[p] = (int32_t)pk.size();
-      gptr[SP] = (int32_t)pk.size();
+      S.info[(size_t)u * 4 + 2] = rwn > 0 ? (uint32_t)(rw0 - L.nPoseRows) : 0u;
+      S.info[(size_t)u * 4 + 3] = (uint32_t)rwn;
+      for (int j = SP * D1; j < 36; ++j) gptr[j] = (int32_t)pk.size();
       const int nsp = (int)pk.size();
       for (int s = 0; s < Smax; ++s)
         for (int p = 0; p < S.CP; ++p) {
@@ -118,7 +158,7 @@ inline void build_stream_layout(const HostLayout &L, StreamHost &S) {
           const int St = L.tile_slots[i / L.TP];
           cols[(size_t)s * S.CP + p] = (p < np && s < St) ? bc(i, s) : i * D1;
         }
-      const int32_t hdr[4] = {Smax, nsp, nlong, 0};
+      const int32_t hdr[4] = {Smax, nsp, nlong, (int32_t)S.info[(size_t)u * 4 + 2]};
       append(hdr, sizeof(hdr));
       append(cols.data(), cols.size() * 4);
       append(gptr.data(), gptr.size() * 4);
@@ -149,7 +189,12 @@ inline void build_stream_layout(const HostLayout &L, StreamHost &S) {
         gptr[j] = (int32_t)pk.size();
         if (j >= ns) continue;
         const int64_t g = (int64_t)n + k0 + j;
-        for (int32_t k = L.grp_ptr[g]; k < L.grp_ptr[g + 1]; ++k) { pk.push_back(L.rem_pk[k]); val.push_back(L.rem_val[k]); }
+        for (int32_t k = L.grp_ptr[g]; k < L.grp_ptr[g + 1]; ++k) {
+          const int64_t ci = L.rem_pk[k] & kColMask;
+          uint32_t e = (kSpGlobal << 30) | (uint32_t)ci;
+          if (S.lm_cache && ci >= L.nPoseRows && ci < L.nPoseRows + L.l) e = (kSpLandmark << 30) | (uint32_t)(ci - L.nPoseRows);
+          pk.push_back(e); val.push_back(L.rem_val[k]);
+        }
         lq[j] = long_of[g];
         if (lq[j] >= 0) ++nlong;
       }
@@ -167,6 +212,8 @@ inline void build_stream_layout(const HostLayout &L, StreamHost &S) {
       S.cost[u] = 1.0f + 0.3f * (float)nlong;
     }
     S.max_rec_bytes = std::max<int>(S.max_rec_bytes, (int)(S.rec.size() - (size_t)S.rec_off[u] * 16));
+    S.info[(size_t)u * 4 + 0] = S.rec_off[u];
+    S.info[(size_t)u * 4 + 1] = (uint32_t)(S.rec.size() / 16) - S.rec_off[u];
   }
   S.rec_off[S.nStrips] = (uint32_t)(S.rec.size() / 16);
   if (S.rec.size() / 16 >= (size_t)0xffffffffu) throw std::invalid_argument("strip records exceed 64 GB");
@@ -203,13 +250,19 @@ inline void stream_to_csr(const HostLayout &L, const StreamHost &S, std::vector<
   auto emit = [&](int64_t ri, int64_t ci, double v) {
     if (v != 0.0) tr.push_back({L.int2ref[ri], L.int2ref[ci], v});
   };
+  auto column = [&](int u, uint32_t e) -> int64_t {  // internal column row of a packed spill entry of strip u
+    const uint32_t kind = e >> 30, idx = e & kColMask;
+    if (kind == kSpRange) return L.nPoseRows + (int64_t)S.info[(size_t)u * 4 + 2] + idx;
+    if (kind == kSpLandmark) return L.nPoseRows + idx;
+    return idx;
+  };
   for (int u = 0; u < S.nStrips; ++u) {
     const unsigned char *rec = S.rec.data() + (size_t)S.rec_off[u] * 16;
     const int32_t *hdr = (const int32_t *)rec;
     const int nsp = hdr[1];
     if (u < S.nPS) {
       const int Sl = hdr[0];
-      const int32_t *cols = hdr + 4, *gptr = cols + (size_t)Sl * S.CP, *lq = gptr + S.GP;
+      const int32_t *cols = hdr + 4, *gptr = cols + (size_t)Sl * S.CP, *lq = gptr + 36;
       const uint32_t *pk = (const uint32_t *)(lq + S.CP);
       const double *sv = (const double *)(pk + ((nsp + 3) & ~3));
       const double *qv = sv + ((nsp + 1) & ~1);
@@ -222,9 +275,9 @@ inline void stream_to_csr(const HostLayout &L, const StreamHost &S, std::vector<
               emit((int64_t)(i0 + p) * D1 + a, (int64_t)cols[(size_t)s * S.CP + p] + b,
                    q[(size_t)(b >> 1) * 64 + (size_t)(p * D1 + a) * 2 + (b & 1)]);
       }
-      for (int p = 0; p < np; ++p)
-        for (int k = gptr[p]; k < gptr[p + 1]; ++k)
-          emit((int64_t)(i0 + p) * D1 + (pk[k] >> 30), pk[k] & kColMask, sv[k]);
+      for (int j = 0; j < np * D1; ++j)
+        for (int k = gptr[j]; k < gptr[j + 1]; ++k)
+          emit((int64_t)i0 * D1 + j, column(u, pk[k]), sv[k]);
     } else {
       const int32_t *gptr = hdr + 4, *lq = gptr + 36;
       const uint32_t *pk = (const uint32_t *)(lq + 32);
@@ -233,7 +286,7 @@ inline void stream_to_csr(const HostLayout &L, const StreamHost &S, std::vector<
       for (int j = 0; j < ns; ++j) {
         const int64_t ri = L.nPoseRows + k0 + j;
         emit(ri, ri, S.sdiagP[(size_t)k0 + j]);
-        for (int k = gptr[j]; k < gptr[j + 1]; ++k) emit(ri, pk[k] & kColMask, sv[k]);
+        for (int k = gptr[j]; k < gptr[j + 1]; ++k) emit(ri, column(u, pk[k]), sv[k]);
       }
     }
   }
