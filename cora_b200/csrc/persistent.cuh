@@ -197,10 +197,11 @@ __device__ __forceinline__ void grid_sync(PCtx &c) {
   ph_begin(c);
   if (c.tid == 0) {
     c.target += (unsigned long long)c.G;
-    __threadfence();
-    atomicAdd(c.bar, 1ULL);
+    // arrive: release-add (MEMBAR.ALL.GPU + REDG; the block barrier above makes it cumulative over the CTA's
+    // writes); wait: acquire-load spin (LDG.STRONG.GPU + CCTL.IVALL: the L1 invalidation that makes plain loads
+    // of other CTAs' data coherent after the barrier).  No MEMBAR.SC on either side.
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(c.bar), "l"(1ULL) : "memory");
     while (ld_acquire_u64(c.bar) < c.target) { }
-    __threadfence();
   }
   ++c.nbar;
   ph_end(c, PH_SYNC);

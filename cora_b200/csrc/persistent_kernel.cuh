@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
         break;
       }
       const double beta = cg.beta;
-      cg_pupdate_flat(c, alpha, beta, v[V_S], v[V_P], v[V_V], v[V_T1]);  // s += alpha p ; p' = -v + beta p
+      if constexpr (STREAM) stream_pupdate<D, R>(L, A.sd, c, rg, alpha, beta, v[V_S], v[V_P], v[V_V], v[V_T1]);
+      else cg_pupdate_flat(c, alpha, beta, v[V_S], v[V_P], v[V_V], v[V_T1]);  // s += alpha p ; p' = -v + beta p
       if (L.numChunks > 0) hub_phase<D>(L, c, v[V_P], beta, v[V_V], -1.0, lp0);
       grid_sync(c);
       swp(V_P, V_T1);

@@ -723,4 +723,70 @@ __device__ __forceinline__ void stream_update(const DevLayout &L, const StreamDe
   ph_end(c, AXPY ? PH_UPDATE : PH_PRECOND);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// STPCG direction update over the warp's strips (IterativeSolvers.h:374,420), one pass:
+//   S += alpha P ;  Pn = -V + beta P
+// Stage: [S rows | P rows | V rows]; S' is staged in place, Pn over the V rows.
+template <int D, int R>
+__device__ __forceinline__ void stream_pupdate(const DevLayout &L, const StreamDev &SD, PCtx &c, Ring &rg, double alpha,
+                                               double beta, double *S, const double *P, const double *V, double *Pn) {
+  constexpr int YW = 32 * R + 2;
+  const int lane = c.tid & 31, warp = c.tid >> 5;
+  const int gw = c.b * (c.nth >> 5) + warp;
+  const int nwarp = c.nth >> 5;
+  const StripList SLst(SD.interleave ? SD.warp_strip[c.b] : SD.warp_strip[gw], SD.interleave ? warp : 0, SD.interleave ? nwarp : 1);
+  const int nk = SLst.count();
+  const int NS = SD.nstage;
+  ph_begin(c);
+  auto issue = [&](int u, int k) {
+    const StripWin W = strip_window<D, R>(L, SD, u);
+    double *stage = rg.base + (size_t)k * SD.stage_doubles;
+    unsigned long long *bar = rg.bar + k;
+    const unsigned yb = (unsigned)W.y_n * 8u;
+    if (CORA_STREAM_STORE == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, 3u * yb);
+    bulk_g2s(stage, S + W.y_al, yb, bar);
+    bulk_g2s(stage + YW, P + W.y_al, yb, bar);
+    bulk_g2s(stage + 2 * YW, V + W.y_al, yb, bar);
+  };
+  int k_next = 0;
+  for (int k = 0; k < NS - 1 && k_next < nk; ++k, ++k_next)
+    if (elect_one()) issue(SLst.at(k_next), k);
+  int st = 0;
+  for (int kcur = 0; kcur < nk; ++kcur) {
+    const int u = SLst.at(kcur);
+    if (k_next < nk) {
+      int sn = st + NS - 1;
+      if (sn >= NS) sn -= NS;
+      if (elect_one()) {
+        if (CORA_STREAM_STORE == 0) bulk_wait_read0();
+        issue(SLst.at(k_next), sn);
+      }
+      ++k_next;
+    }
+    double *stage = rg.base + (size_t)st * SD.stage_doubles;
+    mbar_wait(rg.bar + st, (rg.par >> st) & 1u);
+    rg.par ^= 1u << st;
+    const StripWin W = strip_window<D, R>(L, SD, u);
+    const int sh = (int)(W.y_lo - W.y_al);
+    double *sS = stage + sh, *sV = stage + 2 * YW + sh;
+    const double *sP = stage + YW + sh;
+    // the strip's own rows are one contiguous block: flat, conflict-free, no row structure needed
+    for (int i = lane; i < W.own_n; i += 32) {
+      const double pv = sP[i];
+      sS[i] = fma(alpha, pv, sS[i]);
+      sV[i] = fma(beta, pv, -sV[i]);
+    }
+    __syncwarp();
+    strip_store(S + W.y_lo, sS, W.own_n, lane);
+    strip_store(Pn + W.y_lo, sV, W.own_n, lane);
+    ++st;
+    if (st == NS) st = 0;
+  }
+  if (elect_one()) bulk_wait0();
+  __syncthreads();
+  ph_end(c, PH_PUPDATE);
+}
+
 }  // namespace cora_b200
