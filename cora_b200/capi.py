@@ -523,7 +523,7 @@ class Handle:
         return ms[: n.value].astype(np.float64)
 
     PHASES = ["hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc",
-              "q.wait", "q.qx", "q.epi", "q.store", "ch.pre", "ch.fwd", "ch.bwd", "ch.border", "ch.post"]
+              "q.wait", "q.qx", "q.epi", "q.store", "ch.pre", "ch.fwd", "ch.bwd", "ch.border", "ch.post", "smid", "reduce"]
 
     def phase_profile(self):
         """In-kernel phase profile of the last persistent TNT call: {phase: (total_us, count)}, grid, barriers."""

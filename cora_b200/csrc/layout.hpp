@@ -33,7 +33,8 @@ namespace cora_b200 {
 constexpr int kSMAX = 8;         // max block-ELL slots per pose
 constexpr int kLongGroup = 64;   // spill groups longer than this go to the hub kernel
 constexpr uint32_t kColMask = 0x3fffffffu;
-constexpr int kHubChunk = 128;   // hub-row entries per work item of the persistent kernel
+constexpr int kHubChunk = 128;   // smallest number of hub-row entries per work item of the persistent kernel
+constexpr int kHubItems = 296;   // work items aimed at (one per resident CTA of the persistent kernel on a 148-SM part)
 
 struct HostLayout {
   int d = 0, n = 0, m = 0, l = 0, D1 = 0;
@@ -297,11 +298,16 @@ inline void build_layout(HostLayout &L, int d, int n, int m, int nt, const int32
       L.tile_sp_cnt[t] = cnt;
       L.tile_sp_off[t + 1] = L.tile_sp_off[t] + cnt;
     }
+    // hub rows are split in chunks of equal size, about one chunk per resident CTA of the persistent kernel: the
+    // chunk partial sums are produced by all CTAs in one round and a hub row is left with few partials to add up
     L.long_chunk_ptr.assign(1, 0);
+    const int64_t chunk = std::max<int64_t>(kHubChunk, ((int64_t)L.long_pk.size() + kHubItems - 1) / kHubItems);
     for (size_t q = 0; q < L.long_grp.size(); ++q) {
-      for (int32_t k = L.long_ptr[q]; k < L.long_ptr[q + 1]; k += kHubChunk) {
-        L.chunk_beg.push_back(k);
-        L.chunk_end.push_back(std::min<int32_t>(k + kHubChunk, L.long_ptr[q + 1]));
+      const int64_t e = L.long_ptr[q + 1] - L.long_ptr[q];
+      const int64_t nch = std::max<int64_t>(1, (e + chunk - 1) / chunk), per = (e + nch - 1) / nch;
+      for (int64_t k = L.long_ptr[q]; k < L.long_ptr[q + 1]; k += per) {
+        L.chunk_beg.push_back((int32_t)k);
+        L.chunk_end.push_back((int32_t)std::min<int64_t>(k + per, L.long_ptr[q + 1]));
       }
       L.long_chunk_ptr.push_back((int32_t)L.chunk_beg.size());
     }

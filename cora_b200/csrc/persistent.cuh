@@ -38,7 +38,7 @@ struct TntDev {  // results of one persistent TNT call (device -> host)
   unsigned long long prof_ns[24];  // CTA 0's time per phase kind (PhaseId)
   unsigned int prof_cnt[24];
 };
-enum PhaseId { PH_HUB = 0, PH_GRAD, PH_HESS, PH_UPDATE, PH_PUPDATE, PH_RETRACT, PH_PRECOND, PH_CGINIT, PH_SYNC, PH_MISC, PH_Q_WAIT, PH_Q_QX, PH_Q_EPI, PH_Q_STORE, PH_CH_PRE, PH_CH_FWD, PH_CH_BWD, PH_CH_BORDER, PH_CH_POST, PH_SMID, PH_COUNT };
+enum PhaseId { PH_HUB = 0, PH_GRAD, PH_HESS, PH_UPDATE, PH_PUPDATE, PH_RETRACT, PH_PRECOND, PH_CGINIT, PH_SYNC, PH_MISC, PH_Q_WAIT, PH_Q_QX, PH_Q_EPI, PH_Q_STORE, PH_CH_PRE, PH_CH_FWD, PH_CH_BWD, PH_CH_BORDER, PH_CH_POST, PH_SMID, PH_REDUCE, PH_COUNT };
 
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
@@ -210,34 +210,44 @@ __device__ __forceinline__ void grid_sync(PCtx &c) {
 
 // Sum K per-thread accumulators over the whole grid.  On return every thread of every CTA holds
 // the same totals (summed in a fixed order) and *now_ns = CTA 0's clock at the barrier.
+// Partials are stored [k][cta] so that, after the barrier, every WARP re-reduces them on its own: coalesced
+// loads (the acquire of the barrier invalidated L1; the eight warps' requests for the same lines merge there),
+// a fixed per-lane order and a fixed xor tree -- no block barrier and no shared memory after the grid barrier.
 template <int K>
 __device__ __forceinline__ void grid_reduce(double (&acc)[K], PCtx &c, unsigned long long *now_ns) {
   static_assert(K <= kPPart, "too many partials");
-  block_sum<K>(acc, c.sred);
-  double *part = c.partials + (size_t)c.parity * ((size_t)c.G * kPPart + 8);
-  if (c.tid == 0) {
+  ph_begin(c);
+  const int lane = c.tid & 31, warp = c.tid >> 5, nw = c.nth >> 5;
 #pragma unroll
-    for (int k = 0; k < K; ++k) part[(size_t)c.b * kPPart + k] = acc[k];
-    if (c.b == 0) ((unsigned long long *)part)[(size_t)c.G * kPPart] = global_timer_ns();
+  for (int k = 0; k < K; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < K; ++k) c.sred[warp * K + k] = acc[k];
+  __syncthreads();
+  double *part = c.partials + (size_t)c.parity * ((size_t)c.G * kPPart + 8);
+  if (c.tid < K) {
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s += c.sred[i * K + c.tid];
+    part[(size_t)c.tid * c.G + c.b] = s;
   }
+  if (c.tid == 0 && c.b == 0) ((unsigned long long *)part)[(size_t)c.G * kPPart] = global_timer_ns();
+  ph_end(c, PH_REDUCE);
   grid_sync(c);
   double t[K];
 #pragma unroll
-  for (int k = 0; k < K; ++k) t[k] = 0.0;
-  for (int i = c.tid; i < c.G; i += c.nth)
-#pragma unroll
-    for (int k = 0; k < K; ++k) t[k] += __ldcg(part + (size_t)i * kPPart + k);
-  block_sum<K>(t, c.sred);
-  if (c.tid == 0) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) c.sbc[k] = t[k];
-    c.sbc[K] = __longlong_as_double((long long)__ldcg((const unsigned long long *)part + (size_t)c.G * kPPart));
+  for (int k = 0; k < K; ++k) {
+    double s = 0.0;
+    for (int i = lane; i < c.G; i += 32) s += part[(size_t)k * c.G + i];
+    t[k] = s;
   }
-  __syncthreads();
 #pragma unroll
-  for (int k = 0; k < K; ++k) acc[k] = c.sbc[k];
-  if (now_ns) *now_ns = (unsigned long long)__double_as_longlong(c.sbc[K]);
-  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+    acc[k] = t[k];
+  }
+  if (now_ns) *now_ns = ((const unsigned long long *)part)[(size_t)c.G * kPPart];
+  ph_end(c, PH_REDUCE);
   c.parity ^= 1;
 }
 

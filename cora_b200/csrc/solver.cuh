@@ -468,7 +468,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
     std::printf("\n");
   }
   if (getenv("CORA_B200_PHASE_PROFILE")) {
-    static const char *names[PH_COUNT] = {"hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc", "q.wait", "q.qx", "q.epi", "q.store", "ch.pre", "ch.fwd", "ch.bwd", "ch.border", "ch.post", "smid"};
+    static const char *names[PH_COUNT] = {"hub", "grad", "hess", "update", "pupdate", "retract", "precond", "cginit", "sync", "misc", "q.wait", "q.qx", "q.epi", "q.store", "ch.pre", "ch.fwd", "ch.bwd", "ch.border", "ch.post", "smid", "reduce"};
     std::printf("[persistent] %s grid %d, nbuf %d, smem %zu, barriers %lld, outer %d, CG %lld, device %.3f ms\n", h->persistent_stream ? "stream" : "tile", G, h->persistent_nbuf, smem, o.barriers, o.num_outer, o.total_inner, ms);
     for (int i = 0; i < PH_COUNT; ++i)
       if (o.prof_cnt[i]) std::printf("  %-8s n=%6u total %9.1f us  avg %8.2f us\n", names[i], o.prof_cnt[i], o.prof_ns[i] * 1e-3, o.prof_ns[i] * 1e-3 / o.prof_cnt[i]);
