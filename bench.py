@@ -138,18 +138,26 @@ def initial_guess(arrays, gt, seed, kind):
     return synthetic.perturbed_ground_truth(w["d"], w["n"], w["l"], arrays, gt, w["rank"], seed=seed)
 
 
-def config_dict(args, N, nnz, m):
+def config_dict(args, N, nnz, m, impl="ours"):
     w = WORKLOAD
-    return {"workload": "synthetic 100k-pose SE(3) + 20k range factors (BASELINE configs[2]), rank %d" % w["rank"],
-            "n_poses": w["n"], "n_landmarks": w["l"], "n_ranges": int(m), "N": int(N), "nnz": int(nnz),
-            "rank": w["rank"], "preconditioner": "Jacobi", "outer_iterations_per_step": args.outer,
-            "untimed_startup_outer_iterations": args.pre_outer, "max_TPCG_iterations": 80,
-            "init": {"warm": "ground truth perturbed (rotations 0.05 rad, positions 0.5 m), random SO(r) factor",
-                     "odom": "odometry chain + random landmarks + random SO(r) factor "
-                             "(paper_experiments.cpp:426-534)"}[args.init],
-            "restarts": "one restart per GPU (seed = rank)",
-            "l2": "working set of one CG iteration (Q 41 MB + 8 vectors x 16.8 MB = 175 MB) exceeds the 126 MB L2; "
-                  "no explicit flush"}
+    cfg = {"workload": "synthetic 100k-pose SE(3) + 20k range factors (BASELINE configs[2]), rank %d" % w["rank"],
+           "n_poses": w["n"], "n_landmarks": w["l"], "n_ranges": int(m), "N": int(N), "nnz": int(nnz),
+           "rank": w["rank"], "preconditioner": "Jacobi",
+           "init": {"warm": "ground truth perturbed (rotations 0.05 rad, positions 0.5 m), random SO(r) factor",
+                    "odom": "odometry chain + random landmarks + random SO(r) factor "
+                            "(paper_experiments.cpp:426-534)"}[args.init],
+           "restarts": "one restart per GPU (seed = rank)"}
+    if impl == "ours":
+        cfg.update({"outer_iterations_per_step": args.outer, "untimed_startup_outer_iterations": args.pre_outer,
+                    "max_TPCG_iterations": 80,
+                    "l2": "working set of one CG iteration (Q 41 MB + 8 vectors x 16.8 MB = 175 MB) exceeds the 126 MB "
+                          "L2; no explicit flush"})
+    else:  # the CPU arm runs a BOUNDED SAMPLE of a step: what it runs is what it prints
+        cfg.update({"outer_iterations_per_step": 1, "untimed_startup_outer_iterations": args.ref_pre,
+                    "max_TPCG_iterations": args.ref_cg,
+                    "sample_of": "one of the %d trust-region iterations of a GPU step, same problem, same initial "
+                                 "guess, same STPCG budget" % args.outer})
+    return cfg
 
 
 def cpu_tnt_sample(arrays, gt, Q, m, args, steps, warmup, threads, min_seconds=0.0):
@@ -199,12 +207,106 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config_dict(args, N, Q.nnz, m),
+            "data": "synthetic", "config": config_dict(args, N, Q.nnz, m, impl="reference"),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference itself cannot be built on this image (needs Eigen3 + SuiteSparse): this is the "
                     "oracle's C++ port, kind=port"}
     print(json.dumps(line))
+
+
+def roofline_cfg5(torch, dist, world, local, stream, peak, n=1_000_000, reps=30):
+    """BASELINE configs[4]: synthetic 1M-pose SE(3) graph, rank 5.  HBM-roofline numbers of the data-matrix product
+    (Problem::dataMatrixProduct, src/CORA_problem.cpp:742-757) and of full CG iterations.  The path does not shard a
+    single solve: with N GPUs every rank runs its own replica and the aggregate is reported."""
+    from cora_b200 import capi, synthetic
+    d, r = 3, 5
+    l, m = max(10, n // 10000), n // 5
+    arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=42)
+    Q = capi.assemble(d, n, l, arrays)
+    m = len(arrays["rg_w"])
+    N = d * n + m + n + l
+    h = capi.Handle(d, n, m, n + l, Q, preconditioner=capi.PRECON_JACOBI, device=local, stream=stream)
+    x0 = h.project_to_manifold(synthetic.perturbed_ground_truth(d, n, l, arrays, gt, r, seed=0))
+    h.set_iterate(x0)
+    ab = algorithmic_bytes(Q.nnz, N, r)
+    h.spmm_resident(3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = h.spmm_resident(reps)          # CUDA events around one launch that runs `reps` products back to back
+    pre = h.tnt_resident(capi.default_tnt_params(max_iterations=12, max_computation_time=0.0))  # trust-region start-up
+    res = h.tnt_resident(capi.default_tnt_params(max_iterations=2, max_computation_time=0.0,
+                                                 Delta0=pre.trust_region_radius[-1]))
+    clocks = sampler.stop()
+    t_spmm = ms * 1e-3 / reps
+    cg, outer = int(sum(res.inner_iterations)), len(res.inner_iterations)
+    V = 8 * N * r
+    b_outer = 2 * (12 * Q.nnz + 4 * (N + 1)) + 19 * V + 8 * N
+    t_cg = res.device_time
+    vals = torch.tensor([t_spmm, t_cg, float(cg)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t_spmm, t_cg, cg_all = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        cg_all = float(cg)
+    mxp, _ = ({}, {}) if not hasattr(h, "phase_profile_ctas") else (h.phase_profile_ctas(), None)
+    h.close()
+    gbs_spmm = ab["spmm"] / t_spmm / 1e9
+    gbs_cg = (cg * ab["cg_iter"] + outer * b_outer) / res.device_time / 1e9
+    return {"workload": "synthetic %d-pose SE(3) + %d ranges, %d landmarks, rank %d (BASELINE configs[4]); one replica "
+                        "per GPU" % (n, m, l, r),
+            "N": int(N), "nnz": int(Q.nnz), "replicas": world,
+            "spmm": {"us": 1e6 * t_spmm, "reps": reps, "algorithmic_bytes": ab["spmm"], "achieved_gbs": gbs_spmm,
+                     "frac": gbs_spmm / peak, "aggregate_gbs": world * gbs_spmm,
+                     "timing": "CUDA events around one cooperative launch of `reps` products; max over ranks"},
+            "cg_iteration": {"us": 1e6 * t_cg / max(1, cg), "iterations_timed": cg, "outer_iterations": outer,
+                             "algorithmic_bytes": ab["cg_iter"], "achieved_gbs": gbs_cg, "frac": gbs_cg / peak,
+                             "cg_it_per_s_all_replicas": cg_all / t_cg,
+                             "phases_us_slowest_cta": {k: v[0] for k, v in mxp.items()}},
+            "peak_gbs": peak, "clocks": clocks}
+
+
+def spmv_cfg2(local, stream, reps=1000):
+    """BASELINE configs[1]: Single-Drone SE(3), rank 5 -- the data-matrix product in isolation, `reps` repetitions,
+    GPU (one cooperative launch) against the CPU restatement of Eigen's row-major-sparse x column-major-dense product
+    (one pass over Q per column; 1 thread as the reference runs it, and all host threads)."""
+    from cora_b200 import capi
+    from oracle import cpu_ref
+    path = os.path.join(ROOT, "tests", "golden", "single_drone.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    d, n, l = int(g["d"]), int(g["n"]), int(g["l"])
+    arrays = {k: g[k] for k in g.files if k not in ("d", "n", "l")}
+    Q = capi.assemble(d, n, l, arrays)
+    m = len(arrays["rg_w"])
+    r = 5
+    N = d * n + m + n + l
+    X = np.asfortranarray(np.random.default_rng(0).standard_normal((N, r)))
+    with capi.Handle(d, n, m, n + l, Q, preconditioner=capi.PRECON_JACOBI, device=local, stream=stream) as h:
+        h.set_iterate(X)
+        h.spmm_resident(10)
+        gpu_us = 1e3 * h.spmm_resident(reps) / reps
+        got = h.get_work_vector(1, r)
+    out = {"workload": "Single-Drone SE(3) (examples/data/single_drone.pyfg), rank 5, N = %d, nnz = %d" % (N, Q.nnz),
+           "reps": reps, "gpu_us_per_product": gpu_us}
+    for threads in (1, os.cpu_count() or 1):
+        R = cpu_ref.CpuRef(d, n, m, n + l, Q, preconditioner=1, threads=threads)
+        R.data_matrix_product(X)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ref = R.data_matrix_product(X)
+        us = 1e6 * (time.perf_counter() - t0) / reps
+        out["cpu_us_per_product_%s" % ("1_thread" if threads == 1 else "all_threads")] = us
+        out["cpu_threads_all"] = R.threads
+        R.close()
+    out["max_rel_diff_gpu_vs_cpu"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+    out["speedup_vs_1_thread"] = out["cpu_us_per_product_1_thread"] / gpu_us
+    return out
 
 
 # ------------------------------------------------------------------------ our arm ---
@@ -313,37 +415,81 @@ def run_ours(args):
     timed(step_e2e, args.warmup)
     Te, its_e, _, _, _ = timed(step_e2e, args.steps)
 
-    # ---- solve-to-certificate of the whole problem (BASELINE metric, second half): staircase from the same
-    # start with the reference's default preconditioner; reported beside the CG throughput, not timed into it ----
-    solve_cert = None
-    if not args.no_solve and rank == 0:
+    # ---- solve-to-certificate (BASELINE metric, second half; configs[3] with N > 1): every rank runs the staircase
+    # on ITS restart with the reference's default preconditioner, then the best certified solution is gathered over
+    # NCCL.  Reported beside the CG throughput, not timed into it. ----
+    solve_cert = gather = None
+    if not args.no_solve:
+        comm = None
+        if world > 1:
+            from cora_b200 import restarts
+            comm = restarts.make_native_comm(dist, local)      # communicator created (and warmed) before the clock starts
         h.set_preconditioner(capi.PRECON_REG_CHOLESKY)
-        torch.cuda.synchronize()
+        barrier()
         ts = time.perf_counter()
         out = h.solve(x0, max_rank=7, params=capi.default_tnt_params(max_computation_time=0.0))
         torch.cuda.synchronize()
-        solve_cert = {"seconds": time.perf_counter() - ts, "certified": bool(out["certified"]),
+        t_solve = time.perf_counter() - ts
+        # the PSD test of S + eta I at the solution on its own (src/CORA_utils.cpp:33-57): the certificate proper,
+        # also when the staircase itself stopped on the reference's sv-ratio short-circuit
+        Yd = out["x"]
+        eta = min(max(out["f"] * 5e-6, 1e-7), 1e-1)
+        tp = time.perf_counter()
+        cert = h.certify_solution(Yd, eta, max(10, d + 2))
+        torch.cuda.synchronize()
+        t_psd = time.perf_counter() - tp
+        tall = torch.tensor([t_solve], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tall, op=dist.ReduceOp.MAX)
+        solve_cert = {"seconds": t_solve, "seconds_all_ranks_max": float(tall[0]), "certified": bool(out["certified"]),
+                      "refined_certified": bool(out["refined_certified"]),
                       "f": float(out["f"]), "lifted_f": float(out["lifted_f"]), "lifted_rank": int(out["lifted_rank"]),
                       "cg_iterations": int(out["total_cg_iterations"]), "preconditioner": "RegularizedCholesky",
                       "stages": [{"rank": s["rank"], "status": s["status"], "outer": s["outer"], "cg": s["cg"],
-                                  "certified": s["certified"], "tnt_s": s["tnt_seconds"], "cert_s": s["cert_seconds"]}
-                                 for s in out["stages"]],
-                      "note": "rank 5 -> 7 staircase + rounding + refinement through cora_b200_solve(), host buffers in/out"}
+                                  "certified": s["certified"], "cert_branch": s["cert_branch"], "theta": s["theta"],
+                                  "tnt_s": s["tnt_seconds"], "cert_s": s["cert_seconds"]} for s in out["stages"]],
+                      "psd_test_of_refined_solution": {"certified": bool(cert.is_certified), "branch": h.last_cert_branch,
+                                                       "seconds": t_psd, "eta": eta},
+                      "note": "rank 5 staircase (max rank 7) + rounding + refinement through cora_b200_solve(), host "
+                              "buffers in/out; restart seed = rank"}
+        if world > 1:
+            # the refined rank-d solution of this rank's restart is the resident iterate of its handle
+            h.set_iterate(out["x"])
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tg = time.perf_counter()
+            g0.record()
+            good = bool(out["refined_certified"] or out["certified"])
+            win, wf = h.gather_best_resident(comm, world, rank, float(out["f"]), good)
+            g1.record()
+            torch.cuda.synchronize()
+            t_g = time.perf_counter() - tg
+            xbest = h.get_iterate(d)
+            same = bool(np.array_equal(xbest, out["x"])) if int(win) == rank else None
+            chk = torch.tensor([float(np.abs(xbest).sum())], dtype=torch.float64, device="cuda")
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            tmax = torch.tensor([t_g], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            gather = {"winner_rank": int(win), "winner_f": float(wf), "ms": 1e3 * float(tmax[0]),
+                      "ms_device_rank0": g0.elapsed_time(g1), "bytes_broadcast": int(8 * N * d),
+                      "winner_iterate_bit_identical_on_winner": same,
+                      "all_ranks_hold_the_same_iterate": bool(float(lo[0]) == float(hi[0])),
+                      "transport": "ncclAllGather of {f, certified, rank} + ncclBroadcast of the winner's resident N x d "
+                                   "iterate, device to device (library communicator, warmed at creation)"}
+            comm.close()
         h.set_preconditioner(capi.PRECON_JACOBI)
 
-    # ---- the only exchange of the multi-GPU path: gather the best restart (outside the timed region) ----
-    gather = None
-    if world > 1:
-        from cora_b200 import restarts
-        xr = np.ascontiguousarray(pin_out.numpy().T)           # N x r, this rank's iterate after the e2e leg
-        comm = restarts.make_native_comm(dist, local)
-        barrier()
-        tg = time.perf_counter()
-        win, wf, _ = restarts.gather_best(dist, float(resC.f), False, xr, handle=h, comm=comm)
-        torch.cuda.synchronize()
-        gather = {"winner_rank": int(win), "winner_f": float(wf), "ms": 1e3 * (time.perf_counter() - tg),
-                  "bytes_broadcast": int(8 * N * r), "transport": "ncclAllGather + ncclBroadcast (library communicator)"}
-        comm.close()
+    # ---- the two other BASELINE configurations the north star asks numbers for ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md) (of fallback)"
+    mxp = h.phase_profile_ctas()
+    h.close()
+    cfg5 = None if args.no_cfg5 else roofline_cfg5(torch, dist, world, local, stream, peak)
+    cfg2 = None if (args.no_cfg2 or rank != 0) else spmv_cfg2(local, stream)
 
     # ---- aggregate over ranks ----
     vals = torch.tensor([T, Te, float(its), float(its_e), float(launches)], dtype=torch.float64, device="cuda")
@@ -357,11 +503,6 @@ def run_ours(args):
     e2e = its_e / Te
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md) (of fallback)"
         # algorithmic bytes of everything the kernel did in the timed steps: per CG iteration
         # B_cgiter, per outer iteration retract 4V + f/grad product Q+3V + model Hess-vec Q+4V +
         # preconditioned gradient 3V+8N + STPCG init 5V
@@ -370,29 +511,37 @@ def run_ours(args):
         b_outer = 2 * q + 19 * V + 8 * N
         total_bytes = its_rank0 * ab["cg_iter"] + outer_rank0 * b_outer
         ach = total_bytes / t_kernel / 1e9
-        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (one launch of a smaller slice):
-        # the measured traffic / algorithmic ratio of that capture, scaled to this run's launch
+        # DRAM traffic: cannot be measured without a profiler attached.  What is printed is the traffic / algorithmic
+        # ratio of the committed `ncu --set full` capture of the same kernel (one launch of a smaller slice of the same
+        # workload), scaled to this run's algorithmic bytes per launch -- labelled as such.
         traffic, traffic_note = None, None
-        try:
-            import csv
-            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01f_persistent_ncu_raw.csv"))))
-            hdr, units, vals = rows[0], rows[1], rows[2]
-            get = lambda name: float(vals[hdr.index(name)].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[hdr.index(name)]]
-            cap = get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
-            cap_alg = 160 * ab["cg_iter"] + 2 * b_outer          # the captured launch: 2 outer iterations, 160 CG iterations
-            traffic = cap / cap_alg * total_bytes / max(1, args.steps)
-            traffic_note = ("ncu --set full of one launch with 160 CG + 2 outer iterations (profiles/r01f_persistent_ncu_raw.csv): "
-                            "%.2f GB DRAM read+write vs %.2f GB algorithmic (ratio %.3f); scaled to this launch's algorithmic bytes"
-                            % (cap / 1e9, cap_alg / 1e9, cap / cap_alg))
-        except Exception:
-            pass
+        for cap_file in ("r02_persistent_ncu_raw.csv", "r01f_persistent_ncu_raw.csv"):
+            try:
+                import csv
+                rows = list(csv.reader(open(os.path.join(ROOT, "profiles", cap_file))))
+                hdr, units, vals = rows[0], rows[1], rows[2]
+                get = lambda name: float(vals[hdr.index(name)].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[hdr.index(name)]]
+                cap = get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
+                cap_alg = 160 * ab["cg_iter"] + 2 * b_outer      # the captured launch: 2 outer iterations, 160 CG iterations
+                traffic = cap / cap_alg * total_bytes / max(1, args.steps)
+                traffic_note = ("ncu --set full of one launch with 160 CG + 2 outer iterations (profiles/%s): %.2f GB DRAM "
+                                "read+write vs %.2f GB algorithmic (ratio %.3f); scaled to this launch's algorithmic bytes"
+                                % (cap_file, cap / 1e9, cap_alg / 1e9, cap / cap_alg))
+                break
+            except Exception:
+                continue
         phases = {}
         for k, (us, cnt) in prof.items():
             if cnt:
                 phases[k] = {"avg_us": us / cnt, "count": cnt}
+        for k, (mx_us, md_us) in mxp.items():   # every CTA's clock: the phase lasts as long as its slowest CTA
+            if k in phases:
+                phases[k]["slowest_cta_avg_us"] = mx_us
+                phases[k]["median_cta_avg_us"] = md_us
         if "hess" in phases:
+            t_h = phases["hess"].get("slowest_cta_avg_us", phases["hess"]["avg_us"])
             phases["hess"]["algorithmic_bytes"] = ab["hessvec"]
-            phases["hess"]["achieved_gbs"] = ab["hessvec"] / (phases["hess"]["avg_us"] * 1e-6) / 1e9
+            phases["hess"]["achieved_gbs"] = ab["hessvec"] / (t_h * 1e-6) / 1e9
             phases["hess"]["frac"] = phases["hess"]["achieved_gbs"] / peak
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True,
@@ -403,6 +552,7 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * N * r),
                         "d2h_bytes_per_step": int(8 * N * r)},
                 "gpu_launches": int(launches), "gather_best": gather, "solve_to_cert": solve_cert,
+                "roofline_cfg5": cfg5, "spmv_cfg2": cfg2,
                 "roofline": {"bound": "hbm",
                              "kernel": "k_tnt_persistent<3>: one cooperative launch per step runs the whole TNT slice "
                                        "(%d CG iterations + %d outer iterations per launch on average)"
@@ -411,18 +561,24 @@ def run_ours(args):
                              "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": total_bytes / max(1, args.steps),
                              "avg_launch_us": 1e6 * t_kernel / max(1, args.steps), "launches_timed": args.steps,
-                             "traffic": traffic, "traffic_source": traffic_note, "grid": grid,
+                             "traffic": traffic, "traffic_kind": "scaled from committed capture (not measured in this run)",
+                             "traffic_source": traffic_note, "grid": grid,
                              "timing": "CUDA events on the launching stream around every launch of the timed steps",
-                             "phases_in_kernel_globaltimer_cta0": phases}}
+                             "phases_in_kernel_globaltimer": phases,
+                             "phases_note": "avg_us: CTA 0's clock; slowest_cta_avg_us / median_cta_avg_us: over all CTAs of "
+                                            "the last timed launch"}}
         if not args.no_cpu_baseline and world == 1:
-            v, cits, cT, used = cpu_tnt_sample(arrays, gt, Q, m, args, 2, 0, os.cpu_count() or 1, min_seconds=10.0)
+            ncpu = os.cpu_count() or 1
+            v, cits, cT, used = cpu_tnt_sample(arrays, gt, Q, m, args, 2, 0, ncpu, min_seconds=10.0)
+            v1, cits1, cT1, _ = cpu_tnt_sample(arrays, gt, Q, m, args, 1, 0, 1, min_seconds=6.0)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": used, "kind": "port",
+                "value_1_thread": v1,
                 "sample": "steps of (1 TNT outer iteration, <= %d CG iterations) for >= 10 s of the same problem and initial guess after "
                           "%d untimed outer iterations; C++ restatement of the reference CPU path (oracle/cpu_ref.cpp), "
-                          "%d threads; %d CG iterations in %.1f s" % (args.ref_cg, args.ref_pre, used, cits, cT)}
+                          "%d threads: %d CG iterations in %.1f s; the reference itself is single-threaded: 1 thread: %d CG "
+                          "iterations in %.1f s" % (args.ref_cg, args.ref_pre, used, cits, cT, cits1, cT1)}
         print(json.dumps(line))
-    h.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -438,10 +594,12 @@ def main():
     ap.add_argument("--init", default="warm", choices=["warm", "odom"])
     ap.add_argument("--pre-outer", type=int, default=12,
                     help="untimed TNT outer iterations before the first step (trust-region start-up)")
-    ap.add_argument("--ref-cg", type=int, default=40, help="CG cap per outer iteration of the CPU sample")
+    ap.add_argument("--ref-cg", type=int, default=80, help="CG cap per outer iteration of the CPU sample (= the GPU arm's)")
     ap.add_argument("--ref-pre", type=int, default=8, help="untimed outer iterations before the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the solve-to-certificate leg")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the 1M-pose roofline leg (BASELINE configs[4])")
+    ap.add_argument("--no-cfg2", action="store_true", help="skip the Single-Drone SpMV leg (BASELINE configs[1])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

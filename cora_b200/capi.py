@@ -65,14 +65,17 @@ class StageC(C.Structure):
     _fields_ = [("rank", C.c_int32), ("status", C.c_int32), ("num_outer", C.c_int32), ("certified", C.c_int32),
                 ("cg_iterations", C.c_int64), ("f", C.c_double), ("gradfx_norm", C.c_double),
                 ("theta", C.c_double), ("eta", C.c_double), ("tnt_seconds", C.c_double),
-                ("cert_seconds", C.c_double)]
+                ("cert_seconds", C.c_double), ("cert_branch", C.c_int32), ("reserved", C.c_int32)]
+
+
+CERT_BRANCH = ["none", "sv_ratio", "psd", "eigenpair", "inconclusive"]
 
 
 class SolveResultC(C.Structure):
     _fields_ = [("f", C.c_double), ("lifted_f", C.c_double), ("final_rank", C.c_int32),
                 ("lifted_rank", C.c_int32), ("certified", C.c_int32), ("num_stages", C.c_int32),
                 ("total_cg_iterations", C.c_int64), ("seconds", C.c_double),
-                ("stage_capacity", C.c_int32), ("reserved", C.c_int32), ("stages", C.POINTER(StageC))]
+                ("stage_capacity", C.c_int32), ("refined_certified", C.c_int32), ("stages", C.POINTER(StageC))]
 
 
 @dataclass
@@ -119,7 +122,7 @@ SYMBOLS = [
     "cora_b200_tnt_default_params", "cora_b200_tnt", "cora_b200_set_iterate", "cora_b200_get_iterate",
     "cora_b200_tnt_resident", "cora_b200_spmm_resident", "cora_b200_certify", "cora_b200_saddle_escape",
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
-    "cora_b200_strip_layout_roundtrip",
+    "cora_b200_strip_layout_roundtrip", "cora_b200_effective_preconditioner", "cora_b200_last_cert_branch", "cora_b200_phase_profile_ctas", "cora_b200_gather_best_resident",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
     "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
@@ -352,6 +355,19 @@ class Handle:
         self.close()
 
     # -- configuration ------------------------------------------------------
+    @property
+    def effective_preconditioner(self):
+        """The preconditioner applied (RegularizedCholesky falls back to Jacobi on non-chain graphs)."""
+        v = C.c_int(0)
+        _check(self._lib.cora_b200_effective_preconditioner(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def last_cert_branch(self):
+        v = C.c_int(0)
+        _check(self._lib.cora_b200_last_cert_branch(self._h, C.byref(v)))
+        return CERT_BRANCH[v.value]
+
     def set_preconditioner(self, preconditioner, reg_chol_max_cond=0.0):
         _check(self._lib.cora_b200_set_preconditioner(self._h, C.c_int(preconditioner),
                                                       C.c_double(reg_chol_max_cond)))
@@ -536,6 +552,12 @@ class Handle:
         prof = {name: (float(tot[i]), int(cnt[i])) for i, name in enumerate(self.PHASES[: n.value])}
         return prof, grid.value, bars.value
 
+    def phase_profile_ctas(self):
+        """{phase: (avg us on the slowest CTA, avg us on the median CTA)} of the last persistent TNT call."""
+        mx, md = np.zeros(24), np.zeros(24)
+        _check(self._lib.cora_b200_phase_profile_ctas(self._h, C.c_int(24), _p(mx), _p(md)))
+        return {name: (float(mx[i]), float(md[i])) for i, name in enumerate(self.PHASES) if mx[i] > 0}
+
     def get_work_vector(self, which, r):
         out = np.empty((self.N, r), order="F")
         _check(self._lib.cora_b200_get_work_vector(self._h, C.c_int(which), C.c_int(r), _p(out)))
@@ -588,6 +610,13 @@ class Handle:
                                                C.byref(w), C.byref(wf)))
         return w.value, wf.value, X
 
+    def gather_best_resident(self, comm: "NcclComm", world_size, rank, f, certified):
+        """Device-resident variant: the winner's resident iterate becomes every rank's resident iterate."""
+        w, wf = C.c_int(0), C.c_double(0)
+        _check(self._lib.cora_b200_gather_best_resident(comm._c, self._h, C.c_int(world_size), C.c_int(rank),
+                                                        C.c_double(f), C.c_int(int(certified)), C.byref(w), C.byref(wf)))
+        return w.value, wf.value
+
     def solve(self, X0, max_rank=20, params: Optional[TntParams] = None, verbose=False):
         X0 = self._mat(X0)
         params = params or default_tnt_params()
@@ -604,7 +633,9 @@ class Handle:
             s = stages[i]
             st.append(dict(rank=s.rank, status=TNT_STATUS[s.status], outer=s.num_outer,
                            certified=bool(s.certified), cg=s.cg_iterations, f=s.f, grad=s.gradfx_norm,
-                           theta=s.theta, eta=s.eta, tnt_seconds=s.tnt_seconds, cert_seconds=s.cert_seconds))
+                           theta=s.theta, eta=s.eta, tnt_seconds=s.tnt_seconds, cert_seconds=s.cert_seconds,
+                           cert_branch=CERT_BRANCH[s.cert_branch]))
         return dict(x=out, f=res.f, lifted_f=res.lifted_f, final_rank=res.final_rank,
                     lifted_rank=res.lifted_rank, certified=bool(res.certified),
+                    refined_certified=bool(res.refined_certified),
                     total_cg_iterations=res.total_cg_iterations, seconds=res.seconds, stages=st)

@@ -233,6 +233,20 @@ extern "C" int cora_b200_set_preconditioner(cora_b200_t *h, int preconditioner, 
   API_END
 }
 
+extern "C" int cora_b200_effective_preconditioner(const cora_b200_t *h, int *preconditioner) {
+  API_BEGIN
+  require(h && preconditioner, "NULL argument");
+  *preconditioner = h->precond;
+  API_END
+}
+
+extern "C" int cora_b200_last_cert_branch(const cora_b200_t *h, int *branch) {
+  API_BEGIN
+  require(h && branch, "NULL argument");
+  *branch = h->last_cert_branch;
+  API_END
+}
+
 extern "C" int cora_b200_get_reg_lambda(const cora_b200_t *h, double *lambda) {
   API_BEGIN
   require(h && lambda, "NULL argument");

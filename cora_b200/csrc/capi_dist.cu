@@ -79,6 +79,18 @@ extern "C" int cora_b200_nccl_init(void **comm, int device, int world_size, int 
   std::memcpy(&id, id128, sizeof(id));
   ncclComm_t c = nullptr;
   nccl_check(nccl().CommInitRank(&c, world_size, id, rank), "ncclCommInitRank");
+  {  // warm the communicator: the first collective on a cold communicator costs ~1 s (channel set-up); pay it here,
+     // not inside the gather that follows a solve
+    cudaStream_t s = nullptr;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    DevBuf<double> w;
+    w.alloc(2 * (size_t)world_size + 2);
+    CUDA_CHECK(cudaMemsetAsync(w.p, 0, w.n * sizeof(double), s));
+    nccl_check(nccl().AllGather(w.p + 2 * world_size, w.p, 2, ncclDouble, c, s), "ncclAllGather (warm-up)");
+    nccl_check(nccl().Broadcast(w.p, w.p, 2, ncclDouble, 0, c, s), "ncclBroadcast (warm-up)");
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaStreamDestroy(s);
+  }
   *comm = (void *)c;
   API_END
 }
@@ -118,6 +130,43 @@ extern "C" int cora_b200_gather_best(void *nccl_comm, cora_b200_t *h, int world_
   nccl_check(nccl().Broadcast(h->d_stage.p, h->d_stage.p, nE, ncclDouble, win, comm, h->stream), "ncclBroadcast");
   if (my_rank != win)
     CUDA_CHECK(cudaMemcpyAsync(X_inout, h->d_stage.p, nE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  *winner_rank = win;
+  if (winner_f) *winner_f = fs[win];
+  API_END
+}
+
+// Device-resident variant: every rank holds its solution as the resident iterate of its handle (rank r, as left by
+// cora_b200_solve / cora_b200_tnt_resident); the winner's iterate is broadcast handle to handle over NVLink with no
+// host staging and becomes the resident iterate of every rank.
+extern "C" int cora_b200_gather_best_resident(void *nccl_comm, cora_b200_t *h, int world_size, int my_rank, double f,
+                                              int certified, int *winner_rank, double *winner_f) {
+  API_BEGIN
+  require(nccl_comm && h && winner_rank, "NULL argument");
+  require(world_size > 0 && my_rank >= 0 && my_rank < world_size, "bad argument");
+  require(h->resident_r > 0, "no resident iterate on this handle");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  ncclComm_t comm = (ncclComm_t)nccl_comm;
+  const int r = h->resident_r;
+  DevBuf<double> rec;
+  rec.alloc(3 * (size_t)world_size + 3);
+  double mine[3] = {f, certified ? 1.0 : 0.0, (double)r};
+  CUDA_CHECK(cudaMemcpyAsync(rec.p + 3 * world_size, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+  nccl_check(nccl().AllGather(rec.p + 3 * world_size, rec.p, 3, ncclDouble, comm, h->stream), "ncclAllGather");
+  std::vector<double> all(3 * (size_t)world_size);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), rec.p, all.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  std::vector<double> fs(world_size);
+  std::vector<int> cs(world_size);
+  for (int i = 0; i < world_size; ++i) {
+    fs[i] = all[3 * i]; cs[i] = all[3 * i + 1] != 0.0;
+    if ((int)all[3 * i + 2] != r) throw Error(CORA_B200_EINVAL, "gather_best_resident: the ranks hold iterates of different rank");
+  }
+  int win = 0;
+  if (cora_b200_select_best(world_size, fs.data(), cs.data(), &win) != CORA_B200_OK)
+    throw Error(CORA_B200_ERUNTIME, cora_b200_last_error());
+  double *X = h->ws[V_X].p;  // same internal layout on every rank (same problem)
+  nccl_check(nccl().Broadcast(X, X, (size_t)h->DL.N * r, ncclDouble, win, comm, h->stream), "ncclBroadcast");
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   *winner_rank = win;
   if (winner_f) *winner_f = fs[win];

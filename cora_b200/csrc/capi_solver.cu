@@ -172,6 +172,24 @@ extern "C" int cora_b200_get_work_vector(cora_b200_t *h, int which, int r, doubl
   API_END
 }
 
+extern "C" int cora_b200_phase_profile_ctas(cora_b200_t *h, int capacity, double *max_us, double *median_us) {
+  API_BEGIN
+  require(h && max_us && median_us, "NULL argument");
+  require(h->h_tntdev != nullptr && h->prof_all_grid > 0, "no persistent TNT call has run on this handle");
+  const TntDev &o = *(const TntDev *)h->h_tntdev;
+  const int n = std::min(capacity, (int)PH_COUNT), G = h->prof_all_grid;
+  std::vector<double> col((size_t)G);
+  for (int i = 0; i < n; ++i) {
+    max_us[i] = median_us[i] = 0.0;
+    if (!o.prof_cnt[i]) continue;
+    for (int b = 0; b < G; ++b) col[b] = h->h_prof_all[(size_t)b * PH_COUNT + i] * 1e-3 / o.prof_cnt[i];
+    std::sort(col.begin(), col.end());
+    max_us[i] = col[G - 1];
+    median_us[i] = col[G / 2];
+  }
+  API_END
+}
+
 extern "C" int cora_b200_phase_profile(cora_b200_t *h, int capacity, double *total_us, int64_t *count,
                                        int *n_kinds, int *grid, int64_t *barriers) {
   API_BEGIN

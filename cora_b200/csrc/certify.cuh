@@ -294,6 +294,7 @@ inline std::vector<double> gram_host(H *h, const double *A, int ra, const double
 // ------------------------------------------------------------- certification ---
 struct CertOut {
   bool certified = false;
+  int branch = CORA_B200_CERT_NONE;
   double theta = 0.0;
   int64_t iters = 0;
   bool have_x = false;  // direction of negative curvature left in ws[V_T1] (N x 1 internal)
@@ -387,6 +388,7 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
     sym_eig_jacobi(r, G, ev, V);
     if (ev[r - 1] / std::max(ev[0], 0.0) > 1e12 || !(ev[0] > 0.0)) {
       out.certified = true;
+      out.branch = CORA_B200_CERT_SV_RATIO;
       return out;
     }
   }
@@ -413,6 +415,7 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
     C = nullptr;
     if (pd) {  // S + eta I > 0  (src/CORA_utils.cpp:33-57)
       out.certified = true;
+      out.branch = CORA_B200_CERT_PSD;
       return out;
     }
   } catch (const Error &e) {
@@ -442,6 +445,7 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
     out.iters = L.steps;
     out.theta = L.theta_S;
     out.have_x = true;
+    out.branch = CORA_B200_CERT_EIGENPAIR;
     if (verbose) std::printf("  certify: shift-invert Lanczos sigma=%.3e steps=%d theta=%.6e\n", sigma, L.steps, L.theta_S);
   } else {
     auto op = [&](const double *q, double *y) { Sx(q, y); };
@@ -449,9 +453,12 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
     out.iters = L.steps;
     out.theta = L.theta_S;
     out.have_x = true;
-    // no factorisation available: certified only if the Ritz value with its residual bound stays
-    // above -eta; plain Lanczos converges from above, so this is conservative
+    // No factorisation of S + eta I for this graph (loop closures / several robots), so positive semidefiniteness
+    // cannot be PROVEN: never certified here.  With x' S x < -eta/2 the vector is a valid direction of negative
+    // curvature (the reference's own early exit, src/CORA_utils.cpp:90-99); otherwise the verdict is inconclusive
+    // and the caller must neither certify nor escape along x.
     out.certified = false;
+    out.branch = accept(L.theta_S) ? CORA_B200_CERT_EIGENPAIR : CORA_B200_CERT_INCONCLUSIVE;
     if (verbose) std::printf("  certify: plain Lanczos steps=%d theta=%.6e\n", L.steps, L.theta_S);
   }
   return out;
@@ -466,6 +473,7 @@ inline void certify_host(H *h, int r, const double *Y, double eta, int nx, const
   import_matrix(h, Y, r, h->ws[V_X].p, r);
   h->resident_r = r;
   CertOut c = certify_resident(h, r, eta, max_iters > 0 ? max_iters : 500, 0);
+  h->last_cert_branch = c.branch;
   *is_certified = c.certified ? 1 : 0;
   *theta = c.theta;
   if (num_iters) *num_iters = c.iters;
@@ -614,18 +622,19 @@ inline void solve_staircase(H *h, int r0, const double *X0, int max_rank, const 
   cora_b200_tnt_result tr{};
   CertOut cert;
   double eta = 0.0;
-  res->lifted_f = 0.0; res->lifted_rank = 0; res->certified = 0;
+  res->lifted_f = 0.0; res->lifted_rank = 0; res->certified = 0; res->refined_certified = 0;
   auto record = [&](double tnt_s, double cert_s) {
     if (res->stages && ns < res->stage_capacity) {
       cora_b200_stage &s = res->stages[ns];
       s.rank = rank; s.status = tr.status; s.num_outer = tr.num_outer; s.certified = cert.certified;
       s.cg_iterations = tr.total_inner; s.f = tr.f; s.gradfx_norm = tr.gradfx_norm; s.theta = cert.theta;
       s.eta = eta; s.tnt_seconds = tnt_s; s.cert_seconds = cert_s;
+      s.cert_branch = cert.branch; s.reserved = 0;
     }
     ++ns;
   };
   while (rank <= max_rank) {  // src/CORA.cpp:134
-    if (rank > kMaxGeomRank) throw Error(CORA_B200_EINVAL, "relaxation rank above 24 is not supported");
+    if (rank > kMaxGeomRank) throw Error(CORA_B200_EINVAL, "relaxation rank above 24 is not supported");  // (r0 itself)
     auto ta = clk::now();
     std::memset(&tr, 0, sizeof(tr));
     tnt_resident(h, rank, p, &tr);
@@ -634,6 +643,7 @@ inline void solve_staircase(H *h, int r0, const double *X0, int max_rank, const 
     eta = std::min(std::max(tr.f * 5e-6, 1e-7), 1e-1);  // :154
     auto tb = clk::now();
     cert = certify_resident(h, rank, eta, 500, verbose);
+    h->last_cert_branch = cert.branch;
     const double cert_s = since(tb);
     if (verbose)
       std::printf("rank %d: f=%.9e |g|=%.3e status=%d outer=%d cg=%lld certified=%d theta=%.3e eta=%.3e (tnt %.3fs, cert %.3fs)\n",
@@ -645,11 +655,13 @@ inline void solve_staircase(H *h, int r0, const double *X0, int max_rank, const 
     res->lifted_rank = rank;
     res->certified = cert.certified ? 1 : 0;
     if (cert.certified) break;
+    // no verdict and no descent direction (graphs without a factorisation of S + eta I): lifting the rank along an
+    // unverified vector could end in a spurious sv-ratio "certificate" at the next rank -- stop and round instead
+    if (cert.branch == CORA_B200_CERT_INCONCLUSIVE) break;
+    if (rank + 1 > max_rank || rank + 1 > kMaxGeomRank) break;  // staircase exhausted: round the current iterate
     ++rank;  // problem.incrementRank()
-    if (rank > kMaxGeomRank) throw Error(CORA_B200_EINVAL, "relaxation rank above 24 is not supported");
     saddle_escape_resident(h, rank, cert.theta, 1e-4, 1e-4, verbose);
   }
-  if (rank > max_rank) rank = max_rank + 0;  // loop left without a certificate
   const int cur = h->resident_r;
   if (cur > d) {  // :200-233
     project_solution_resident(h, cur);
@@ -667,6 +679,9 @@ inline void solve_staircase(H *h, int r0, const double *X0, int max_rank, const 
       std::printf("refine rank %d: f=%.9e |g|=%.3e status=%d outer=%d cg=%lld certified=%d theta=%.3e\n", d, tr.f,
                   tr.gradfx_norm, tr.status, tr.num_outer, (long long)tr.total_inner, (int)cert.certified, cert.theta);
     record(tnt_s, cert_s);
+    res->refined_certified = cert.certified ? 1 : 0;
+  } else {
+    res->refined_certified = res->certified;
   }
   res->f = tr.f;
   res->final_rank = h->resident_r;

@@ -92,6 +92,8 @@ struct cora_b200_handle {
   double lambda_reg = -1.0;
   bool lambda_user = false;
   cora_b200::ChainChol *chol = nullptr;  // RegularizedCholesky factor of (Q + lambda I)[:-1,:-1]
+  int precond_requested = CORA_B200_PRECON_JACOBI;  // what the caller asked for (precond: what is applied)
+  int last_cert_branch = CORA_B200_CERT_NONE;
   // resident iterate rank
   int resident_r = 0;
   int64_t launches = 0;
@@ -106,6 +108,9 @@ struct cora_b200_handle {
   cora_b200::DevBuf<unsigned long long> d_bar;
   cora_b200::DevBuf<int> d_cta_t0;
   cora_b200::DevBuf<unsigned char> d_tntdev;
+  cora_b200::DevBuf<unsigned long long> d_prof_all;   // [grid][PH_COUNT] per-CTA phase times of the last launch
+  std::vector<unsigned long long> h_prof_all;
+  int prof_all_grid = 0;
   void *h_tntdev = nullptr;  // pinned TntDev
   std::vector<double> h_trace;
   int trace_cap = 0;

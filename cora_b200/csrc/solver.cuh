@@ -49,10 +49,20 @@ inline void precondition_project(H *h, const double *Y, double *R, double *Vout,
 inline void update_preconditioner(H *h) {
   destroy_chain_chol(h->chol);
   h->chol = nullptr;
+  h->precond_requested = h->precond;
   if (h->precond == CORA_B200_PRECON_REG_CHOLESKY) {
     if (!h->lambda_user) h->lambda_reg = estimate_spectral_norm(h) / (h->reg_max_cond - 1.0);  // :556-591
     bool pd = false;
-    h->chol = build_chain_chol(h, h->d_bval.p, h->d_sdiag.p, h->lambda_reg, /*pin_last=*/true, &pd);
+    try {
+      h->chol = build_chain_chol(h, h->d_bval.p, h->d_sdiag.p, h->lambda_reg, /*pin_last=*/true, &pd);
+    } catch (const Error &e) {
+      if (e.code != CORA_B200_ENOTIMPL) throw;
+      // Not an [odometry chain + landmark border] graph (loop closures, several robots): there is no device
+      // factorisation for it yet.  RegularizedCholesky is the reference's DEFAULT, so a drop-in caller must still
+      // get a working handle: apply Jacobi instead and report it (cora_b200_effective_preconditioner).
+      h->precond = CORA_B200_PRECON_JACOBI;
+      return;
+    }
     if (!pd) throw Error(CORA_B200_ERUNTIME, "RegularizedCholesky: Q + lambda I is not positive definite");
   }
 }
@@ -416,8 +426,9 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
     A.lamS[0] = h->d_lamS.p; A.lamS[1] = h->d_lamS.p + h->d_lamS.n / 2;
   }
   const bool phase_prof = getenv("CORA_B200_PHASE_PROFILE") != nullptr;
-  DevBuf<unsigned long long> d_prof_all;
-  if (phase_prof) { d_prof_all.alloc((size_t)G * PH_COUNT); A.prof_all = d_prof_all.p; }
+  if (h->d_prof_all.n < (size_t)G * PH_COUNT) h->d_prof_all.alloc((size_t)G * PH_COUNT);
+  A.prof_all = h->d_prof_all.p;
+  A.calibrate = phase_prof ? 1 : 0;
   CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
   CUDA_CHECK(cudaMemsetAsync(h->d_bar.p, 0, 2 * sizeof(unsigned long long), h->stream));
   DevLayout Lc = h->DL;
@@ -428,6 +439,10 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
   check_launch(h);
   CUDA_CHECK(cudaMemcpyAsync(h->h_tntdev, h->d_tntdev.p, sizeof(TntDev), cudaMemcpyDeviceToHost, h->stream));
   CUDA_CHECK(cudaMemcpyAsync(h->h_trace.data(), h->d_trace.p, (size_t)TR_ROWS * h->trace_cap * sizeof(double),
+                             cudaMemcpyDeviceToHost, h->stream));
+  h->h_prof_all.resize((size_t)G * PH_COUNT);
+  h->prof_all_grid = G;
+  CUDA_CHECK(cudaMemcpyAsync(h->h_prof_all.data(), h->d_prof_all.p, h->h_prof_all.size() * sizeof(unsigned long long),
                              cudaMemcpyDeviceToHost, h->stream));
   CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   CUDA_CHECK(cudaEventSynchronize(h->ev1));
@@ -472,8 +487,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
     std::printf("[persistent] %s grid %d, nbuf %d, smem %zu, barriers %lld, outer %d, CG %lld, device %.3f ms\n", h->persistent_stream ? "stream" : "tile", G, h->persistent_nbuf, smem, o.barriers, o.num_outer, o.total_inner, ms);
     for (int i = 0; i < PH_COUNT; ++i)
       if (o.prof_cnt[i]) std::printf("  %-8s n=%6u total %9.1f us  avg %8.2f us\n", names[i], o.prof_cnt[i], o.prof_ns[i] * 1e-3, o.prof_ns[i] * 1e-3 / o.prof_cnt[i]);
-    std::vector<unsigned long long> pa((size_t)G * PH_COUNT);
-    CUDA_CHECK(cudaMemcpy(pa.data(), d_prof_all.p, pa.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const std::vector<unsigned long long> &pa = h->h_prof_all;
     for (int i = 0; i < PH_COUNT; ++i) {
       if (!o.prof_cnt[i]) continue;
       std::vector<double> col(G);

@@ -74,6 +74,12 @@ int cora_b200_destroy(cora_b200_t *h);
 int cora_b200_size(const cora_b200_t *h, int64_t *N);
 /* Problem::setPreconditioner (include/CORA/CORA_problem.h:335-337) + updatePreconditioner */
 int cora_b200_set_preconditioner(cora_b200_t *h, int preconditioner, double reg_chol_max_cond);
+/* The preconditioner actually applied.  Preconditioner::RegularizedCholesky (the reference's default,
+ * src/pyfg_text_parser.cpp:116-120) is factored on the device for graphs made of one odometry chain plus
+ * landmark / range factors (all BASELINE configurations); for any other graph (loop closures, several
+ * robots) the handle is still created and applies Jacobi instead -- this call reports it. */
+int cora_b200_effective_preconditioner(const cora_b200_t *h, int *preconditioner);
+
 /* lambda of RegularizedCholesky actually used (src/CORA_problem.cpp:591) */
 int cora_b200_get_reg_lambda(const cora_b200_t *h, double *lambda);
 /* override lambda (parity runs pass the oracle's converged ||Q||_2/(c-1)) */
@@ -195,6 +201,10 @@ int cora_b200_get_work_vector(cora_b200_t *h, int which, int r, double *out);
  * *grid / *barriers: CTAs of the cooperative launch and grid barriers executed. */
 int cora_b200_phase_profile(cora_b200_t *h, int capacity, double *total_us, int64_t *count,
                             int *n_kinds, int *grid, int64_t *barriers);
+/* Per phase kind: the average time of one execution of the phase on the slowest CTA and on the median CTA
+ * (every CTA's clock; the persistent kernel runs as fast as its slowest CTA allows). */
+int cora_b200_phase_profile_ctas(cora_b200_t *h, int capacity, double *max_us, double *median_us);
+
 /* timed data-matrix products on the resident iterate: reps launches of Q*X, returns
  * the CUDA-event milliseconds for all of them (roofline leg of bench.py) */
 int cora_b200_spmm_resident(cora_b200_t *h, int reps, float *ms_total);
@@ -207,6 +217,9 @@ int cora_b200_certify(cora_b200_t *h, int r, const double *Y, double eta, int nx
                       int *is_certified, double *theta, double *x, double *all_eigvecs,
                       int all_eigvecs_cols_capacity, int *all_eigvecs_cols,
                       int64_t *num_iters);
+/* Which test decided the last cora_b200_certify / staircase stage on this handle (CORA_B200_CERT_*). */
+int cora_b200_last_cert_branch(const cora_b200_t *h, int *branch);
+
 
 /* saddleEscape (src/CORA.cpp:245-350): Y is N x (r_new-1), v has N entries, Y_out
  * is N x r_new. */
@@ -218,6 +231,16 @@ int cora_b200_saddle_escape(cora_b200_t *h, int r_new, const double *Y, double t
 int cora_b200_project_solution(cora_b200_t *h, int r, const double *Y, double *Y_out);
 
 /* One stage record of the staircase (one TNT + one certification). */
+/* How certify_solution (src/CORA_problem.cpp:1030-1103) reached its verdict. */
+enum {
+  CORA_B200_CERT_NONE = 0,
+  CORA_B200_CERT_SV_RATIO = 1,     /* sigma_max/sigma_min(Y) > 1e6 short-circuit (:1039-1049): certified                 */
+  CORA_B200_CERT_PSD = 2,          /* Cholesky of S + eta I succeeded (src/CORA_utils.cpp:33-57): certified              */
+  CORA_B200_CERT_EIGENPAIR = 3,    /* S + eta I not PD; eigen-search found x' S x < -eta/2: not certified, direction in x */
+  CORA_B200_CERT_INCONCLUSIVE = 4  /* no factorisation of S + eta I available for this graph and the eigen-search found
+                                      no negative curvature: NOT certified, and no descent direction either              */
+};
+
 typedef struct cora_b200_stage {
   int32_t rank;
   int32_t status;
@@ -230,6 +253,8 @@ typedef struct cora_b200_stage {
   double eta;
   double tnt_seconds;
   double cert_seconds;
+  int32_t cert_branch;  /* CORA_B200_CERT_*: which test decided `certified` */
+  int32_t reserved;
 } cora_b200_stage;
 
 typedef struct cora_b200_solve_result {
@@ -242,7 +267,7 @@ typedef struct cora_b200_solve_result {
   int64_t total_cg_iterations;
   double seconds;       /* solve-to-certificate wall-clock                     */
   int32_t stage_capacity;
-  int32_t reserved;
+  int32_t refined_certified; /* certificate of the refined rank-d solution (the reference's last certify_solution call) */
   cora_b200_stage *stages; /* caller-allocated, stage_capacity entries or NULL */
 } cora_b200_solve_result;
 
@@ -259,6 +284,11 @@ int cora_b200_solve(cora_b200_t *h, int r0, const double *X0, int max_rank,
 int cora_b200_gather_best(void *nccl_comm, cora_b200_t *h, int world_size, int my_rank,
                           int r_max, double f, int certified, double *X_inout,
                           int *winner_rank, double *winner_f);
+/* Same selection; the iterates stay on the devices: every rank's RESIDENT iterate (rank r, as left by
+ * cora_b200_solve / cora_b200_tnt_resident) is replaced by the winner's with one ncclBroadcast, no host staging. */
+int cora_b200_gather_best_resident(void *nccl_comm, cora_b200_t *h, int world_size, int my_rank, double f,
+                                   int certified, int *winner_rank, double *winner_f);
+
 /* the selection rule of gather_best as a pure host function (CPU-testable): arg-min of f over the
  * certified ranks, over all ranks when none is certified; ties go to the lowest rank */
 int cora_b200_select_best(int world_size, const double *f, const int *certified, int *winner);

@@ -8,5 +8,5 @@ python - <<PY
 import json
 d=json.loads(open("gpurun_out/${NAME}_bench.log").read().strip().splitlines()[-1])
 print("value %.1f  us/CG %.1f  e2e %.1f  frac %.3f" % (d["value"],d["us_per_cg_iteration"],d["e2e"]["value"],d["roofline"]["frac"]))
-for k,v in d["roofline"]["phases_in_kernel_globaltimer_cta0"].items(): print("  %-8s %8.2f us x %d" % (k, v["avg_us"], v["count"]))
+for k,v in d["roofline"]["phases_in_kernel_globaltimer"].items(): print("  %-8s %8.2f us x %d" % (k, v["avg_us"], v["count"]))
 PY

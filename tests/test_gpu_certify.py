@@ -134,6 +134,53 @@ def test_staircase_datasets_known_answers(lib, name, r0, f_lift, f_ref):
     with make_handle(p, preconditioner=capi.PRECON_REG_CHOLESKY) as h:
         out = h.solve(x0, max_rank=10, params=_params())
     assert out["certified"], out["stages"]
+    # the certificate of the lifted stage is the PSD test of S + eta I (Cholesky), not the sv-ratio short-circuit
+    lifted = [s for s in out["stages"] if s["certified"]][0]
+    assert lifted["cert_branch"] == "psd", out["stages"]
+    assert all(s["cert_branch"] == "eigenpair" for s in out["stages"][: out["stages"].index(lifted)]), out["stages"]
     assert abs(out["lifted_f"] - f_lift) <= 2e-3 * f_lift, out["stages"]
     assert abs(out["f"] - f_ref) <= 1e-4 * f_ref, out["stages"]
     assert out["final_rank"] == p.d
+
+
+def test_staircase_without_factorisation_never_certifies_spuriously(lib):
+    """Loop-closure graph: there is no device factorisation of S + eta I, so positive semidefiniteness is never
+    proven.  The staircase may lift the rank only along a verified direction of negative curvature
+    (x' S x < -eta/2), must stop at an inconclusive verdict, and must not report a PSD certificate."""
+    from cora_b200 import capi
+    p = make_synthetic(n=80, l=3, m=50, d=3, seed=3, loop_closures=[(0, 40), (10, 70)])
+    p.update_problem_data()
+    x0 = np.random.default_rng(1).uniform(-1, 1, size=(p.N, 4))
+    with make_handle(p, preconditioner=capi.PRECON_REG_CHOLESKY) as h:
+        assert h.effective_preconditioner == capi.PRECON_JACOBI
+        out = h.solve(x0, max_rank=7, params=_params())
+    st = out["stages"]
+    assert all(s["cert_branch"] != "psd" for s in st), st
+    for i, s in enumerate(st[:-1]):
+        if s["cert_branch"] == "inconclusive":  # only the rounding / refinement stage may follow
+            assert i == len(st) - 2 and st[-1]["rank"] == p.d, st
+        if s["cert_branch"] == "eigenpair":
+            assert s["theta"] < -s["eta"] / 2, st
+    if out["certified"]:
+        assert [s for s in st if s["certified"]][0]["cert_branch"] == "sv_ratio", st
+    assert out["x"].shape == (p.N, p.d) and np.isfinite(out["f"])
+
+
+def test_native_nccl_gather_best_world_size_one(lib):
+    """cora_b200_gather_best / _gather_best_resident over a real NCCL communicator (one rank: the collectives run,
+    the winner is rank 0 and its iterate must come back bit-for-bit; SCALE covers N > 1)."""
+    from cora_b200 import capi
+    p = make_synthetic(n=200, l=3, m=80, d=3, seed=4)
+    p.update_problem_data()
+    X = np.asfortranarray(np.random.default_rng(3).standard_normal((p.N, 3)))
+    comm = capi.NcclComm(0, 1, 0, capi.nccl_unique_id())
+    try:
+        with make_handle(p) as h:
+            win, wf, Xw = h.gather_best(comm, 1, 0, 12.5, True, X)
+            assert win == 0 and wf == 12.5 and np.array_equal(Xw, X)
+            h.set_iterate(X)
+            win, wf = h.gather_best_resident(comm, 1, 0, 7.25, False)
+            assert win == 0 and wf == 7.25
+            assert np.array_equal(h.get_iterate(3), X)
+    finally:
+        comm.close()

@@ -176,12 +176,21 @@ def test_regularized_cholesky_preconditioner(lib):
             assert np.all(Z[-1] == 0.0)  # CORA_preconditioners.cpp:77-80
 
 
-def test_regularized_cholesky_rejects_loop_closures(lib):
+def test_regularized_cholesky_falls_back_to_jacobi_on_loop_closures(lib):
+    """RegularizedCholesky is the reference's default (src/pyfg_text_parser.cpp:116-120): on a graph without a device
+    factorisation (a loop closure) the handle must still be created; it applies Jacobi and says so."""
     from cora_b200 import capi
     p = make_synthetic(n=60, l=3, m=40, d=3, seed=5, loop_closures=[(0, 30)])
     p.update_problem_data()
-    with pytest.raises(capi.NotImplementedInReference):
-        make_handle(p, preconditioner=capi.PRECON_REG_CHOLESKY)
+    V = np.asfortranarray(np.random.default_rng(0).standard_normal((p.N, 4)))
+    with make_handle(p, preconditioner=capi.PRECON_REG_CHOLESKY) as h:
+        assert h.effective_preconditioner == capi.PRECON_JACOBI
+        Z = h.precondition(V)
+    assert np.abs(Z - V / p.Q.diagonal()[:, None]).max() <= 1e-12 * np.abs(Z).max()
+    pc = make_synthetic(n=60, l=3, m=40, d=3, seed=5)
+    pc.update_problem_data()
+    with make_handle(pc, preconditioner=capi.PRECON_REG_CHOLESKY) as h:
+        assert h.effective_preconditioner == capi.PRECON_REG_CHOLESKY
 
 
 @pytest.mark.gpu
