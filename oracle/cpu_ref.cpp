@@ -16,8 +16,14 @@
 //     decrease costs one more Hessian-vector product (:511-512), <r,v> is recomputed three times
 //     per CG iteration (IterativeSolvers.h:290,341,408) and the metric forms the r x r product
 //     V1^T V2 before taking its trace (src/CORA.cpp:119-122).
-// Preconditioner: Jacobi (src/CORA_problem.cpp:616-618,888-889) or none; the RegularizedCholesky
-// path needs CHOLMOD and is restated only in the NumPy/SciPy oracle.
+// Preconditioner: Jacobi (src/CORA_problem.cpp:616-618,888-889), none, or RegularizedCholesky
+// (src/CORA_problem.cpp:544-614, src/CORA_preconditioners.cpp:46-83).  The reference hands
+// (Q + lambda I)[0:N-1, 0:N-1] to CHOLMOD (absent here); for the graphs of the BASELINE configurations -- one
+// odometry chain plus landmark / range factors -- a fill-free elimination order exists and the factor is
+// restated directly: range rows first (each is a diagonal entry with two couplings), the poses as a
+// block-tridiagonal Cholesky in trajectory order, the landmarks last through their dense Schur complement.
+// Same matrix, same solution, no fill beyond the landmark border (what AMD + CHOLMOD produce on a chain);
+// sequential like CHOLMOD's solve, one dense column per worker thread at most.
 // Threads: the reference is single threaded.  cpu_ref_set_threads(T > 1) runs the row
 // loops of the products and the per-pose loops on a small std::thread pool (this image has no
 // libgomp) -- a stronger comparator than the reference; `cpu_ref_threads()` reports what is in use.
@@ -37,6 +43,19 @@
 
 namespace {
 
+// Cholesky factor of an [odometry chain + landmark border + range rows] matrix, the last row pinned to zero
+// (src/CORA_preconditioners.cpp:77-80) when `pinned`.
+struct ChainFactor {
+  bool built = false, pos_def = false, pinned = false;
+  int B = 0, n = 0, l = 0, m = 0;
+  std::vector<double> rdinv;          // m: 1 / diagonal of the range rows
+  std::vector<int32_t> rx;            // 2m: translation index of the two couplings (pose i -> i, landmark j -> n + j)
+  std::vector<double> re;             // 2m: coupling values
+  std::vector<double> Ld, G;          // n x B x B: Cholesky factors of the pivots, sub-diagonal blocks G_i = U_i^T L_i^-T
+  std::vector<double> Y;              // (n B) x l column-major: L^-1 (border)
+  std::vector<double> LC;             // l x l lower Cholesky factor of the landmark Schur complement
+};
+
 struct Ref {
   int d = 0, n = 0, m = 0, nt = 0;
   int64_t N = 0;
@@ -44,6 +63,8 @@ struct Ref {
   std::vector<double> val, jac;  // jac = 1 / diag(Q)
   int precond = CORA_B200_PRECON_JACOBI;
   int64_t spmm_count = 0;
+  ChainFactor chol;              // RegularizedCholesky: factor of (Q + lambda I) with the last row pinned
+  double lambda_reg = 0.0;
 };
 
 typedef std::vector<double> Mat;  // column-major N x r
@@ -220,13 +241,292 @@ void hessvec(Ref &P, const Mat &Y, const Mat &G, const Mat &Yd, int r, Mat &out)
   tangent_projection(P, Y, W, r, out);
 }
 
-// Problem::precondition (src/CORA_problem.cpp:869-903), Jacobi / none
+// ------------------------------------------------- chain Cholesky (RegularizedCholesky) ----
+// Dense helpers on small row-major B x B blocks.
+static bool chol_lower(double *A, int B) {  // in place, lower triangle; false: not positive definite
+  for (int j = 0; j < B; ++j) {
+    double s = A[j * B + j];
+    for (int k = 0; k < j; ++k) s -= A[j * B + k] * A[j * B + k];
+    if (!(s > 0.0)) return false;
+    const double dj = std::sqrt(s);
+    A[j * B + j] = dj;
+    for (int i = j + 1; i < B; ++i) {
+      double t = A[i * B + j];
+      for (int k = 0; k < j; ++k) t -= A[i * B + k] * A[j * B + k];
+      A[i * B + j] = t / dj;
+    }
+    for (int k = j + 1; k < B; ++k) A[j * B + k] = 0.0;
+  }
+  return true;
+}
+static void fwd_lower(const double *L, int B, double *x) {  // x <- L^-1 x
+  for (int i = 0; i < B; ++i) {
+    double s = x[i];
+    for (int k = 0; k < i; ++k) s -= L[i * B + k] * x[k];
+    x[i] = s / L[i * B + i];
+  }
+}
+static void bwd_lower(const double *L, int B, double *x) {  // x <- L^-T x
+  for (int i = B - 1; i >= 0; --i) {
+    double s = x[i];
+    for (int k = i + 1; k < B; ++k) s -= L[k * B + i] * x[k];
+    x[i] = s / L[i * B + i];
+  }
+}
+
+// Factor M = A + shift I restricted to rows/columns 0..N-1 (pin_last: the last row and column replaced by the
+// identity), A given as CSR in the reference row order [d n rotations | m ranges | n translations | l landmarks].
+// Returns false (with a message) when the graph is not a chain + landmark border.
+static bool chain_factor(ChainFactor &F, int d, int n, int m, int nt, const int32_t *rowptr, const int32_t *col,
+                         const double *val, double shift, bool pin_last, std::string &err) {
+  const int B = d + 1, l = nt - n, BB = B * B;
+  const int64_t dn = (int64_t)d * n, t0 = dn + m, N = dn + m + nt;
+  F = ChainFactor();
+  F.B = B; F.n = n; F.l = l; F.m = m; F.pinned = pin_last;
+  // unknowns of pose i: rotation rows d i .. d i + d - 1, translation t0 + i  -> local index 0..d-1, d
+  auto pose_of = [&](int64_t row, int &a) -> int {
+    if (row < dn) { a = (int)(row % d); return (int)(row / d); }
+    if (row >= t0 && row < t0 + n) { a = d; return (int)(row - t0); }
+    return -1;
+  };
+  std::vector<double> A((size_t)std::max(n, 1) * BB, 0.0), U((size_t)std::max(n, 1) * BB, 0.0);
+  std::vector<double> C((size_t)std::max(l, 1) * std::max(l, 1), 0.0), Bd((size_t)std::max(n, 1) * B * std::max(l, 1), 0.0);
+  F.rdinv.assign(std::max(m, 1), 0.0); F.rx.assign((size_t)std::max(m, 1) * 2, -1); F.re.assign((size_t)std::max(m, 1) * 2, 0.0);
+  bool pd = true;
+  for (int64_t row = 0; row < N; ++row) {
+    int a = 0;
+    const int i = pose_of(row, a);
+    for (int32_t k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+      const int64_t c = col[k];
+      const double v = val[k];
+      int b = 0;
+      const int j = pose_of(c, b);
+      if (i >= 0) {                                   // pose row
+        if (j >= 0) {
+          if (j == i) A[(size_t)i * BB + a * B + b] += v;
+          else if (j == i + 1) U[(size_t)i * BB + a * B + b] += v;
+          else if (j == i - 1) { /* transpose of U[i-1] */ }
+          else if (v != 0.0) { err = "not an odometry chain: a pose is coupled to a non-adjacent pose"; return false; }
+        } else if (c >= t0 + n) {
+          Bd[((size_t)(c - t0 - n)) * n * B + (size_t)i * B + a] += v;   // column-major by landmark
+        } else { /* range column: taken from the range row */ }
+      } else if (row >= t0 + n) {                     // landmark row
+        if (c >= t0 + n) C[(size_t)(row - t0 - n) * l + (c - t0 - n)] += v;
+      } else {                                        // range row k
+        const int kk = (int)(row - dn);
+        if (c == row) { F.rdinv[kk] += v; continue; }
+        int x = -1;
+        if (c >= t0 && c < t0 + n) x = (int)(c - t0);
+        else if (c >= t0 + n) x = n + (int)(c - t0 - n);
+        if (x < 0) { err = "a range row is coupled to a non-translation variable"; return false; }
+        int slot = F.rx[(size_t)kk * 2] < 0 ? 0 : (F.rx[(size_t)kk * 2 + 1] < 0 ? 1 : 2);
+        if (slot == 2) { err = "a range row has more than two couplings"; return false; }
+        F.rx[(size_t)kk * 2 + slot] = x;
+        F.re[(size_t)kk * 2 + slot] = v;
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < B; ++a) A[(size_t)i * BB + a * B + a] += shift;
+  for (int j = 0; j < l; ++j) C[(size_t)j * l + j] += shift;
+  // eliminate the range rows: Schur complement onto their translations
+  for (int k = 0; k < m; ++k) {
+    const double delta = F.rdinv[k] + shift;
+    if (!(delta > 0.0)) { pd = false; F.rdinv[k] = 1.0; continue; }
+    F.rdinv[k] = 1.0 / delta;
+    for (int p = 0; p < 2; ++p)
+      for (int q = 0; q < 2; ++q) {
+        const int x = F.rx[(size_t)k * 2 + p], y = F.rx[(size_t)k * 2 + q];
+        if (x < 0 || y < 0) continue;
+        const double v = -F.re[(size_t)k * 2 + p] * F.re[(size_t)k * 2 + q] * F.rdinv[k];
+        if (x < n && y < n) {
+          if (x == y) A[(size_t)x * BB + d * B + d] += v;
+          else if (y == x + 1) U[(size_t)x * BB + d * B + d] += v;
+          else if (y == x - 1) { }
+          else { err = "a range factor joins two non-adjacent poses"; return false; }
+        } else if (x < n) {
+          Bd[(size_t)(y - n) * n * B + (size_t)x * B + d] += v;
+        } else if (y >= n) {
+          C[(size_t)(x - n) * l + (y - n)] += v;
+        }
+      }
+  }
+  // pin the last unknown
+  if (pin_last) {
+    if (l > 0) {
+      const int j = l - 1;
+      for (int q = 0; q < l; ++q) { C[(size_t)j * l + q] = 0.0; C[(size_t)q * l + j] = 0.0; }
+      C[(size_t)j * l + j] = 1.0;
+      for (size_t q = 0; q < (size_t)n * B; ++q) Bd[(size_t)j * n * B + q] = 0.0;
+    } else if (n > 0) {
+      const int i = n - 1;
+      for (int a = 0; a < B; ++a) { A[(size_t)i * BB + d * B + a] = 0.0; A[(size_t)i * BB + a * B + d] = 0.0; }
+      A[(size_t)i * BB + d * B + d] = 1.0;
+      if (i > 0) for (int a = 0; a < B; ++a) U[(size_t)(i - 1) * BB + a * B + d] = 0.0;
+    }
+  }
+  // block-tridiagonal Cholesky: S_i = A_i - G_{i-1} G_{i-1}^T, L_i = chol(S_i), G_i = U_i^T L_i^-T
+  F.Ld.assign((size_t)std::max(n, 1) * BB, 0.0); F.G.assign((size_t)std::max(n, 1) * BB, 0.0);
+  for (int i = 0; i < n; ++i) {
+    double *S = &F.Ld[(size_t)i * BB];
+    for (int e = 0; e < BB; ++e) S[e] = A[(size_t)i * BB + e];
+    if (i > 0) {
+      const double *Gp = &F.G[(size_t)(i - 1) * BB];
+      for (int a = 0; a < B; ++a)
+        for (int b = 0; b < B; ++b) {
+          double t = 0.0;
+          for (int k = 0; k < B; ++k) t += Gp[a * B + k] * Gp[b * B + k];
+          S[a * B + b] -= t;
+        }
+    }
+    if (!chol_lower(S, B)) {
+      pd = false;
+      for (int e = 0; e < BB; ++e) S[e] = 0.0;
+      for (int a = 0; a < B; ++a) S[a * B + a] = 1.0;
+    }
+    if (i + 1 < n) {  // G_i row a = L_i^-1 (column a of U_i):  G_i = U_i^T L_i^-T  <=>  G_i^T = L_i^-1 U_i
+      double *Gi = &F.G[(size_t)i * BB];
+      for (int a = 0; a < B; ++a) {
+        double x[4];
+        for (int k = 0; k < B; ++k) x[k] = U[(size_t)i * BB + k * B + a];
+        fwd_lower(S, B, x);
+        for (int k = 0; k < B; ++k) Gi[a * B + k] = x[k];
+      }
+    }
+  }
+  // border: Y = L^-1 Bd, landmark Schur complement C - Y^T Y
+  if (l > 0) {
+    F.Y = Bd;
+    for (int j = 0; j < l; ++j) {
+      double *y = &F.Y[(size_t)j * n * B];
+      for (int i = 0; i < n; ++i) {
+        double *yi = y + (size_t)i * B;
+        if (i > 0) {
+          const double *Gp = &F.G[(size_t)(i - 1) * BB], *yp = y + (size_t)(i - 1) * B;
+          for (int a = 0; a < B; ++a) {
+            double t = 0.0;
+            for (int k = 0; k < B; ++k) t += Gp[a * B + k] * yp[k];
+            yi[a] -= t;
+          }
+        }
+        fwd_lower(&F.Ld[(size_t)i * BB], B, yi);
+      }
+    }
+    F.LC = C;
+    for (int a = 0; a < l; ++a)
+      for (int b = 0; b <= a; ++b) {
+        const double *ya = &F.Y[(size_t)a * n * B], *yb = &F.Y[(size_t)b * n * B];
+        double t = 0.0;
+        for (size_t q = 0; q < (size_t)n * B; ++q) t += ya[q] * yb[q];
+        F.LC[(size_t)a * l + b] -= t;
+        F.LC[(size_t)b * l + a] = F.LC[(size_t)a * l + b];
+      }
+    if (!chol_lower(F.LC.data(), l)) {
+      pd = false;
+      std::fill(F.LC.begin(), F.LC.end(), 0.0);
+      for (int a = 0; a < l; ++a) F.LC[(size_t)a * l + a] = 1.0;
+    }
+  }
+  F.pos_def = pd;
+  F.built = true;
+  return true;
+}
+
+// out = M^-1 V with the last row of the result zero (blockCholeskySolve, src/CORA_preconditioners.cpp:46-83)
+static void chain_solve(const Ref &P, const Mat &V, int r, Mat &out) {
+  const ChainFactor &F = P.chol;
+  const int B = F.B, n = F.n, l = F.l, m = F.m, d = P.d, BB = B * B;
+  const int64_t N = P.N, dn = (int64_t)d * n, t0 = dn + m;
+  out.assign(V.size(), 0.0);
+  auto trow = [&](int x) -> int64_t { return x < n ? t0 + x : t0 + n + (x - n); };
+  pfor(r, [&](int64_t c_) {
+    const int c = (int)c_;
+    const double *v = &V[(size_t)c * N];
+    double *z = &out[(size_t)c * N];
+    std::vector<double> u((size_t)std::max(n, 1) * B), w((size_t)std::max(l, 1));
+    // right-hand side on [poses | landmarks] after eliminating the ranges
+    for (int i = 0; i < n; ++i) {
+      for (int a = 0; a < d; ++a) u[(size_t)i * B + a] = v[(size_t)d * i + a];
+      u[(size_t)i * B + d] = v[t0 + i];
+    }
+    for (int j = 0; j < l; ++j) w[j] = v[t0 + n + j];
+    for (int k = 0; k < m; ++k)
+      for (int p = 0; p < 2; ++p) {
+        const int x = F.rx[(size_t)k * 2 + p];
+        if (x < 0) continue;
+        const double t = F.re[(size_t)k * 2 + p] * F.rdinv[k] * v[dn + k];
+        if (x < n) u[(size_t)x * B + d] -= t; else w[x - n] -= t;
+      }
+    if (F.pinned) { if (l > 0) w[l - 1] = 0.0; else if (n > 0) u[(size_t)(n - 1) * B + d] = 0.0; }
+    // forward: u <- L^-1 u
+    for (int i = 0; i < n; ++i) {
+      double *ui = &u[(size_t)i * B];
+      if (i > 0) {
+        const double *Gp = &F.G[(size_t)(i - 1) * BB], *up = &u[(size_t)(i - 1) * B];
+        for (int a = 0; a < B; ++a) {
+          double t = 0.0;
+          for (int k = 0; k < B; ++k) t += Gp[a * B + k] * up[k];
+          ui[a] -= t;
+        }
+      }
+      fwd_lower(&F.Ld[(size_t)i * BB], B, ui);
+    }
+    // landmarks: w <- LC^-T LC^-1 (w - Y^T u)
+    if (l > 0) {
+      for (int j = 0; j < l; ++j) {
+        const double *y = &F.Y[(size_t)j * n * B];
+        double t = 0.0;
+        for (size_t q = 0; q < (size_t)n * B; ++q) t += y[q] * u[q];
+        w[j] -= t;
+      }
+      fwd_lower(F.LC.data(), l, w.data());
+      bwd_lower(F.LC.data(), l, w.data());
+      for (int j = 0; j < l; ++j) {
+        const double *y = &F.Y[(size_t)j * n * B];
+        const double wj = w[j];
+        for (size_t q = 0; q < (size_t)n * B; ++q) u[q] -= y[q] * wj;
+      }
+    }
+    // backward: u <- L^-T u
+    for (int i = n - 1; i >= 0; --i) {
+      double *ui = &u[(size_t)i * B];
+      if (i + 1 < n) {
+        const double *Gi = &F.G[(size_t)i * BB], *un = &u[(size_t)(i + 1) * B];
+        for (int a = 0; a < B; ++a) {
+          double t = 0.0;
+          for (int k = 0; k < B; ++k) t += Gi[k * B + a] * un[k];
+          ui[a] -= t;
+        }
+      }
+      bwd_lower(&F.Ld[(size_t)i * BB], B, ui);
+    }
+    for (int i = 0; i < n; ++i) {
+      for (int a = 0; a < d; ++a) z[(size_t)d * i + a] = u[(size_t)i * B + a];
+      z[t0 + i] = u[(size_t)i * B + d];
+    }
+    for (int j = 0; j < l; ++j) z[t0 + n + j] = w[j];
+    // back-substitute the ranges
+    for (int k = 0; k < m; ++k) {
+      double s = v[dn + k];
+      for (int p = 0; p < 2; ++p) {
+        const int x = F.rx[(size_t)k * 2 + p];
+        if (x >= 0) s -= F.re[(size_t)k * 2 + p] * z[trow(x)];
+      }
+      z[dn + k] = s * F.rdinv[k];
+    }
+    if (F.pinned) z[N - 1] = 0.0;
+  });
+}
+
+// Problem::precondition (src/CORA_problem.cpp:869-903)
 void precondition(const Ref &P, const Mat &V, int r, Mat &out) {
   const int64_t N = P.N;
   out.resize(V.size());
   if (P.precond == CORA_B200_PRECON_JACOBI) {
     for (int c = 0; c < r; ++c)
       pfor(N, [&](int64_t i_) { const int64_t i = (int64_t)i_; out[(size_t)c * N + i] = P.jac[i] * V[(size_t)c * N + i]; });
+  } else if (P.precond == CORA_B200_PRECON_REG_CHOLESKY) {
+    chain_solve(P, V, r, out);
   } else {
     out = V;
   }
@@ -546,8 +846,12 @@ int cpu_ref_tnt(void *h, int r, const double *X0, const cora_b200_tnt_params *p,
                 cora_b200_tnt_result *res) {
   if (!h || !X0 || !p || !X_out || !res || r < 1 || r > 64) { g_err = "bad argument"; return 1; }
   Ref &P = *(Ref *)h;
-  if (P.precond != CORA_B200_PRECON_JACOBI && P.precond != CORA_B200_PRECON_NONE) {
-    g_err = "cpu_ref restates the Jacobi preconditioner only";
+  if (P.precond == CORA_B200_PRECON_REG_CHOLESKY && !P.chol.built) {
+    g_err = "RegularizedCholesky: call cpu_ref_set_reg_cholesky(lambda) first";
+    return 4;
+  }
+  if (P.precond != CORA_B200_PRECON_JACOBI && P.precond != CORA_B200_PRECON_NONE && P.precond != CORA_B200_PRECON_REG_CHOLESKY) {
+    g_err = "cpu_ref restates Jacobi, RegularizedCholesky and no preconditioner";
     return 4;
   }
   tnt(P, r, X0, *p, X_out, res);
@@ -555,5 +859,39 @@ int cpu_ref_tnt(void *h, int r, const double *X0, const cora_b200_tnt_params *p,
 }
 
 int64_t cpu_ref_spmm_count(void *h) { return ((Ref *)h)->spmm_count; }
+
+// RegularizedCholesky with regularisation lambda (the caller passes the reference's lambda = ||Q||_2 / (c - 1),
+// src/CORA_problem.cpp:556-591): factor (Q + lambda I) with the last row pinned and select the preconditioner.
+int cpu_ref_set_reg_cholesky(void *h, double lambda) {
+  Ref &P = *(Ref *)h;
+  std::string err;
+  if (!chain_factor(P.chol, P.d, P.n, P.m, P.nt, P.rowptr.data(), P.col.data(), P.val.data(), lambda, true, err)) {
+    g_err = err;
+    return 2;
+  }
+  if (!P.chol.pos_def) { g_err = "Q + lambda I is not positive definite"; return 3; }
+  P.lambda_reg = lambda;
+  P.precond = CORA_B200_PRECON_REG_CHOLESKY;
+  return 0;
+}
+
+int cpu_ref_precondition(void *h, int r, const double *V, double *out) {
+  Ref &P = *(Ref *)h;
+  Mat v(V, V + (size_t)P.N * r), o;
+  precondition(P, v, r, o);
+  std::memcpy(out, o.data(), o.size() * sizeof(double));
+  return 0;
+}
+
+// Positive-definiteness test of S + shift I for a symmetric matrix S on the same kind of graph, by Cholesky
+// (the PSD half of fast_verification, src/CORA_utils.cpp:33-57).  *pos_def = 1 / 0.
+int cpu_ref_chain_posdef(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr, const int32_t *col,
+                         const double *val, double shift, int *pos_def) {
+  ChainFactor F;
+  std::string err;
+  if (!chain_factor(F, d, n_poses, n_ranges, n_trans, rowptr, col, val, shift, false, err)) { g_err = err; return 2; }
+  *pos_def = F.pos_def ? 1 : 0;
+  return 0;
+}
 
 }  // extern "C"

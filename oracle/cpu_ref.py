@@ -38,6 +38,7 @@ def load():
         lib = C.CDLL(build())
         lib.cpu_ref_last_error.restype = C.c_char_p
         lib.cpu_ref_spmm_count.restype = C.c_int64
+        lib.cpu_ref_set_reg_cholesky.argtypes = [C.c_void_p, C.c_double]
         _lib = lib
     return _lib
 
@@ -52,7 +53,7 @@ def _f(a):
 class CpuRef:
     """One problem on the host: CSR data matrix in the reference row order + Jacobi preconditioner."""
 
-    def __init__(self, d, n_poses, n_ranges, n_trans, Q, preconditioner=1, threads=None):
+    def __init__(self, d, n_poses, n_ranges, n_trans, Q, preconditioner=1, threads=None, reg_lambda=None):
         import scipy.sparse as sp
         lib = load()
         Q = sp.csr_matrix(Q)
@@ -68,10 +69,14 @@ class CpuRef:
             lib.cpu_ref_set_threads(C.c_int(int(threads)))
         rc = lib.cpu_ref_create(C.byref(self._h), C.c_int(d), C.c_int(n_poses), C.c_int(n_ranges), C.c_int(n_trans),
                                 rp.ctypes.data_as(i32), ci.ctypes.data_as(i32), va.ctypes.data_as(_PD),
-                                C.c_int64(Q.nnz), C.c_int(preconditioner))
+                                C.c_int64(Q.nnz), C.c_int(1 if preconditioner == 3 else preconditioner))
         if rc:
             raise RuntimeError(lib.cpu_ref_last_error().decode())
         self._lib = lib
+        if preconditioner == 3:   # RegularizedCholesky: lambda = ||Q||_2 / (c - 1), src/CORA_problem.cpp:556-591
+            if reg_lambda is None:
+                raise ValueError("RegularizedCholesky needs reg_lambda")
+            self.set_reg_cholesky(reg_lambda)
 
     @property
     def threads(self):
@@ -112,6 +117,16 @@ class CpuRef:
         A = _f(A)
         return self._call("cpu_ref_project", A.shape[1], A)
 
+    def set_reg_cholesky(self, lam):
+        """Select RegularizedCholesky with regularisation `lam` (= ||Q||_2 / (c - 1) of the reference)."""
+        rc = self._lib.cpu_ref_set_reg_cholesky(self._h, C.c_double(float(lam)))
+        if rc:
+            raise RuntimeError(self._lib.cpu_ref_last_error().decode())
+
+    def precondition(self, V):
+        V = _f(V)
+        return self._call("cpu_ref_precondition", V.shape[1], V)
+
     def spmm_count(self):
         return int(self._lib.cpu_ref_spmm_count(self._h))
 
@@ -126,3 +141,22 @@ class CpuRef:
         if rc:
             raise RuntimeError(self._lib.cpu_ref_last_error().decode())
         return capi.Handle._unpack_result(res, keep, out)
+
+
+def chain_posdef(d, n_poses, n_ranges, n_trans, S, shift):
+    """Cholesky test of S + shift I (S: symmetric sparse, reference row order) on a chain + landmark graph."""
+    import scipy.sparse as sp
+    lib = load()
+    S = sp.csr_matrix(S)
+    S.sort_indices()
+    rp = np.ascontiguousarray(S.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(S.indices, dtype=np.int32)
+    va = np.ascontiguousarray(S.data, dtype=np.float64)
+    pd = C.c_int(0)
+    i32 = C.POINTER(C.c_int32)
+    rc = lib.cpu_ref_chain_posdef(C.c_int(d), C.c_int(n_poses), C.c_int(n_ranges), C.c_int(n_trans),
+                                  rp.ctypes.data_as(i32), ci.ctypes.data_as(i32), va.ctypes.data_as(_PD),
+                                  C.c_double(float(shift)), C.byref(pd))
+    if rc:
+        raise RuntimeError(lib.cpu_ref_last_error().decode())
+    return bool(pd.value)

@@ -63,3 +63,53 @@ def test_tnt_trajectory_matches_numpy_oracle(threads):
     # the reference's operation count: per outer iteration f, QM and the model decrease each cost a
     # data-matrix product on top of one per CG iteration (TNT.h:508,511-512,573)
     assert R.spmm_count() >= sum(got.inner_iterations) + 2 * len(got.inner_iterations)
+
+
+@pytest.mark.parametrize("case", ["synth2", "synth3", "plaza2", "single_drone", "no_landmarks"])
+def test_regularized_cholesky_against_oracle_sparse_lu(case):
+    """RegularizedCholesky of the C++ port (ranges, block-tridiagonal chain, landmark border) against the oracle's
+    sparse LU of the same matrix (Q + lambda I)[0:N-1, 0:N-1] (src/CORA_problem.cpp:544-614), last row zero
+    (src/CORA_preconditioners.cpp:77-80) -- the equality tests/test.cpp:25-214 asserts for CHOLMOD."""
+    if case == "synth2":
+        p = make_synthetic(300, 3, 120, d=2, seed=5, rank=4, preconditioner=co.REG_CHOLESKY)
+    elif case == "synth3":
+        p = make_synthetic(300, 4, 160, d=3, seed=6, rank=5, preconditioner=co.REG_CHOLESKY)
+    elif case == "no_landmarks":
+        p = make_synthetic(120, 0, 0, d=3, seed=7, rank=4, preconditioner=co.REG_CHOLESKY)
+    else:
+        p = load_dataset(case, rank=4, preconditioner=co.REG_CHOLESKY)
+    p.update_problem_data()
+    V = np.random.default_rng(2).standard_normal((p.N, 3))
+    R = _ref(p, preconditioner=3, reg_lambda=p.lambda_reg)
+    Z = R.precondition(V)
+    ref = p.precondition(V)
+    assert np.abs(Z - ref).max() <= 1e-8 * np.abs(ref).max()
+    assert np.all(Z[-1] == 0.0)
+
+
+def test_chain_posdef_matches_dense_eigenvalues():
+    """The Cholesky PSD test of the port (PSD half of fast_verification, src/CORA_utils.cpp:33-57) against dense
+    eigenvalues of the certificate matrix at a random point and at the ground truth."""
+    p = make_synthetic(60, 3, 40, d=3, seed=8, rank=4)
+    p.update_problem_data()
+    Y = p.project_to_manifold(np.random.default_rng(0).standard_normal((p.N, 4)))
+    S = p.certificate_matrix(Y)
+    lam_min = float(np.linalg.eigvalsh(S.toarray())[0])
+    assert lam_min < 0
+    for shift, want in ((-lam_min * 0.9, False), (-lam_min * 1.1, True), (0.0, False)):
+        assert cpu_ref.chain_posdef(p.d, p.n, p.m, p.n + p.l, S, shift) == want
+
+
+def test_tnt_with_regularized_cholesky_matches_numpy_oracle():
+    from cora_b200 import capi, synthetic
+    d, n, l, m, r = 3, 300, 3, 120, 5
+    p = make_synthetic(n, l, m, d=d, seed=13, rank=r, preconditioner=co.REG_CHOLESKY)
+    p.update_problem_data()
+    arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=13)
+    x0 = p.project_to_manifold(synthetic.perturbed_ground_truth(d, n, l, arrays, gt, r, seed=1))
+    R = _ref(p, preconditioner=3, reg_lambda=p.lambda_reg)
+    got = R.tnt(x0, capi.default_tnt_params(max_iterations=12, max_computation_time=0.0))
+    ref = co.problem_tnt(p, x0, co.cora_tnt_params(max_iterations=12))
+    k = min(len(ref.inner_iterations), len(got.inner_iterations), 6)
+    assert got.inner_iterations[:k] == ref.inner_iterations[:k]
+    assert np.allclose(got.objective_values[:k], ref.objective_values[:k], rtol=1e-8)
