@@ -945,9 +945,11 @@ class CoraResult:
 
 
 def solve_cora(problem: Problem, x0, max_rank=20, params: Optional[TNTParams] = None,
-               verbose=False) -> CoraResult:
-    """solveCORA, src/CORA.cpp:26-243."""
+               verbose=False, tnt_fn=None) -> CoraResult:
+    """solveCORA, src/CORA.cpp:26-243.  tnt_fn(problem, X, params) -> TNTResult replaces the NumPy TNT (the C++
+    restatement oracle/cpu_ref.cpp runs the same algorithm two orders of magnitude faster: oracle/cpu_solve.py)."""
     params = params or cora_tnt_params()
+    problem_tnt_ = tnt_fn or problem_tnt
     if x0.shape[0] != problem.N:
         raise ValueError("solveCora::Explicit: bad x0 shape")
     X = problem.project_to_manifold(x0)
@@ -958,7 +960,7 @@ def solve_cora(problem: Problem, x0, max_rank=20, params: Optional[TNTParams] = 
     stages = []
     lifted_f, lifted_rank = float("nan"), 0
     while problem.rank <= max_rank:
-        res = problem_tnt(problem, X, params)
+        res = problem_tnt_(problem, X, params)
         total += int(sum(res.inner_iterations))
         eta = min(max(res.f * 5e-6, 1e-7), 1e-1)  # :154
         boot = res.x if first else cert.all_eigvecs
@@ -980,7 +982,7 @@ def solve_cora(problem: Problem, x0, max_rank=20, params: Optional[TNTParams] = 
     if X.shape[1] > problem.d:  # :200-233
         X = project_solution(problem, X)
         problem.set_rank(problem.d)
-        res = problem_tnt(problem, X, params)
+        res = problem_tnt_(problem, X, params)
         total += int(sum(res.inner_iterations))
         eta = min(max(res.f * 5e-6, 1e-7), 1e-1)
         cert = problem.certify_solution(res.x, eta, 10, boot)

@@ -5,7 +5,14 @@ correct implementations agree only to ~1e-4, so BOTH sides run with relative_dec
 
 Both sides: Preconditioner::RegularizedCholesky with the same lambda, the same initial point.  Stage 1: TNT at the
 lifted rank (where the relaxation certifies); stage 2: both refine at rank d from the SAME rounded
-point (the oracle's projectSolution of the CPU result, src/CORA.cpp:352-441)."""
+point (the oracle's projectSolution of the CPU result, src/CORA.cpp:352-441).
+
+What "the same optimum" means: at the lifted rank the landscape of Plaza2 / Single-Drone has several near-optimal
+critical points whose costs differ by 1e-5 .. 1e-4 relative and which all pass the reference's certificate
+(S + eta I >= 0 with eta = 5e-6 f, src/CORA.cpp:154) -- the CPU restatement itself lands on 723.9580, 723.9665 or
+724.0626 on Plaza2 at rank 4 depending on nothing but its thread count (summation order).  So the tight solves of
+both sides start from a COMMON point already inside one basin: the CPU restatement's result with the reference's own
+stopping rules.  From there two correct implementations must agree to 1e-6."""
 import numpy as np
 import pytest
 
@@ -59,10 +66,14 @@ def _problem(name, r):
 
 @pytest.mark.parametrize("name,r_lift", [("plaza2", 4), ("single_drone", 5), ("synthetic_5k", 5)])
 def test_final_cost_matches_cpu_restatement_to_1e6(lib, name, r_lift):
+    from cora_b200 import capi
     p, x0 = _problem(name, r_lift)
     d = p.d
     p.rank = r_lift
-    cpu, gpu = _both(p, x0, 400)
+    R = cpu_ref.CpuRef(p.d, p.n, p.m, p.n + p.l, p.Q, preconditioner=3, reg_lambda=p.lambda_reg)
+    loose = R.tnt(x0, capi.default_tnt_params(max_iterations=250, max_computation_time=0.0))  # src/CORA.cpp:95-109
+    R.close()
+    cpu, gpu = _both(p, loose.x, 400)
     assert abs(gpu.f - cpu.f) <= REL * abs(cpu.f), ("lifted", gpu.f, cpu.f, gpu.status, cpu.status)
     # rounding of the CPU solution (oracle), then both refine at rank d from that same point
     Yd = co.project_solution(p, cpu.x)
