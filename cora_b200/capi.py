@@ -123,6 +123,7 @@ SYMBOLS = [
     "cora_b200_tnt_resident", "cora_b200_spmm_resident", "cora_b200_certify", "cora_b200_saddle_escape",
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
     "cora_b200_strip_layout_roundtrip", "cora_b200_effective_preconditioner", "cora_b200_last_cert_branch", "cora_b200_phase_profile_ctas", "cora_b200_gather_best_resident",
+    "cora_b200_odometry_initialization", "cora_b200_save_solution",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
     "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
@@ -287,6 +288,32 @@ def parse_pyfg(path_or_text, from_text=False):
         return d, n, l, A
     finally:
         lib.cora_b200_pyfg_free(g)
+
+
+def odometry_initialization(d, n, l, arrays, rank, seed=0, reference_sign=False):
+    """getOdomInitialization (examples/paper_experiments.cpp:426-534) from measurement stacks; N x rank, F order."""
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    rp_i, rp_j, rp_t = i64(arrays["rp_i"]), i64(arrays["rp_j"]), f64(arrays["rp_t"])
+    rot_i, rot_j, rot_R = i64(arrays["rot_i"]), i64(arrays["rot_j"]), f64(arrays["rot_R"])
+    rg_a, rg_b = i64(arrays["rg_a"]), i64(arrays["rg_b"])
+    m = len(rg_a)
+    N = d * n + m + n + l
+    out = np.zeros((N, rank), order="F")
+    pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    _check(load().cora_b200_odometry_initialization(
+        C.c_int(d), C.c_int(n), C.c_int(l), C.c_int64(len(rp_i)), pi(rp_i), pi(rp_j), _p(rp_t),
+        C.c_int64(len(rot_i)), pi(rot_i), pi(rot_j), _p(rot_R), C.c_int64(m), pi(rg_a), pi(rg_b), C.c_int(rank),
+        C.c_uint64(seed), C.c_int(int(reference_sign)), _p(out)))
+    return out
+
+
+def save_solution(path, X, d, n, m, nt, fmt="tum", first=0, count=None):
+    """saveSolnToTum / saveSolnToG20 (src/CORA_utils.cpp:234-350) of a rounded N x d solution."""
+    X = np.asfortranarray(np.asarray(X, dtype=np.float64))
+    count = n - first if count is None else count
+    _check(load().cora_b200_save_solution(str(path).encode(), C.c_int({"tum": 0, "g2o": 1}[fmt]), C.c_int(d), C.c_int(n),
+                                          C.c_int(m), C.c_int(nt), _p(X), C.c_int64(first), C.c_int64(count)))
 
 
 def assemble(d, n, l, arrays):

@@ -2,6 +2,7 @@
 #include <mutex>
 
 #include "assemble.hpp"
+#include "pose_io.hpp"
 #include "pyfg.hpp"
 #include "chain_chol.cuh"
 #include "ops.cuh"
@@ -454,6 +455,30 @@ extern "C" int cora_b200_strip_layout_roundtrip(int d, int n_poses, int n_ranges
                                                 double *out_val, int64_t *stats) {
   return layout_roundtrip_impl(true, d, n_poses, n_ranges, n_trans, rowptr, col, val, nnz, out_rowptr, out_col,
                                out_val, stats);
+}
+
+// ------------------------------------------------- initialisation / export ----
+extern "C" int cora_b200_odometry_initialization(int d, int n_poses, int n_landmarks, int64_t E, const int64_t *rp_i,
+                                                 const int64_t *rp_j, const double *rp_t, int64_t Ep,
+                                                 const int64_t *rot_i, const int64_t *rot_j, const double *rot_R,
+                                                 int64_t m, const int64_t *rg_a, const int64_t *rg_b, int rank,
+                                                 uint64_t seed, int reference_sign, double *X_out) {
+  API_BEGIN
+  require(X_out != nullptr && (E == 0 || (rp_i && rp_j && rp_t)) && (Ep == 0 || (rot_i && rot_j && rot_R)) &&
+              (m == 0 || (rg_a && rg_b)), "NULL argument");
+  require(n_poses >= 0 && n_landmarks >= 0, "negative size");
+  odometry_initialization(d, n_poses, n_landmarks, E, rp_i, rp_j, rp_t, Ep, rot_i, rot_j, rot_R, m, rg_a, rg_b, rank,
+                          seed, reference_sign, X_out);
+  API_END
+}
+
+extern "C" int cora_b200_save_solution(const char *path, int format, int d, int n_poses, int n_ranges, int n_trans,
+                                       const double *X, int64_t first_pose, int64_t count) {
+  API_BEGIN
+  require(path && X, "NULL argument");
+  require(format == 0 || format == 1, "format: 0 = TUM, 1 = g2o");
+  save_solution(path, format == 1, d, n_poses, n_ranges, n_trans, X, first_pose, count);
+  API_END
 }
 
 // ------------------------------------------------------------------ assembly ----

@@ -312,6 +312,23 @@ int cora_b200_assemble(int d, int n_poses, int n_landmarks, int64_t E, const int
                        const double *rg_r, const double *rg_w, int64_t *nnz, int32_t *rowptr,
                        int32_t *col, double *val);
 
+/* ---- either side of the solver (host): the odometry initialisation of the reference's experiments
+ * (getOdomInitialization, examples/paper_experiments.cpp:426-534) from the measurement stacks of
+ * cora_b200_assemble, and export of a rounded N x d solution (src/CORA_utils.cpp:204-350: getRotation's
+ * determinant / orthogonality checks included -> ERUNTIME).  X is column-major in the reference row order.
+ * reference_sign != 0: range rows initialised with (second - first) as paper_experiments.cpp:500-506 does; 0: the
+ * sign the data matrix implies.  Every random draw (start pose of further chains, landmarks, SO(rank) factor)
+ * comes from `seed` (the reference's are unseeded). */
+int cora_b200_odometry_initialization(int d, int n_poses, int n_landmarks, int64_t E, const int64_t *rp_i,
+                                      const int64_t *rp_j, const double *rp_t, int64_t Ep, const int64_t *rot_i,
+                                      const int64_t *rot_j, const double *rot_R, int64_t m, const int64_t *rg_a,
+                                      const int64_t *rg_b, int rank, uint64_t seed, int reference_sign,
+                                      double *X_out /* N x rank */);
+/* format 0: TUM "time x y z qx qy qz qw" (saveSolnToTum), 1: g2o VERTEX_SE3:QUAT / VERTEX_SE2 (saveSolnToG20);
+ * poses first_pose .. first_pose + count - 1 in index order, time = position in that list. */
+int cora_b200_save_solution(const char *path, int format, int d, int n_poses, int n_ranges, int n_trans,
+                            const double *X /* N x d */, int64_t first_pose, int64_t count);
+
 /* ---- PyFG text -> measurement stacks (host): parsePyfgTextToProblem (src/pyfg_text_parser.cpp:112-321)
  * with the data model of src/CORA_problem.cpp:24-113 and the precisions of
  * include/CORA/Measurements.h:79-152.  `path_or_text` is a file name, or the file contents when
