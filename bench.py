@@ -160,14 +160,17 @@ def config_dict(args, N, nnz, m, impl="ours"):
     return cfg
 
 
-def cpu_tnt_sample(arrays, gt, Q, m, args, steps, warmup, threads, min_seconds=0.0):
+def cpu_tnt_sample(arrays, gt, Q, m, args, steps, warmup, threads, min_seconds=0.0, reg_lambda=None):
     """The CPU restatement of the reference (oracle/cpu_ref.cpp) on a bounded sample of the workload:
     the same problem and initial guess, `ref_pre` untimed outer iterations, then steps of one TNT outer
     iteration with at most `ref_cg` CG iterations.  Returns (CG it/s, CG iterations, seconds, threads)."""
     from cora_b200 import capi
     from oracle import cpu_ref
     w = WORKLOAD
-    R = cpu_ref.CpuRef(w["d"], w["n"], m, w["n"] + w["l"], Q, preconditioner=1, threads=threads)
+    if reg_lambda is None:
+        R = cpu_ref.CpuRef(w["d"], w["n"], m, w["n"] + w["l"], Q, preconditioner=1, threads=threads)
+    else:   # the reference's default preconditioner (RegularizedCholesky, same lambda as the GPU side)
+        R = cpu_ref.CpuRef(w["d"], w["n"], m, w["n"] + w["l"], Q, preconditioner=3, reg_lambda=reg_lambda, threads=threads)
     x = R.project_to_manifold(initial_guess(arrays, gt, 0, args.init))
     pre = R.tnt(x, capi.default_tnt_params(max_iterations=args.ref_pre, max_TPCG_iterations=args.ref_cg,
                                            max_computation_time=0.0))
@@ -425,6 +428,7 @@ def run_ours(args):
             from cora_b200 import restarts
             comm = restarts.make_native_comm(dist, local)      # communicator created (and warmed) before the clock starts
         h.set_preconditioner(capi.PRECON_REG_CHOLESKY)
+        reg_lambda = h.reg_lambda
         barrier()
         ts = time.perf_counter()
         out = h.solve(x0, max_rank=7, params=capi.default_tnt_params(max_computation_time=0.0))
@@ -451,7 +455,35 @@ def run_ours(args):
                       "psd_test_of_refined_solution": {"certified": bool(cert.is_certified), "branch": h.last_cert_branch,
                                                        "seconds": t_psd, "eta": eta},
                       "note": "rank 5 staircase (max rank 7) + rounding + refinement through cora_b200_solve(), host "
-                              "buffers in/out; restart seed = rank"}
+                              "buffers in/out; restart seed = rank; the reference's own stopping rules (src/CORA.cpp:95-109)"}
+        if rank == 0:
+            # the same staircase with relative_decrease_tolerance = stepsize_tolerance = 0: the rank-5 solve then runs on to
+            # the optimum of the rank-5 relaxation, where the certificate is the Cholesky PSD test of S + eta I itself
+            tt = time.perf_counter()
+            outt = h.solve(x0, max_rank=7, params=capi.default_tnt_params(
+                max_computation_time=0.0, relative_decrease_tolerance=0.0, stepsize_tolerance=0.0,
+                gradient_tolerance=1e-3, preconditioned_gradient_tolerance=0.0))
+            torch.cuda.synchronize()
+            solve_cert["tight_stopping_rules"] = {
+                "seconds": time.perf_counter() - tt, "lifted_f": float(outt["lifted_f"]), "f": float(outt["f"]),
+                "certified": bool(outt["certified"]), "cg_iterations": int(outt["total_cg_iterations"]),
+                "stages": [{"rank": s["rank"], "status": s["status"], "outer": s["outer"], "cg": s["cg"],
+                            "certified": s["certified"], "cert_branch": s["cert_branch"], "tnt_s": s["tnt_seconds"],
+                            "cert_s": s["cert_seconds"]} for s in outt["stages"]]}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            # CPU side of the same solve (RegularizedCholesky restated in oracle/cpu_ref.cpp): a full CPU
+            # solve-to-certificate of this problem takes ~20 minutes (scripts/cpu_solve_100k.py, profiles/), so the
+            # default run times a BOUNDED SAMPLE of its truncated-Newton iterations and extrapolates -- labelled so
+            ncpu = os.cpu_count() or 1
+            vc, citc, cTc, usedc = cpu_tnt_sample(arrays, gt, Q, m, args, 1, 0, ncpu, min_seconds=10.0,
+                                                  reg_lambda=reg_lambda)
+            solve_cert["cpu"] = {
+                "kind": "port", "cores": usedc, "cg_it_per_s_regularized_cholesky": vc,
+                "sample": "%d CG iterations of the CPU restatement with RegularizedCholesky in %.1f s (same problem, same "
+                          "start, same lambda)" % (citc, cTc),
+                "seconds_extrapolated": int(out["total_cg_iterations"]) / max(vc, 1e-12),
+                "extrapolation": "GPU staircase CG iterations / CPU CG rate; excludes the CPU's certification and rounding",
+                "full_run_record": "profiles/r02_cpu_solve_100k.json (scripts/cpu_solve_100k.py)"}
         if world > 1:
             # the refined rank-d solution of this rank's restart is the resident iterate of its handle
             h.set_iterate(out["x"])

@@ -5,6 +5,7 @@
 #include "pose_io.hpp"
 #include "pyfg.hpp"
 #include "chain_chol.cuh"
+#include "chain_factor_dev.cuh"
 #include "ops.cuh"
 #include "solver.cuh"
 #include "lanczos.cuh"
@@ -200,6 +201,7 @@ extern "C" int cora_b200_destroy(cora_b200_t *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   destroy_chain_chol(h->chol);
+  destroy_chain_sym(h->chain_sym);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   if (h->h_tntdev) cudaFreeHost(h->h_tntdev);

@@ -870,47 +870,9 @@ static __global__ void __launch_bounds__(kThreads) k_chain_post(int n, int l, in
 template <typename T>
 inline void upload_vec(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t s) { b.upload(v, s); }
 
-inline ChainChol *build_chain_chol(H *h, const double *d_bval, const double *d_sdiag, double shift, bool pin_last,
-                                   bool *pos_def, bool want_solve = true) {
-  const HostLayout &L = h->HL;
-  // the block-ELL and scalar-diagonal values come from the device (Q or S = Q - Lambda)
-  std::vector<double> bval((size_t)L.tile_boff[L.numTiles]), sdiag((size_t)L.l + L.m);
-  CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  if (!bval.empty()) CUDA_CHECK(cudaMemcpy(bval.data(), d_bval, bval.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  if (!sdiag.empty()) CUDA_CHECK(cudaMemcpy(sdiag.data(), d_sdiag, sdiag.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  ChainChol *C = new ChainChol();
-  try {
-    C->B = L.D1;
-    if (L.D1 == 3) chain_factor_host<3>(C->host, L, bval.data(), sdiag.data(), shift, pin_last, want_solve);
-    else chain_factor_host<4>(C->host, L, bval.data(), sdiag.data(), shift, pin_last, want_solve);
-    *pos_def = C->host.pos_def;
-    if (!want_solve || !C->host.pos_def) return C;
-    cudaStream_t s = h->stream;
-    ChainFactorHost &F = C->host;
-    for (auto &Lv : F.levels) {
-      ChainLevelDev *D = new ChainLevelDev();
-      D->G = Lv.G;
-      D->fwd.upload(Lv.fwd, s); D->bwd.upload(Lv.bwd, s); D->UR.upload(Lv.UR, s);
-      C->levels.push_back(D);
-      CUDA_CHECK(cudaStreamSynchronize(s));
-      std::vector<double>().swap(Lv.fwd);
-      std::vector<double>().swap(Lv.bwd);
-    }
-    C->rdinv.upload(F.rdinv, s); C->rinc_e.upload(F.rinc_e, s); C->rend_e.upload(F.rend_e, s);
-    C->bl_val.upload(F.bl_val, s); C->W.upload(F.W, s); C->SLinv.upload(F.SLinv, s);
-    { std::vector<int> t(F.rinc_ptr.begin(), F.rinc_ptr.end()); C->rinc_ptr.upload(t, s);
-      std::vector<int> k(F.rinc_k.begin(), F.rinc_k.end()); C->rinc_k.upload(k, s);
-      std::vector<int> x(F.rend_x.begin(), F.rend_x.end()); C->rend_x.upload(x, s);
-      std::vector<int> p(F.bl_ptr.begin(), F.bl_ptr.end()); C->bl_ptr.upload(p, s);
-      std::vector<int> rw(F.bl_row.begin(), F.bl_row.end()); C->bl_row.upload(rw, s);
-      CUDA_CHECK(cudaStreamSynchronize(s)); }
-    std::vector<double>().swap(F.W);
-  } catch (...) {
-    delete C;
-    throw;
-  }
-  return C;
-}
+// build_chain_chol: chain_factor_dev.cuh (the factorisation runs on the device)
+ChainChol *build_chain_chol(H *h, const double *d_bval, const double *d_sdiag, double shift, bool pin_last,
+                            bool *pos_def, bool want_solve = true);
 
 inline void chain_ensure_ws(H *h, ChainChol *C, int r) {
   if (r <= C->ws_cols) return;

@@ -1,0 +1,567 @@
+// chain_factor_dev.cuh -- the chain Cholesky factorisation of chain_chol.cuh computed ON THE DEVICE.
+//
+// Round 1 copied the block values back to the host (38 MB at 100k poses, blocking) and factored on one CPU thread,
+// once per preconditioner, once per PSD test and up to 60 more times in the shift search of the certification
+// (src/CORA_problem.cpp:544-614 -> getBlockCholeskyFactorization, src/CORA_preconditioners.cpp:16-44; the PSD half
+// of fast_verification, src/CORA_utils.cpp:33-57).  Here the STRUCTURE of the factorisation (which range touches
+// which translation, the border entries, the chunk geometry of every level) is extracted once per handle from the
+// layout -- it depends on Q's pattern only -- and every factorisation of M = values + shift I is a short sequence
+// of kernels on the values resident in HBM (Q, or S = Q - Lambda patched on the same structure):
+//   ranges:    rdinv_k = 1 / (sdiag_k + shift)
+//   poses:     A_i, U_i from the block-ELL slots + the Schur terms of the eliminated ranges
+//   border:    value = static coupling - sum over the ranges joining that pose and landmark
+//   landmarks: C = static + shift + sdiag - range terms (one CTA per landmark)
+//   levels:    factor_chunk<B> per chunk (the very routine the host test hook runs), separators -> next level
+//   W = T^-1 B with the solve kernels, S_L = C - B^T W reduced per landmark; only the l x l inverse of S_L and the
+//   positive-definiteness flag cross PCIe.
+#pragma once
+#include "chain_chol.cuh"
+
+namespace cora_b200 {
+
+struct ChainSymLevel {
+  ChunkGeo G;
+  DevBuf<double> A, U, SL, SR, CP;  // scratch of one factorisation (A, U: this level's chain; Schur pieces per chunk)
+};
+
+// Structure of the chain factorisation of this handle's graph (values of Q for the static couplings).
+struct ChainSym {
+  bool built = false;
+  int B = 0, n = 0, l = 0, m = 0;
+  std::vector<int32_t> rend_x;
+  std::vector<double> rend_e;
+  std::vector<int32_t> tinc_ptr, tinc_k;   // per translation (n poses, then l landmarks): incident ranges
+  std::vector<double> tinc_e;
+  std::vector<int32_t> bl_ptr, bl_row;     // border entries by landmark, sorted by pose-section row
+  std::vector<double> bl_static;
+  std::vector<int32_t> blc_ptr, blc_k;     // per border entry: ranges joining that translation and landmark
+  std::vector<double> blc_coef;
+  std::vector<int32_t> uc_ptr, uc_k;       // per pose i: ranges joining t_i and t_{i+1}
+  std::vector<double> uc_coef;
+  std::vector<int32_t> cc_j, cc_j2, cc_k;  // landmark-landmark ranges (both orders)
+  std::vector<double> cc_coef;
+  std::vector<double> Cstat;               // l x l static landmark-landmark couplings (off the diagonal array)
+  std::vector<long long> Aoff, Uoff;       // per pose: offset of the diagonal / (i, i+1) slot in the block values (-1: none)
+  // device copies
+  DevBuf<int> d_rend_x, d_tinc_ptr, d_tinc_k, d_bl_ptr, d_bl_row, d_blc_ptr, d_blc_k, d_uc_ptr, d_uc_k, d_cc_j, d_cc_j2, d_cc_k;
+  DevBuf<double> d_rend_e, d_tinc_e, d_bl_static, d_blc_coef, d_uc_coef, d_cc_coef, d_Cstat;
+  DevBuf<long long> d_Aoff, d_Uoff;
+  std::vector<ChainSymLevel *> lv;
+  DevBuf<double> d_C, d_SL;                // l x l
+  DevBuf<int> d_flag;
+  // range incidence by translation for the solve, with the pinned translation left out: [0] no pin, [1] pinned
+  std::vector<int32_t> rinc_ptr[2], rinc_k[2];
+  std::vector<double> rinc_e[2];
+  ~ChainSym() { for (auto *p : lv) delete p; }
+};
+
+// ---------------------------------------------------------------- symbolic ----
+template <int B>
+inline void chain_symbolic_build(ChainSym &S, const HostLayout &L) {
+  constexpr int BB = B * B;
+  const int n = L.n, l = L.l, m = L.m, D1 = L.D1, d = L.d;
+  S.B = B; S.n = n; S.l = l; S.m = m;
+  auto not_chain = [](const char *why) {
+    throw Error(CORA_B200_ENOTIMPL,
+                std::string("RegularizedCholesky / Cholesky certificate: the pose graph is not an odometry "
+                            "chain (") + why + "); only block-tridiagonal pose coupling + landmark border is "
+                            "implemented -- use Preconditioner::Jacobi");
+  };
+  S.Aoff.assign((size_t)std::max(n, 1), -1); S.Uoff.assign((size_t)std::max(n, 1), -1);
+  for (int i = 0; i < n; ++i) {
+    const int t = i / L.TP, p = i % L.TP;
+    const int Sl = L.tile_slots[t];
+    for (int s = 0; s < Sl; ++s) {
+      const int j = L.bcol[L.tile_coff[t] + (int64_t)s * L.TP + p] / D1;
+      const long long off = L.tile_boff[t] + (long long)s * BB * L.TP + p;
+      bool nz = false;
+      for (int e = 0; e < BB; ++e) nz = nz || L.bval[off + (long long)e * L.TP] != 0.0;
+      if (s > 0 && j == i) continue;  // padding slot
+      if (j == i) S.Aoff[i] = off;
+      else if (j == i + 1) S.Uoff[i] = off;
+      else if (j == i - 1) { }
+      else if (nz) not_chain("a pose is coupled to a non-adjacent pose");
+    }
+  }
+  const int64_t rg0 = L.nPoseRows + l;
+  auto trans_index = [&](int64_t ci) -> int {
+    if (ci < L.nPoseRows) return (ci % D1 != d) ? -1 : (int)(ci / D1);
+    if (ci < rg0) return n + (int)(ci - L.nPoseRows);
+    return -1;
+  };
+  auto for_group = [&](int64_t g, auto &&fn) {
+    for (int32_t k = L.grp_ptr[g]; k < L.grp_ptr[g + 1]; ++k) fn(L.rem_pk[k], L.rem_val[k]);
+    auto it = std::lower_bound(L.long_grp.begin(), L.long_grp.end(), (int32_t)g);
+    if (it != L.long_grp.end() && *it == g) {
+      const size_t q = it - L.long_grp.begin();
+      for (int32_t k = L.long_ptr[q]; k < L.long_ptr[q + 1]; ++k) fn(L.long_pk[k], L.long_val[k]);
+    }
+  };
+  S.rend_x.assign((size_t)std::max(m, 1) * 2, -1);
+  S.rend_e.assign((size_t)std::max(m, 1) * 2, 0.0);
+  for (int k = 0; k < m; ++k) {
+    int cnt = 0;
+    for_group((int64_t)n + l + k, [&](uint32_t pk, double v) {
+      const int x = trans_index(pk & kColMask);
+      if (x < 0) not_chain("a range row is coupled to a non-translation variable");
+      if (cnt >= 2) not_chain("a range row has more than two couplings");
+      if (cnt == 1 && S.rend_x[(size_t)k * 2] == x) {  // both couplings on the same translation: one coupling
+        S.rend_e[(size_t)k * 2] += v;
+        return;
+      }
+      S.rend_x[(size_t)k * 2 + cnt] = x;
+      S.rend_e[(size_t)k * 2 + cnt] = v;
+      ++cnt;
+    });
+  }
+  // incident ranges of every translation; adjacent-pose, pose-landmark and landmark-landmark pair terms
+  const int nt = n + l;
+  S.tinc_ptr.assign((size_t)nt + 1, 0);
+  for (int k = 0; k < m; ++k)
+    for (int p = 0; p < 2; ++p) if (S.rend_x[(size_t)k * 2 + p] >= 0) ++S.tinc_ptr[S.rend_x[(size_t)k * 2 + p] + 1];
+  for (int x = 0; x < nt; ++x) S.tinc_ptr[x + 1] += S.tinc_ptr[x];
+  S.tinc_k.assign((size_t)S.tinc_ptr[nt], 0); S.tinc_e.assign((size_t)S.tinc_ptr[nt], 0.0);
+  {
+    std::vector<int32_t> fill(S.tinc_ptr.begin(), S.tinc_ptr.end() - 1);
+    for (int k = 0; k < m; ++k)
+      for (int p = 0; p < 2; ++p) {
+        const int x = S.rend_x[(size_t)k * 2 + p];
+        if (x < 0) continue;
+        S.tinc_k[fill[x]] = k; S.tinc_e[fill[x]] = S.rend_e[(size_t)k * 2 + p]; ++fill[x];
+      }
+  }
+  struct BEnt { int32_t row, j, k; double v; };  // k >= 0: a range contribution with coefficient v (times rdinv_k)
+  std::vector<BEnt> bents;
+  std::vector<std::vector<std::pair<int32_t, double>>> uc((size_t)std::max(n, 1));
+  S.Cstat.assign((size_t)std::max(l, 1) * std::max(l, 1), 0.0);
+  for (int k = 0; k < m; ++k) {
+    const int x0 = S.rend_x[(size_t)k * 2], x1 = S.rend_x[(size_t)k * 2 + 1];
+    if (x0 < 0 || x1 < 0 || x0 == x1) continue;  // (x, x) terms come from the incidence lists
+    const double coef = S.rend_e[(size_t)k * 2] * S.rend_e[(size_t)k * 2 + 1];
+    const int a = std::min(x0, x1), b = std::max(x0, x1);
+    if (b < n) {
+      if (b == a + 1) uc[a].push_back({k, coef});
+      else not_chain("a range factor joins two non-adjacent poses");
+    } else if (a < n) {
+      bents.push_back({(int32_t)(a * D1 + d), (int32_t)(b - n), k, coef});
+    } else {
+      S.cc_j.push_back(a - n); S.cc_j2.push_back(b - n); S.cc_k.push_back(k); S.cc_coef.push_back(coef);
+      S.cc_j.push_back(b - n); S.cc_j2.push_back(a - n); S.cc_k.push_back(k); S.cc_coef.push_back(coef);
+    }
+  }
+  S.uc_ptr.assign((size_t)std::max(n, 1) + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    S.uc_ptr[i + 1] = S.uc_ptr[i] + (int32_t)uc[i].size();
+    for (auto &e : uc[i]) { S.uc_k.push_back(e.first); S.uc_coef.push_back(e.second); }
+  }
+  for (int i = 0; i < n; ++i)
+    for_group(i, [&](uint32_t pk, double v) {
+      const int64_t ci = pk & kColMask;
+      const int a = (int)(pk >> 30);
+      if (ci < L.nPoseRows) not_chain("pose-pose coupling outside the block-ELL");
+      if (ci < rg0) bents.push_back({(int32_t)(i * D1 + a), (int32_t)(ci - L.nPoseRows), -1, v});
+    });
+  for (int j = 0; j < l; ++j)
+    for_group((int64_t)n + j, [&](uint32_t pk, double v) {
+      const int64_t ci = pk & kColMask;
+      if (ci >= L.nPoseRows && ci < rg0) S.Cstat[(size_t)j * l + (ci - L.nPoseRows)] += v;
+    });
+  std::stable_sort(bents.begin(), bents.end(), [](const BEnt &x, const BEnt &y) {
+    return x.j != y.j ? x.j < y.j : x.row < y.row;
+  });
+  S.bl_ptr.assign((size_t)l + 1, 0);
+  S.blc_ptr.assign(1, 0);
+  for (size_t q = 0; q < bents.size();) {
+    size_t e = q;
+    double v = 0.0;
+    while (e < bents.size() && bents[e].j == bents[q].j && bents[e].row == bents[q].row) {
+      if (bents[e].k < 0) v += bents[e].v;
+      else { S.blc_k.push_back(bents[e].k); S.blc_coef.push_back(bents[e].v); }
+      ++e;
+    }
+    S.bl_row.push_back(bents[q].row);
+    S.bl_static.push_back(v);
+    S.blc_ptr.push_back((int32_t)S.blc_k.size());
+    ++S.bl_ptr[bents[q].j + 1];
+    q = e;
+  }
+  for (int j = 0; j < l; ++j) S.bl_ptr[j + 1] += S.bl_ptr[j];
+  // range incidence for the solve kernels, with / without the pinned translation (src/CORA_preconditioners.cpp:77-80)
+  for (int pin = 0; pin < 2; ++pin) {
+    const int pinned = pin ? (l > 0 ? n + l - 1 : n - 1) : -1;
+    S.rinc_ptr[pin].assign((size_t)nt + 1, 0);
+    for (int x = 0; x < nt; ++x)
+      S.rinc_ptr[pin][x + 1] = S.rinc_ptr[pin][x] + (x == pinned ? 0 : S.tinc_ptr[x + 1] - S.tinc_ptr[x]);
+    S.rinc_k[pin].clear(); S.rinc_e[pin].clear();
+    for (int x = 0; x < nt; ++x) {
+      if (x == pinned) continue;
+      for (int32_t q = S.tinc_ptr[x]; q < S.tinc_ptr[x + 1]; ++q) { S.rinc_k[pin].push_back(S.tinc_k[q]); S.rinc_e[pin].push_back(S.tinc_e[q]); }
+    }
+  }
+}
+
+
+// ----------------------------------------------------------------- kernels ----
+static __global__ void __launch_bounds__(kThreads) k_cf_ranges(int m, int l, const double *__restrict__ sdiag, double shift,
+                                                               double *rdinv, int *flag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const double delta = sdiag[l + k] + shift;
+  if (!(delta > 0.0)) { rdinv[k] = 1.0; atomicAnd(flag, 0); }
+  else rdinv[k] = 1.0 / delta;
+}
+
+template <int B>
+__global__ void __launch_bounds__(kThreads) k_cf_pose_blocks(int n, int TP, const double *__restrict__ bval,
+                                                             const long long *__restrict__ Aoff,
+                                                             const long long *__restrict__ Uoff, double shift,
+                                                             const int *__restrict__ tinc_ptr, const int *__restrict__ tinc_k,
+                                                             const double *__restrict__ tinc_e,
+                                                             const int *__restrict__ uc_ptr, const int *__restrict__ uc_k,
+                                                             const double *__restrict__ uc_coef,
+                                                             const double *__restrict__ rdinv, int pinned_pose_row,
+                                                             double *A, double *U) {
+  constexpr int BB = B * B, d = B - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[BB], u[BB];
+  for (int e = 0; e < BB; ++e) {
+    a[e] = Aoff[i] >= 0 ? bval[Aoff[i] + (long long)e * TP] : 0.0;
+    u[e] = Uoff[i] >= 0 ? bval[Uoff[i] + (long long)e * TP] : 0.0;
+  }
+  for (int q = 0; q < B; ++q) a[q * B + q] += shift;
+  double s = 0.0;  // Schur complement of the ranges incident to t_i (in list order: deterministic)
+  for (int q = tinc_ptr[i]; q < tinc_ptr[i + 1]; ++q) s += tinc_e[q] * tinc_e[q] * rdinv[tinc_k[q]];
+  a[d * B + d] -= s;
+  double su = 0.0;
+  for (int q = uc_ptr[i]; q < uc_ptr[i + 1]; ++q) su += uc_coef[q] * rdinv[uc_k[q]];
+  u[d * B + d] -= su;
+  if (pinned_pose_row >= 0) {
+    if (i == n - 1) {
+      for (int q = 0; q < B; ++q) { a[d * B + q] = 0.0; a[q * B + d] = 0.0; }
+      a[d * B + d] = 1.0;
+    }
+    if (i == n - 2)
+      for (int q = 0; q < B; ++q) u[q * B + d] = 0.0;
+  }
+  for (int e = 0; e < BB; ++e) { A[(size_t)i * BB + e] = a[e]; U[(size_t)i * BB + e] = u[e]; }
+}
+
+static __global__ void __launch_bounds__(kThreads) k_cf_border(int nb, const int *__restrict__ bl_ptr, int l,
+                                                               const double *__restrict__ bl_static,
+                                                               const int *__restrict__ blc_ptr, const int *__restrict__ blc_k,
+                                                               const double *__restrict__ blc_coef,
+                                                               const double *__restrict__ rdinv, const int *__restrict__ bl_row,
+                                                               int pinned_landmark, int pinned_pose_row, double *bl_val) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nb) return;
+  double v = bl_static[q];
+  for (int e = blc_ptr[q]; e < blc_ptr[q + 1]; ++e) v -= blc_coef[e] * rdinv[blc_k[e]];
+  if (bl_row[q] == pinned_pose_row) v = 0.0;
+  if (pinned_landmark >= 0 && q >= bl_ptr[pinned_landmark] && q < bl_ptr[pinned_landmark + 1]) v = 0.0;
+  bl_val[q] = v;
+}
+
+// one CTA per landmark j: row j of C = static + (sdiag_j + shift) on the diagonal - range terms
+static __global__ void __launch_bounds__(kThreads) k_cf_landmarks(int n, int l, const double *__restrict__ sdiag, double shift,
+                                                                  const double *__restrict__ Cstat,
+                                                                  const int *__restrict__ tinc_ptr, const int *__restrict__ tinc_k,
+                                                                  const double *__restrict__ tinc_e,
+                                                                  const double *__restrict__ rdinv, int ncc,
+                                                                  const int *__restrict__ cc_j, const int *__restrict__ cc_j2,
+                                                                  const int *__restrict__ cc_k, const double *__restrict__ cc_coef,
+                                                                  int pinned_landmark, double *C) {
+  __shared__ double sred[kThreads];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  double s = 0.0;
+  for (int q = tinc_ptr[n + j] + tid; q < tinc_ptr[n + j + 1]; q += kThreads) s += tinc_e[q] * tinc_e[q] * rdinv[tinc_k[q]];
+  sred[tid] = s;
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (tid < o) sred[tid] += sred[tid + o];
+    __syncthreads();
+  }
+  for (int j2 = tid; j2 < l; j2 += kThreads) {
+    double v = Cstat[(size_t)j * l + j2];
+    if (j2 == j) v += sdiag[j] + shift - sred[0];
+    for (int e = 0; e < ncc; ++e)
+      if (cc_j[e] == j && cc_j2[e] == j2) v -= cc_coef[e] * rdinv[cc_k[e]];
+    if (pinned_landmark >= 0 && (j == pinned_landmark || j2 == pinned_landmark)) v = (j == j2) ? 1.0 : 0.0;
+    C[(size_t)j * l + j2] = v;
+  }
+}
+
+template <int B>
+__global__ void __launch_bounds__(128) k_cf_factor_level(const ChunkGeo G, const double *A, const double *U, double *fwd,
+                                                         double *bwd, double *UR, double *SL, double *SR, double *CP,
+                                                         int *flag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= G.K) return;
+  if (!factor_chunk<B>(G, k, A, U, fwd, bwd, UR, SL, SR, CP)) atomicAnd(flag, 0);
+}
+
+template <int B>
+__global__ void __launch_bounds__(kThreads) k_cf_next_level(const ChunkGeo G, int nn, const double *__restrict__ A,
+                                                            const double *__restrict__ SL, const double *__restrict__ SR,
+                                                            const double *__restrict__ CP, double *A2, double *U2) {
+  constexpr int BB = B * B;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nn * BB) return;
+  const int q = t / BB, e = t - q * BB;
+  const size_t s = (size_t)((q + 1) * G.c - 1);
+  A2[t] = A[s * BB + e] - SR[(size_t)q * BB + e] - SL[(size_t)(q + 1) * BB + e];
+  U2[t] = (q < nn - 1) ? CP[(size_t)(q + 1) * BB + e] : 0.0;
+}
+
+static __global__ void __launch_bounds__(kThreads) k_cf_scatter_border(int nb, int l, const int *__restrict__ bl_ptr,
+                                                                       const int *__restrict__ bl_row,
+                                                                       const double *__restrict__ bl_val, double *W) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nb) return;
+  int j = 0;  // landmark of entry q (binary search in bl_ptr)
+  int lo = 0, hi = l;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (bl_ptr[mid] <= q) lo = mid; else hi = mid; }
+  j = lo;
+  W[(size_t)bl_row[q] * l + j] = bl_val[q];
+}
+
+// one CTA per landmark j: row j of S_L = C - B^T W (fixed summation order per thread, tree over the CTA)
+static __global__ void __launch_bounds__(kThreads) k_cf_schur(int l, const int *__restrict__ bl_ptr, const int *__restrict__ bl_row,
+                                                              const double *__restrict__ bl_val, const double *__restrict__ W,
+                                                              const double *__restrict__ C, double *SLm) {
+  __shared__ double sred[kThreads];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  for (int j2 = 0; j2 < l; ++j2) {
+    double s = 0.0;
+    for (int q = bl_ptr[j] + tid; q < bl_ptr[j + 1]; q += kThreads) s += bl_val[q] * W[(size_t)bl_row[q] * l + j2];
+    sred[tid] = s;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+      if (tid < o) sred[tid] += sred[tid + o];
+      __syncthreads();
+    }
+    if (tid == 0) SLm[(size_t)j * l + j2] = C[(size_t)j * l + j2] - sred[0];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------- driver ----
+template <typename T, typename Tsrc>
+inline void upload_as(DevBuf<T> &b, const std::vector<Tsrc> &v, cudaStream_t s) {
+  std::vector<T> t(v.begin(), v.end());
+  b.upload(t, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+inline void chain_symbolic_upload(H *h, ChainSym &S) {
+  cudaStream_t s = h->stream;
+  upload_as(S.d_rend_x, S.rend_x, s); upload_as(S.d_rend_e, S.rend_e, s);
+  upload_as(S.d_tinc_ptr, S.tinc_ptr, s); upload_as(S.d_tinc_k, S.tinc_k, s); upload_as(S.d_tinc_e, S.tinc_e, s);
+  upload_as(S.d_bl_ptr, S.bl_ptr, s); upload_as(S.d_bl_row, S.bl_row, s); upload_as(S.d_bl_static, S.bl_static, s);
+  upload_as(S.d_blc_ptr, S.blc_ptr, s); upload_as(S.d_blc_k, S.blc_k, s); upload_as(S.d_blc_coef, S.blc_coef, s);
+  upload_as(S.d_uc_ptr, S.uc_ptr, s); upload_as(S.d_uc_k, S.uc_k, s); upload_as(S.d_uc_coef, S.uc_coef, s);
+  upload_as(S.d_cc_j, S.cc_j, s); upload_as(S.d_cc_j2, S.cc_j2, s); upload_as(S.d_cc_k, S.cc_k, s);
+  upload_as(S.d_cc_coef, S.cc_coef, s);
+  upload_as(S.d_Cstat, S.Cstat, s); upload_as(S.d_Aoff, S.Aoff, s); upload_as(S.d_Uoff, S.Uoff, s);
+  const int BB = S.B * S.B;
+  int cur = S.n;
+  while (true) {
+    ChainSymLevel *Lv = new ChainSymLevel();
+    Lv->G = make_geo(cur);
+    Lv->A.alloc((size_t)std::max(cur, 1) * BB); Lv->U.alloc((size_t)std::max(cur, 1) * BB);
+    Lv->SL.alloc((size_t)(Lv->G.K + 1) * BB); Lv->SR.alloc((size_t)(Lv->G.K + 1) * BB); Lv->CP.alloc((size_t)(Lv->G.K + 1) * BB);
+    S.lv.push_back(Lv);
+    const int nn = Lv->G.top ? 0 : Lv->G.K - 1;
+    if (nn == 0) break;
+    cur = nn;
+  }
+  S.d_C.alloc((size_t)std::max(S.l, 1) * std::max(S.l, 1));
+  S.d_SL.alloc((size_t)std::max(S.l, 1) * std::max(S.l, 1));
+  S.d_flag.alloc(1);
+}
+
+// Factor M = values + shift I on the device.  d_bval / d_sdiag: block-ELL values and scalar-row diagonal on the
+// handle's structure (Q, or S = Q - Lambda).  Throws ENOTIMPL when the graph is not a chain + landmark border.
+template <int B>
+inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d_bval, const double *d_sdiag, double shift,
+                                bool pin_last, bool want_solve) {
+  constexpr int BB = B * B;
+  const int n = S.n, l = S.l, m = S.m, d = B - 1;
+  cudaStream_t s = h->stream;
+  ChainFactorHost &F = C->host;
+  F.B = B; F.n = n; F.l = l; F.m = m; F.pos_def = true;
+  F.pinned_landmark = -1; F.pinned_pose_row = -1;
+  if (pin_last) {
+    if (l > 0) F.pinned_landmark = l - 1;
+    else if (n > 0) F.pinned_pose_row = B * (n - 1) + d;
+  }
+  const int pin = pin_last ? 1 : 0;
+  F.rend_x = S.rend_x; F.bl_ptr = S.bl_ptr;
+  F.rinc_ptr = S.rinc_ptr[pin];  // (host copies of the structure: the persistent kernel's chunking reads them)
+  const int one = 1;
+  CUDA_CHECK(cudaMemcpyAsync(S.d_flag.p, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+  C->rdinv.alloc((size_t)std::max(m, 1));
+  if (m > 0) {
+    k_cf_ranges<<<(m + kThreads - 1) / kThreads, kThreads, 0, s>>>(m, l, d_sdiag, shift, C->rdinv.p, S.d_flag.p);
+    check_launch(h);
+  }
+  if (n > 0) {
+    k_cf_pose_blocks<B><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        n, h->HL.TP, d_bval, S.d_Aoff.p, S.d_Uoff.p, shift, S.d_tinc_ptr.p, S.d_tinc_k.p, S.d_tinc_e.p, S.d_uc_ptr.p,
+        S.d_uc_k.p, S.d_uc_coef.p, C->rdinv.p, F.pinned_pose_row, S.lv[0]->A.p, S.lv[0]->U.p);
+    check_launch(h);
+  }
+  const int nb = (int)S.bl_row.size();
+  C->bl_val.alloc((size_t)std::max(nb, 1));
+  if (nb > 0) {
+    k_cf_border<<<(nb + kThreads - 1) / kThreads, kThreads, 0, s>>>(nb, S.d_bl_ptr.p, l, S.d_bl_static.p, S.d_blc_ptr.p,
+                                                                   S.d_blc_k.p, S.d_blc_coef.p, C->rdinv.p, S.d_bl_row.p,
+                                                                   F.pinned_landmark, F.pinned_pose_row, C->bl_val.p);
+    check_launch(h);
+  }
+  if (l > 0) {
+    k_cf_landmarks<<<l, kThreads, 0, s>>>(n, l, d_sdiag, shift, S.d_Cstat.p, S.d_tinc_ptr.p, S.d_tinc_k.p, S.d_tinc_e.p,
+                                         C->rdinv.p, (int)S.cc_j.size(), S.d_cc_j.p, S.d_cc_j2.p, S.d_cc_k.p, S.d_cc_coef.p,
+                                         F.pinned_landmark, S.d_C.p);
+    check_launch(h);
+  }
+  // levels
+  F.levels.clear();
+  for (auto *p : C->levels) delete p;
+  C->levels.clear();
+  for (size_t lvi = 0; lvi < S.lv.size(); ++lvi) {
+    ChainSymLevel *Sv = S.lv[lvi];
+    const ChunkGeo G = Sv->G;
+    ChainLevelDev *D = new ChainLevelDev();
+    D->G = G;
+    D->fwd.alloc((size_t)G.c * 3 * BB * G.K); D->bwd.alloc((size_t)G.c * 2 * BB * G.K); D->UR.alloc((size_t)G.K * BB);
+    CUDA_CHECK(cudaMemsetAsync(D->fwd.p, 0, D->fwd.n * sizeof(double), s));
+    CUDA_CHECK(cudaMemsetAsync(D->bwd.p, 0, D->bwd.n * sizeof(double), s));
+    CUDA_CHECK(cudaMemsetAsync(D->UR.p, 0, D->UR.n * sizeof(double), s));
+    C->levels.push_back(D);
+    ChainLevelHost Hl;
+    Hl.G = G;
+    F.levels.push_back(Hl);
+    if (n > 0) {
+      k_cf_factor_level<B><<<(G.K + 127) / 128, 128, 0, s>>>(G, Sv->A.p, Sv->U.p, D->fwd.p, D->bwd.p, D->UR.p, Sv->SL.p,
+                                                            Sv->SR.p, Sv->CP.p, S.d_flag.p);
+      check_launch(h);
+    }
+    const int nn = G.top ? 0 : G.K - 1;
+    if (nn == 0) break;
+    k_cf_next_level<B><<<(nn * BB + kThreads - 1) / kThreads, kThreads, 0, s>>>(G, nn, Sv->A.p, Sv->SL.p, Sv->SR.p, Sv->CP.p,
+                                                                              S.lv[lvi + 1]->A.p, S.lv[lvi + 1]->U.p);
+    check_launch(h);
+  }
+  // landmark Schur complement S_L = C - B^T T^-1 B
+  if (l > 0) {
+    C->W.alloc((size_t)std::max(n, 1) * B * l);
+    CUDA_CHECK(cudaMemsetAsync(C->W.p, 0, C->W.n * sizeof(double), s));
+    if (nb > 0) {
+      k_cf_scatter_border<<<(nb + kThreads - 1) / kThreads, kThreads, 0, s>>>(nb, l, S.d_bl_ptr.p, S.d_bl_row.p, C->bl_val.p,
+                                                                             C->W.p);
+      check_launch(h);
+    }
+    if (n > 0) {  // W <- T^-1 W with the solve kernels (l columns, leading dimension l)
+      const int nl = (int)C->levels.size();
+      std::vector<DevBuf<double>> sol(nl), rhs(nl), cL(nl), cR(nl);
+      for (int lv = 0; lv < nl; ++lv) {
+        const ChunkGeo G = C->levels[lv]->G;
+        if (lv > 0) { sol[lv].alloc((size_t)std::max(G.n, 1) * B * l); rhs[lv].alloc((size_t)std::max(G.n, 1) * B * l); }
+        cL[lv].alloc((size_t)(G.K + 1) * B * l); cR[lv].alloc((size_t)(G.K + 1) * B * l);
+        CUDA_CHECK(cudaMemsetAsync(cL[lv].p, 0, cL[lv].n * sizeof(double), s));
+        CUDA_CHECK(cudaMemsetAsync(cR[lv].p, 0, cR[lv].n * sizeof(double), s));
+      }
+      auto solp = [&](int lv) { return lv == 0 ? C->W.p : sol[lv].p; };
+      auto rhsp = [&](int lv) { return lv == 0 ? C->W.p : rhs[lv].p; };
+      for (int lv = 0; lv < nl; ++lv) {
+        ChainLevelDev *D = C->levels[lv];
+        const int grid = (D->G.K * l + 127) / 128;
+        const bool top = (lv == nl - 1);
+        k_chain_forward<B><<<grid, 128, 0, s>>>(D->G, l, l, D->fwd.p, D->UR.p, solp(lv), rhsp(lv),
+                                                lv > 0 ? rhsp(lv - 1) : nullptr, lv > 0 ? C->levels[lv - 1]->G.c : 0,
+                                                lv > 0 ? cL[lv - 1].p : nullptr, lv > 0 ? cR[lv - 1].p : nullptr, cL[lv].p,
+                                                cR[lv].p, top ? D->bwd.p : nullptr, nullptr);
+        check_launch(h);
+      }
+      for (int lv = nl - 2; lv >= 0; --lv) {
+        ChainLevelDev *D = C->levels[lv];
+        const int grid = (D->G.K * l + 127) / 128;
+        k_chain_backward<B><<<grid, 128, 0, s>>>(D->G, l, l, D->bwd.p, solp(lv), solp(lv + 1), nullptr);
+        check_launch(h);
+      }
+      CUDA_CHECK(cudaStreamSynchronize(s));  // the scratch buffers above are released when they go out of scope
+    }
+    k_cf_schur<<<l, kThreads, 0, s>>>(l, S.d_bl_ptr.p, S.d_bl_row.p, C->bl_val.p, C->W.p, S.d_C.p, S.d_SL.p);
+    check_launch(h);
+  }
+  // what crosses PCIe: the flag and the l x l Schur complement
+  int flag = 1;
+  CUDA_CHECK(cudaMemcpyAsync(&flag, S.d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  std::vector<double> SLm((size_t)std::max(l, 1) * std::max(l, 1), 0.0);
+  if (l > 0) CUDA_CHECK(cudaMemcpyAsync(SLm.data(), S.d_SL.p, (size_t)l * l * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  F.pos_def = flag != 0;
+  if (l > 0) {
+    for (int a = 0; a < l; ++a)
+      for (int b = a + 1; b < l; ++b) {
+        const double v = 0.5 * (SLm[(size_t)a * l + b] + SLm[(size_t)b * l + a]);
+        SLm[(size_t)a * l + b] = SLm[(size_t)b * l + a] = v;
+      }
+    F.pos_def = dense_spd_inverse(SLm, l) && F.pos_def;
+    if (want_solve && F.pos_def) C->SLinv.upload(SLm, s);
+  }
+  if (want_solve && F.pos_def) {
+    C->rend_e.upload(S.rend_e, s);
+    C->rinc_e.upload(S.rinc_e[pin], s);
+    { std::vector<int> t(S.rinc_ptr[pin].begin(), S.rinc_ptr[pin].end()); C->rinc_ptr.upload(t, s);
+      std::vector<int> k(S.rinc_k[pin].begin(), S.rinc_k[pin].end()); C->rinc_k.upload(k, s);
+      std::vector<int> x(S.rend_x.begin(), S.rend_x.end()); C->rend_x.upload(x, s);
+      std::vector<int> p(S.bl_ptr.begin(), S.bl_ptr.end()); C->bl_ptr.upload(p, s);
+      std::vector<int> rw(S.bl_row.begin(), S.bl_row.end()); C->bl_row.upload(rw, s); }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+}
+
+
+// The structure of this handle's chain factorisation, built on first use (throws ENOTIMPL for non-chain graphs,
+// every time: the verdict is cached).
+inline ChainSym &chain_symbolic(H *h) {
+  if (h->chain_sym_state == 2) throw Error(CORA_B200_ENOTIMPL, h->chain_sym_error);
+  if (h->chain_sym_state == 0) {
+    ChainSym *S = new ChainSym();
+    try {
+      if (h->HL.D1 == 3) chain_symbolic_build<3>(*S, h->HL);
+      else chain_symbolic_build<4>(*S, h->HL);
+    } catch (const Error &e) {
+      delete S;
+      if (e.code == CORA_B200_ENOTIMPL) { h->chain_sym_state = 2; h->chain_sym_error = e.what(); }
+      throw;
+    }
+    chain_symbolic_upload(h, *S);
+    S->built = true;
+    h->chain_sym = S;
+    h->chain_sym_state = 1;
+  }
+  return *h->chain_sym;
+}
+
+inline ChainChol *build_chain_chol(H *h, const double *d_bval, const double *d_sdiag, double shift, bool pin_last,
+                                   bool *pos_def, bool want_solve) {
+  ChainSym &S = chain_symbolic(h);
+  ChainChol *C = new ChainChol();
+  try {
+    C->B = h->HL.D1;
+    if (h->HL.D1 == 3) chain_factor_device<3>(h, S, C, d_bval, d_sdiag, shift, pin_last, want_solve);
+    else chain_factor_device<4>(h, S, C, d_bval, d_sdiag, shift, pin_last, want_solve);
+    *pos_def = C->host.pos_def;
+  } catch (...) {
+    delete C;
+    throw;
+  }
+  return C;
+}
+
+inline void destroy_chain_sym(ChainSym *s) { delete s; }
+
+}  // namespace cora_b200

@@ -53,6 +53,7 @@ enum Vec {
 };
 
 struct ChainChol;  // chain_chol.cuh
+struct ChainSym;   // chain_factor_dev.cuh
 
 }  // namespace cora_b200
 
@@ -92,6 +93,9 @@ struct cora_b200_handle {
   double lambda_reg = -1.0;
   bool lambda_user = false;
   cora_b200::ChainChol *chol = nullptr;  // RegularizedCholesky factor of (Q + lambda I)[:-1,:-1]
+  cora_b200::ChainSym *chain_sym = nullptr;  // structure of the chain factorisation (built on first use)
+  int chain_sym_state = 0;                   // 0: not built, 1: built, 2: not a chain graph
+  std::string chain_sym_error;
   int precond_requested = CORA_B200_PRECON_JACOBI;  // what the caller asked for (precond: what is applied)
   int last_cert_branch = CORA_B200_CERT_NONE;
   // resident iterate rank

@@ -209,7 +209,7 @@ inline void build_stream_layout(const HostLayout &L, StreamHost &S) {
       append(pk.data(), pk.size() * 4);
       append(val.data(), val.size() * 8);
       pad16();
-      S.cost[u] = 1.0f + 0.3f * (float)nlong;
+      S.cost[u] = 1.0f + 0.8f * (float)nlong;
     }
     S.max_rec_bytes = std::max<int>(S.max_rec_bytes, (int)(S.rec.size() - (size_t)S.rec_off[u] * 16));
     S.info[(size_t)u * 4 + 0] = S.rec_off[u];
