@@ -44,6 +44,7 @@ CB_HD void chain_prefetch(const double *p) {
 }
 
 constexpr int kChunk = 8;    // chain blocks per chunk (7 interior + 1 separator): the substitutions are serial per chunk, so the chunk length times the number of levels is the latency of one apply
+constexpr int kPrefetchAllK = 4096;  // levels with at most this many chunks request a whole chunk's coefficients at once
 constexpr int kTopMax = 8;   // a level with at most this many blocks is solved by one thread per column
 
 // ----------------------------------------------------------- B x B block helpers ---
@@ -233,8 +234,16 @@ CB_HD void forward_chunk(const ChunkGeo G, int k, int col, int ld, const double 
     }
     if (j == L) break;
     const double *f = fwd + (size_t)j * 3 * BB * K + k;
-    if (j + 1 < L)
+    if (K <= kPrefetchAllK) {
+      // a small level: its few threads walk the chunk at one memory round trip per step, and the coefficients
+      // (streamed out of L2 by the rest of the CG iteration) come from HBM -- request the whole chunk up front,
+      // once per chunk (the columns of a chunk share the coefficients)
+      if (j == 0 && col == 0)
+        for (int jj = 1; jj < L; ++jj)
+          for (int e = 0; e < 3 * BB; ++e) chain_prefetch(fwd + ((size_t)jj * 3 * BB + e) * K + k);
+    } else if (j + 1 < L) {
       for (int e = 0; e < 3 * BB; ++e) chain_prefetch(f + (size_t)(3 * BB + e) * K);
+    }
     double y[B];
     CB_UNROLL
     for (int a = 0; a < B; ++a) {
@@ -290,8 +299,13 @@ CB_HD void backward_chunk(const ChunkGeo G, int k, int col, int ld, const double
   for (int j = L - 1; j >= 0; --j) {
     const int g = g0 + j;
     const double *f = bwd + (size_t)j * 2 * BB * K + k;
-    if (j > 0)
+    if (K <= kPrefetchAllK) {
+      if (j == L - 1 && col == 0)
+        for (int jj = 0; jj < L - 1; ++jj)
+          for (int e = 0; e < 2 * BB; ++e) chain_prefetch(bwd + ((size_t)jj * 2 * BB + e) * K + k);
+    } else if (j > 0) {
       for (int e = 0; e < 2 * BB; ++e) chain_prefetch(f - (size_t)(2 * BB - e) * K);
+    }
     double x[B];
     CB_UNROLL
     for (int a = 0; a < B; ++a) {
