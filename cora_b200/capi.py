@@ -123,7 +123,7 @@ SYMBOLS = [
     "cora_b200_tnt_resident", "cora_b200_spmm_resident", "cora_b200_certify", "cora_b200_saddle_escape",
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
     "cora_b200_strip_layout_roundtrip", "cora_b200_effective_preconditioner", "cora_b200_last_cert_branch", "cora_b200_phase_profile_ctas", "cora_b200_gather_best_resident",
-    "cora_b200_odometry_initialization", "cora_b200_save_solution",
+    "cora_b200_odometry_initialization", "cora_b200_save_solution", "cora_b200_debug_min_eigenpair",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
     "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
@@ -636,6 +636,13 @@ class Handle:
                                                C.c_int(X.shape[1]), C.c_double(f), C.c_int(int(certified)), _p(X),
                                                C.byref(w), C.byref(wf)))
         return w.value, wf.value, X
+
+    def debug_min_eigenpair(self, max_iters=200):
+        """Test hook: (theta, x, steps) of the smallest eigenpair of the handle's matrix by the device Lanczos."""
+        th, st = C.c_double(0), C.c_int(0)
+        x = np.zeros(self.N)
+        _check(self._lib.cora_b200_debug_min_eigenpair(self._h, C.c_int(max_iters), C.byref(th), _p(x), C.byref(st)))
+        return th.value, x, st.value
 
     def gather_best_resident(self, comm: "NcclComm", world_size, rank, f, certified):
         """Device-resident variant: the winner's resident iterate becomes every rank's resident iterate."""

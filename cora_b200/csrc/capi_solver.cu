@@ -220,6 +220,14 @@ extern "C" int cora_b200_certify(cora_b200_t *h, int r, const double *Y, double 
   API_END
 }
 
+extern "C" int cora_b200_debug_min_eigenpair(cora_b200_t *h, int max_iters, double *theta, double *x, int *steps) {
+  API_BEGIN
+  require(h && theta && x, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  debug_min_eigenpair(h, max_iters, theta, x, steps);
+  API_END
+}
+
 extern "C" int cora_b200_saddle_escape(cora_b200_t *h, int r_new, const double *Y, double theta, const double *v,
                                        double gradient_tolerance, double preconditioned_gradient_tolerance,
                                        double *Y_out) {

@@ -464,6 +464,33 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
   return out;
 }
 
+// Test hook: smallest eigenpair of the handle's own matrix by the device Lanczos of the certification (plain mode,
+// full re-orthogonalisation).  Lets the reference's eigenpair known answers (I - 2 x x^T -> (-1, +-x),
+// tests/test_certification.cpp:45-79) pin the CUDA eigen-search directly: any symmetric matrix can be loaded as a
+// "problem" made of landmark rows only.
+inline void debug_min_eigenpair(H *h, int max_iters, double *theta, double *x_out, int *steps) {
+  ensure_workspace(h, 1);
+  h->resident_r = 0;
+  const long long N = h->DL.N;
+  double *x = h->ws[V_T1].p, *w = h->ws[V_T0].p, *t = h->ws[V_Z].p;
+  auto Qx = [&](const double *q, double *y) {
+    launch_qprod(h, QM_SPMM, q, nullptr, nullptr, y, nullptr, 1, POST_STORE, SC_TMP, nullptr);
+  };
+  auto rayleigh = [&](const double *v) -> double {
+    Qx(v, t);
+    launch_dot2(h, v, t, v, v, N, SC_TMP);
+    read_scal(h);
+    return h->h_scal[SC_TMP] / h->h_scal[SC_TMP + 1];
+  };
+  auto never = [](double) { return false; };
+  DevBuf<double> basis;
+  const int kmax = (int)std::min<long long>(std::max(2, max_iters), N - 1);
+  LanczosResult L = device_lanczos(h, Qx, rayleigh, never, /*pick_largest=*/false, kmax, basis, w, x, 12345u);
+  *theta = L.theta_S;
+  if (steps) *steps = L.steps;
+  export_matrix(h, x, 1, x_out);
+}
+
 inline void certify_host(H *h, int r, const double *Y, double eta, int nx, const double *bootstrap,
                          int bootstrap_cols, int max_iters, int *is_certified, double *theta, double *x,
                          double *all_eigvecs, int cap, int *ncols, int64_t *num_iters) {

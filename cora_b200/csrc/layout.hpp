@@ -301,7 +301,12 @@ inline void build_layout(HostLayout &L, int d, int n, int m, int nt, const int32
     // hub rows are split in chunks of equal size, about one chunk per resident CTA of the persistent kernel: the
     // chunk partial sums are produced by all CTAs in one round and a hub row is left with few partials to add up
     L.long_chunk_ptr.assign(1, 0);
-    const int64_t chunk = std::max<int64_t>(kHubChunk, ((int64_t)L.long_pk.size() + kHubItems - 1) / kHubItems);
+    int64_t chunk = std::max<int64_t>(kHubChunk, ((int64_t)L.long_pk.size() + kHubItems - 1) / kHubItems);
+    for (;; chunk += std::max<int64_t>(1, chunk / 64)) {  // rounding up per row must not push the count past one round
+      int64_t cnt = 0;
+      for (size_t q = 0; q < L.long_grp.size(); ++q) cnt += std::max<int64_t>(1, (L.long_ptr[q + 1] - L.long_ptr[q] + chunk - 1) / chunk);
+      if (cnt <= kHubItems || chunk >= (int64_t)L.long_pk.size()) break;
+    }
     for (size_t q = 0; q < L.long_grp.size(); ++q) {
       const int64_t e = L.long_ptr[q + 1] - L.long_ptr[q];
       const int64_t nch = std::max<int64_t>(1, (e + chunk - 1) / chunk), per = (e + nch - 1) / nch;

@@ -166,10 +166,17 @@ struct PCtx {
   }
 };
 
+// In-kernel phase clocks (thread 0 of every CTA, %globaltimer).  CORA_NO_PHASE_TIMERS compiles them out (A/B of
+// their own cost); CORA_STRIP_TIMERS adds the per-strip wait / compute split of the streaming phases.
 __device__ __forceinline__ void ph_begin(PCtx &c) {
+#ifndef CORA_NO_PHASE_TIMERS
   if (c.tid == 0) c.tph[0] = global_timer_ns();
+#endif
 }
 __device__ __forceinline__ void ph_end(PCtx &c, int id) {
+#ifdef CORA_NO_PHASE_TIMERS
+  return;
+#endif
   if (c.tid == 0) {
     const unsigned long long t = global_timer_ns();
     c.prof_ns[id] += t - c.tph[0];
@@ -179,9 +186,14 @@ __device__ __forceinline__ void ph_end(PCtx &c, int id) {
 }
 
 __device__ __forceinline__ void sub_begin(PCtx &c) {
+#ifdef CORA_STRIP_TIMERS
   if (c.tid == 0) c.tph[1] = global_timer_ns();
+#endif
 }
 __device__ __forceinline__ void sub_end(PCtx &c, int id) {
+#ifndef CORA_STRIP_TIMERS
+  return;
+#endif
   if (c.tid == 0) {
     const unsigned long long t = global_timer_ns();
     c.prof_ns[id] += t - c.tph[1];

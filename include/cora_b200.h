@@ -217,6 +217,10 @@ int cora_b200_certify(cora_b200_t *h, int r, const double *Y, double eta, int nx
                       int *is_certified, double *theta, double *x, double *all_eigvecs,
                       int all_eigvecs_cols_capacity, int *all_eigvecs_cols,
                       int64_t *num_iters);
+/* Test hook: smallest eigenpair of the handle's OWN matrix by the device Lanczos the certification uses (the
+ * reference's eigenpair known answers, tests/test_certification.cpp:45-79, load I - 2 x x^T as a matrix of landmark
+ * rows only: d any, n_poses = n_ranges = 0, n_trans = N). */
+int cora_b200_debug_min_eigenpair(cora_b200_t *h, int max_iters, double *theta, double *x /* N */, int *steps);
 /* Which test decided the last cora_b200_certify / staircase stage on this handle (CORA_B200_CERT_*). */
 int cora_b200_last_cert_branch(const cora_b200_t *h, int *branch);
 

@@ -184,3 +184,22 @@ def test_native_nccl_gather_best_world_size_one(lib):
             assert np.array_equal(h.get_iterate(3), X)
     finally:
         comm.close()
+
+
+@pytest.mark.parametrize("n", [10, 1000])
+def test_device_lanczos_known_answers(lib, n):
+    """The reference's eigenpair known answers (tests/test_certification.cpp:45-79: S = I - 2 x x^T has the smallest
+    eigenpair (-1, +-x); S = I - x x^T has lambda_min = 0) on the CUDA eigen-search itself: the matrix is loaded as a
+    problem of landmark rows only."""
+    import scipy.sparse as sp
+    from cora_b200 import capi
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    x /= np.linalg.norm(x)
+    for scale, lam in ((2.0, -1.0), (1.0, 0.0)):
+        S = sp.csr_matrix(np.eye(n) - scale * np.outer(x, x))
+        with capi.Handle(3, 0, 0, n, S, preconditioner=capi.PRECON_JACOBI) as h:
+            theta, v, steps = h.debug_min_eigenpair(200)
+        assert abs(theta - lam) <= 1e-8, (theta, steps)
+        assert steps <= 12                      # two distinct eigenvalues: Lanczos terminates in two steps
+        assert min(np.linalg.norm(v - x), np.linalg.norm(v + x)) <= 1e-6
