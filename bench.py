@@ -258,13 +258,23 @@ def roofline_cfg5(torch, dist, world, local, stream, peak, n=1_000_000, reps=30)
         cg_all = float(cg)
     mxp, _ = ({}, {}) if not hasattr(h, "phase_profile_ctas") else (h.phase_profile_ctas(), None)
     h.close()
+    traffic = None
+    try:   # DRAM bytes per product from the committed ncu capture of this kernel on this workload (8 products per launch)
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r02_spmm_1m_ncu_raw.csv"))))
+        hdr, units, v = rows[0], rows[1], rows[2]
+        get = lambda name: float(v[hdr.index(name)].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[hdr.index(name)]]
+        traffic = (get("dram__bytes_read.sum") + get("dram__bytes_write.sum")) / 8.0
+    except Exception:
+        pass
     gbs_spmm = ab["spmm"] / t_spmm / 1e9
     gbs_cg = (cg * ab["cg_iter"] + outer * b_outer) / res.device_time / 1e9
     return {"workload": "synthetic %d-pose SE(3) + %d ranges, %d landmarks, rank %d (BASELINE configs[4]); one replica "
                         "per GPU" % (n, m, l, r),
             "N": int(N), "nnz": int(Q.nnz), "replicas": world,
             "spmm": {"us": 1e6 * t_spmm, "reps": reps, "algorithmic_bytes": ab["spmm"], "achieved_gbs": gbs_spmm,
-                     "frac": gbs_spmm / peak, "aggregate_gbs": world * gbs_spmm,
+                     "frac": gbs_spmm / peak, "aggregate_gbs": world * gbs_spmm, "traffic": traffic,
+                     "traffic_kind": "committed ncu --set full capture (profiles/r02_spmm_1m_ncu_raw.csv), not measured in this run",
                      "timing": "CUDA events around one cooperative launch of `reps` products; max over ranks"},
             "cg_iteration": {"us": 1e6 * t_cg / max(1, cg), "iterations_timed": cg, "outer_iterations": outer,
                              "algorithmic_bytes": ab["cg_iter"], "achieved_gbs": gbs_cg, "frac": gbs_cg / peak,
@@ -470,6 +480,26 @@ def run_ours(args):
                 "stages": [{"rank": s["rank"], "status": s["status"], "outer": s["outer"], "cg": s["cg"],
                             "certified": s["certified"], "cert_branch": s["cert_branch"], "tnt_s": s["tnt_seconds"],
                             "cert_s": s["cert_seconds"]} for s in outt["stages"]]}
+        if rank == 0:
+            # the certificate proper at full size: TNT at rank 5 with the tight rules, then the Cholesky test of
+            # S + eta I on the resident iterate (PSD half of fast_verification), timed on its own
+            h.set_iterate(x0)
+            rt = h.tnt_resident(capi.default_tnt_params(
+                max_iterations=250, max_computation_time=0.0, relative_decrease_tolerance=0.0, stepsize_tolerance=0.0,
+                gradient_tolerance=1e-3, preconditioned_gradient_tolerance=0.0))
+            eta5 = min(max(rt.f * 5e-6, 1e-7), 1e-1)
+            times, verdicts = [], []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                tq = time.perf_counter()
+                verdicts.append(h.psd_test(eta5, r=r))
+                torch.cuda.synchronize()
+                times.append(time.perf_counter() - tq)
+            solve_cert["psd_test_rank5_tight"] = {
+                "f": float(rt.f), "gradient_norm": float(rt.gradfx_norm), "status": rt.status, "eta": eta5,
+                "is_psd": bool(verdicts[-1]), "ms_median": 1e3 * float(np.median(times)),
+                "what": "Lambda blocks + certificate values + chain Cholesky of S + eta I (N = %d), all on the device; "
+                        "wall clock of cora_b200_psd_test on the resident iterate" % N}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             # CPU side of the same solve (RegularizedCholesky restated in oracle/cpu_ref.cpp): a full CPU
             # solve-to-certificate of this problem takes ~20 minutes (scripts/cpu_solve_100k.py, profiles/), so the

@@ -123,7 +123,7 @@ SYMBOLS = [
     "cora_b200_tnt_resident", "cora_b200_spmm_resident", "cora_b200_certify", "cora_b200_saddle_escape",
     "cora_b200_project_solution", "cora_b200_solve", "cora_b200_gather_best", "cora_b200_layout_roundtrip",
     "cora_b200_strip_layout_roundtrip", "cora_b200_effective_preconditioner", "cora_b200_last_cert_branch", "cora_b200_phase_profile_ctas", "cora_b200_gather_best_resident",
-    "cora_b200_odometry_initialization", "cora_b200_save_solution", "cora_b200_debug_min_eigenpair",
+    "cora_b200_odometry_initialization", "cora_b200_save_solution", "cora_b200_debug_min_eigenpair", "cora_b200_psd_test",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
     "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
@@ -636,6 +636,16 @@ class Handle:
                                                C.c_int(X.shape[1]), C.c_double(f), C.c_int(int(certified)), _p(X),
                                                C.byref(w), C.byref(wf)))
         return w.value, wf.value, X
+
+    def psd_test(self, eta, Y=None, r=None):
+        """Is S(Y) + eta I positive definite (Cholesky on the device)?  Y None: the resident iterate of rank r."""
+        v = C.c_int(0)
+        if Y is None:
+            _check(self._lib.cora_b200_psd_test(self._h, C.c_int(r), None, C.c_double(eta), C.byref(v)))
+        else:
+            Y = self._mat(Y)
+            _check(self._lib.cora_b200_psd_test(self._h, C.c_int(Y.shape[1]), _p(Y), C.c_double(eta), C.byref(v)))
+        return bool(v.value)
 
     def debug_min_eigenpair(self, max_iters=200):
         """Test hook: (theta, x, steps) of the smallest eigenpair of the handle's matrix by the device Lanczos."""

@@ -220,6 +220,22 @@ extern "C" int cora_b200_certify(cora_b200_t *h, int r, const double *Y, double 
   API_END
 }
 
+extern "C" int cora_b200_psd_test(cora_b200_t *h, int r, const double *Y, double eta, int *is_psd) {
+  API_BEGIN
+  require(h && is_psd, "NULL argument");
+  check_geom_rank(r);
+  CUDA_CHECK(cudaSetDevice(h->device));
+  ensure_workspace(h, r);
+  if (Y != nullptr) {  // NULL: test the resident iterate
+    h->resident_r = 0;
+    import_matrix(h, Y, r, h->ws[V_X].p, r);
+    h->resident_r = r;
+  }
+  require(h->resident_r == r, "no resident iterate of this rank");
+  *is_psd = psd_test_resident(h, r, eta) ? 1 : 0;
+  API_END
+}
+
 extern "C" int cora_b200_debug_min_eigenpair(cora_b200_t *h, int max_iters, double *theta, double *x, int *steps) {
   API_BEGIN
   require(h && theta && x, "NULL argument");

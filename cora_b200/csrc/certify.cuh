@@ -464,6 +464,19 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
   return out;
 }
 
+// The PSD half of fast_verification on its own (src/CORA_utils.cpp:33-57): is S(Y) + eta I positive definite?
+// Lambda blocks, certificate values on Q's structure and the chain Cholesky all run on the device; no sv-ratio
+// short-circuit, no eigen-search.  Throws ENOTIMPL on graphs without a device factorisation.
+inline bool psd_test_resident(H *h, int r, double eta) {
+  ensure_workspace(h, r);
+  compute_lambda(h, h->ws[V_X].p, r);
+  DevLayout LS = build_certificate_layout(h, 0.0);
+  bool pd = false;
+  ChainChol *C = build_chain_chol(h, LS.bval, LS.sdiag, eta, /*pin_last=*/false, &pd, /*want_solve=*/false);
+  destroy_chain_chol(C);
+  return pd;
+}
+
 // Test hook: smallest eigenpair of the handle's own matrix by the device Lanczos of the certification (plain mode,
 // full re-orthogonalisation).  Lets the reference's eigenpair known answers (I - 2 x x^T -> (-1, +-x),
 // tests/test_certification.cpp:45-79) pin the CUDA eigen-search directly: any symmetric matrix can be loaded as a

@@ -217,6 +217,11 @@ int cora_b200_certify(cora_b200_t *h, int r, const double *Y, double eta, int nx
                       int *is_certified, double *theta, double *x, double *all_eigvecs,
                       int all_eigvecs_cols_capacity, int *all_eigvecs_cols,
                       int64_t *num_iters);
+/* The PSD half of fast_verification alone (src/CORA_utils.cpp:33-57): *is_psd = 1 iff S(Y) + eta I is positive
+ * definite (Cholesky on the device).  Y == NULL tests the resident iterate of rank r.  No sv-ratio short-circuit
+ * (src/CORA_problem.cpp:1039-1049), no eigen-search.  ENOTIMPL on graphs without a device factorisation. */
+int cora_b200_psd_test(cora_b200_t *h, int r, const double *Y, double eta, int *is_psd);
+
 /* Test hook: smallest eigenpair of the handle's OWN matrix by the device Lanczos the certification uses (the
  * reference's eigenpair known answers, tests/test_certification.cpp:45-79, load I - 2 x x^T as a matrix of landmark
  * rows only: d any, n_poses = n_ranges = 0, n_trans = N). */

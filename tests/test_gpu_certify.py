@@ -203,3 +203,18 @@ def test_device_lanczos_known_answers(lib, n):
         assert abs(theta - lam) <= 1e-8, (theta, steps)
         assert steps <= 12                      # two distinct eigenvalues: Lanczos terminates in two steps
         assert min(np.linalg.norm(v - x), np.linalg.norm(v + x)) <= 1e-6
+
+
+def test_psd_test_matches_dense_eigenvalues(lib):
+    """cora_b200_psd_test (Cholesky of S + eta I on the device: the PSD half of fast_verification,
+    src/CORA_utils.cpp:33-57) against dense eigenvalues of the oracle's certificate matrix, either side of
+    -lambda_min(S)."""
+    p = make_synthetic(n=120, l=3, m=60, d=3, seed=8, rank=4)
+    p.update_problem_data()
+    Y = p.project_to_manifold(np.random.default_rng(0).standard_normal((p.N, 4)))
+    lam_min = float(np.linalg.eigvalsh(p.certificate_matrix(Y).toarray())[0])
+    assert lam_min < 0
+    with make_handle(p) as h:
+        assert h.psd_test(-lam_min * 1.05, Y) is True
+        assert h.psd_test(-lam_min * 0.95, Y) is False
+        assert h.psd_test(1e-6, Y) is False

@@ -80,4 +80,6 @@ def test_final_cost_matches_cpu_restatement_to_1e6(lib, name, r_lift):
     p.rank = d
     cpu2, gpu2 = _both(p, Yd, 200)
     assert abs(gpu2.f - cpu2.f) <= REL * abs(cpu2.f), ("refined", gpu2.f, cpu2.f, gpu2.status, cpu2.status)
-    assert gpu2.f >= gpu.f * (1 - 1e-9)   # the rank-d cost can only be above the relaxation's
+    # the rank-d cost can only be above the relaxation's (up to the convergence tolerance of the two solves: on the
+    # synthetic chain the relaxation is tight and the two costs coincide to ~1e-9)
+    assert gpu2.f >= gpu.f * (1 - REL)
