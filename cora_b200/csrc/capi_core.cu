@@ -201,6 +201,7 @@ extern "C" int cora_b200_destroy(cora_b200_t *h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   destroy_chain_chol(h->chol);
+  destroy_chain_chol(h->chol_spare);
   destroy_chain_sym(h->chain_sym);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);

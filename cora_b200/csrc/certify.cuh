@@ -411,7 +411,7 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
   try {
     bool pd = false;
     C = build_chain_chol(h, LS.bval, LS.sdiag, eta, /*pin_last=*/false, &pd, /*want_solve=*/false);
-    destroy_chain_chol(C);
+    release_chain_chol(h, C);
     C = nullptr;
     if (pd) {  // S + eta I > 0  (src/CORA_utils.cpp:33-57)
       out.certified = true;
@@ -435,13 +435,13 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
       bool pd = false;
       C = build_chain_chol(h, LS.bval, LS.sdiag, sigma, false, &pd, true);
       if (pd) break;
-      destroy_chain_chol(C);
+      release_chain_chol(h, C);
       C = nullptr;
     }
     if (!C) throw Error(CORA_B200_ERUNTIME, "certification: could not shift S to positive definiteness");
     auto op = [&](const double *q, double *y) { chain_solve(h, C, q, y, 1, nullptr); };
     LanczosResult L = device_lanczos(h, op, rayleigh, accept, /*pick_largest=*/true, std::min(kmax, 80), basis, w, x, 12345u);
-    destroy_chain_chol(C);
+    release_chain_chol(h, C);
     out.iters = L.steps;
     out.theta = L.theta_S;
     out.have_x = true;
@@ -473,7 +473,7 @@ inline bool psd_test_resident(H *h, int r, double eta) {
   DevLayout LS = build_certificate_layout(h, 0.0);
   bool pd = false;
   ChainChol *C = build_chain_chol(h, LS.bval, LS.sdiag, eta, /*pin_last=*/false, &pd, /*want_solve=*/false);
-  destroy_chain_chol(C);
+  release_chain_chol(h, C);
   return pd;
 }
 

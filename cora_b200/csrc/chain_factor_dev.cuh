@@ -47,6 +47,7 @@ struct ChainSym {
   DevBuf<double> d_rend_e, d_tinc_e, d_bl_static, d_blc_coef, d_uc_coef, d_cc_coef, d_Cstat;
   DevBuf<long long> d_Aoff, d_Uoff;
   std::vector<ChainSymLevel *> lv;
+  std::vector<DevBuf<double>> wsol, wrhs, wcL, wcR;  // work vectors of the W = T^-1 B solve (l columns), per level
   DevBuf<double> d_C, d_SL;                // l x l
   DevBuf<int> d_flag;
   // range incidence by translation for the solve, with the pinned translation left out: [0] no pin, [1] pinned
@@ -400,7 +401,7 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
   F.rinc_ptr = S.rinc_ptr[pin];  // (host copies of the structure: the persistent kernel's chunking reads them)
   const int one = 1;
   CUDA_CHECK(cudaMemcpyAsync(S.d_flag.p, &one, sizeof(int), cudaMemcpyHostToDevice, s));
-  C->rdinv.alloc((size_t)std::max(m, 1));
+  C->rdinv.reserve((size_t)std::max(m, 1));
   if (m > 0) {
     k_cf_ranges<<<(m + kThreads - 1) / kThreads, kThreads, 0, s>>>(m, l, d_sdiag, shift, C->rdinv.p, S.d_flag.p);
     check_launch(h);
@@ -412,7 +413,7 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
     check_launch(h);
   }
   const int nb = (int)S.bl_row.size();
-  C->bl_val.alloc((size_t)std::max(nb, 1));
+  C->bl_val.reserve((size_t)std::max(nb, 1));
   if (nb > 0) {
     k_cf_border<<<(nb + kThreads - 1) / kThreads, kThreads, 0, s>>>(nb, S.d_bl_ptr.p, l, S.d_bl_static.p, S.d_blc_ptr.p,
                                                                    S.d_blc_k.p, S.d_blc_coef.p, C->rdinv.p, S.d_bl_row.p,
@@ -427,18 +428,21 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
   }
   // levels
   F.levels.clear();
-  for (auto *p : C->levels) delete p;
-  C->levels.clear();
+  if (C->levels.size() != S.lv.size()) {  // (a recycled factor of the same handle keeps its level buffers)
+    for (auto *p : C->levels) delete p;
+    C->levels.clear();
+    for (size_t lvi = 0; lvi < S.lv.size(); ++lvi) C->levels.push_back(new ChainLevelDev());
+  }
   for (size_t lvi = 0; lvi < S.lv.size(); ++lvi) {
     ChainSymLevel *Sv = S.lv[lvi];
     const ChunkGeo G = Sv->G;
-    ChainLevelDev *D = new ChainLevelDev();
+    ChainLevelDev *D = C->levels[lvi];
     D->G = G;
-    D->fwd.alloc((size_t)G.c * 3 * BB * G.K); D->bwd.alloc((size_t)G.c * 2 * BB * G.K); D->UR.alloc((size_t)G.K * BB);
-    CUDA_CHECK(cudaMemsetAsync(D->fwd.p, 0, D->fwd.n * sizeof(double), s));
-    CUDA_CHECK(cudaMemsetAsync(D->bwd.p, 0, D->bwd.n * sizeof(double), s));
-    CUDA_CHECK(cudaMemsetAsync(D->UR.p, 0, D->UR.n * sizeof(double), s));
-    C->levels.push_back(D);
+    const size_t nf = (size_t)G.c * 3 * BB * G.K, nbw = (size_t)G.c * 2 * BB * G.K, nu = (size_t)G.K * BB;
+    D->fwd.reserve(nf); D->bwd.reserve(nbw); D->UR.reserve(nu);
+    CUDA_CHECK(cudaMemsetAsync(D->fwd.p, 0, nf * sizeof(double), s));
+    CUDA_CHECK(cudaMemsetAsync(D->bwd.p, 0, nbw * sizeof(double), s));
+    CUDA_CHECK(cudaMemsetAsync(D->UR.p, 0, nu * sizeof(double), s));
     ChainLevelHost Hl;
     Hl.G = G;
     F.levels.push_back(Hl);
@@ -455,8 +459,8 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
   }
   // landmark Schur complement S_L = C - B^T T^-1 B
   if (l > 0) {
-    C->W.alloc((size_t)std::max(n, 1) * B * l);
-    CUDA_CHECK(cudaMemsetAsync(C->W.p, 0, C->W.n * sizeof(double), s));
+    C->W.reserve((size_t)std::max(n, 1) * B * l);
+    CUDA_CHECK(cudaMemsetAsync(C->W.p, 0, (size_t)std::max(n, 1) * B * l * sizeof(double), s));
     if (nb > 0) {
       k_cf_scatter_border<<<(nb + kThreads - 1) / kThreads, kThreads, 0, s>>>(nb, l, S.d_bl_ptr.p, S.d_bl_row.p, C->bl_val.p,
                                                                              C->W.p);
@@ -464,13 +468,15 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
     }
     if (n > 0) {  // W <- T^-1 W with the solve kernels (l columns, leading dimension l)
       const int nl = (int)C->levels.size();
-      std::vector<DevBuf<double>> sol(nl), rhs(nl), cL(nl), cR(nl);
+      std::vector<DevBuf<double>> &sol = S.wsol, &rhs = S.wrhs, &cL = S.wcL, &cR = S.wcR;  // kept across factorisations
+      if ((int)sol.size() != nl) { sol = std::vector<DevBuf<double>>(nl); rhs = std::vector<DevBuf<double>>(nl);
+                                   cL = std::vector<DevBuf<double>>(nl); cR = std::vector<DevBuf<double>>(nl); }
       for (int lv = 0; lv < nl; ++lv) {
         const ChunkGeo G = C->levels[lv]->G;
-        if (lv > 0) { sol[lv].alloc((size_t)std::max(G.n, 1) * B * l); rhs[lv].alloc((size_t)std::max(G.n, 1) * B * l); }
-        cL[lv].alloc((size_t)(G.K + 1) * B * l); cR[lv].alloc((size_t)(G.K + 1) * B * l);
-        CUDA_CHECK(cudaMemsetAsync(cL[lv].p, 0, cL[lv].n * sizeof(double), s));
-        CUDA_CHECK(cudaMemsetAsync(cR[lv].p, 0, cR[lv].n * sizeof(double), s));
+        if (lv > 0) { sol[lv].reserve((size_t)std::max(G.n, 1) * B * l); rhs[lv].reserve((size_t)std::max(G.n, 1) * B * l); }
+        cL[lv].reserve((size_t)(G.K + 1) * B * l); cR[lv].reserve((size_t)(G.K + 1) * B * l);
+        CUDA_CHECK(cudaMemsetAsync(cL[lv].p, 0, (size_t)(G.K + 1) * B * l * sizeof(double), s));
+        CUDA_CHECK(cudaMemsetAsync(cR[lv].p, 0, (size_t)(G.K + 1) * B * l * sizeof(double), s));
       }
       auto solp = [&](int lv) { return lv == 0 ? C->W.p : sol[lv].p; };
       auto rhsp = [&](int lv) { return lv == 0 ? C->W.p : rhs[lv].p; };
@@ -490,7 +496,6 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
         k_chain_backward<B><<<grid, 128, 0, s>>>(D->G, l, l, D->bwd.p, solp(lv), solp(lv + 1), nullptr);
         check_launch(h);
       }
-      CUDA_CHECK(cudaStreamSynchronize(s));  // the scratch buffers above are released when they go out of scope
     }
     k_cf_schur<<<l, kThreads, 0, s>>>(l, S.d_bl_ptr.p, S.d_bl_row.p, C->bl_val.p, C->W.p, S.d_C.p, S.d_SL.p);
     check_launch(h);
@@ -549,7 +554,9 @@ inline ChainSym &chain_symbolic(H *h) {
 inline ChainChol *build_chain_chol(H *h, const double *d_bval, const double *d_sdiag, double shift, bool pin_last,
                                    bool *pos_def, bool want_solve) {
   ChainSym &S = chain_symbolic(h);
-  ChainChol *C = new ChainChol();
+  ChainChol *C = h->chol_spare ? h->chol_spare : new ChainChol();  // recycle the buffers of the last released factor
+  h->chol_spare = nullptr;
+  C->ws_cols = C->ws_cols;  // (work vectors of the apply are sized by columns only: still valid)
   try {
     C->B = h->HL.D1;
     if (h->HL.D1 == 3) chain_factor_device<3>(h, S, C, d_bval, d_sdiag, shift, pin_last, want_solve);
@@ -563,5 +570,13 @@ inline ChainChol *build_chain_chol(H *h, const double *d_bval, const double *d_s
 }
 
 inline void destroy_chain_sym(ChainSym *s) { delete s; }
+
+// Release a factor: its device buffers are kept for the next factorisation of the same handle (the PSD tests and the
+// shift search of the certification factor the same structure again and again).
+inline void release_chain_chol(H *h, ChainChol *C) {
+  if (!C) return;
+  if (h->chol_spare == nullptr) h->chol_spare = C;
+  else delete C;
+}
 
 }  // namespace cora_b200

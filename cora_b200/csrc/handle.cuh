@@ -17,6 +17,9 @@ struct DevBuf {
     n = count;
     if (count) CUDA_CHECK(cudaMalloc((void **)&p, count * sizeof(T)));
   }
+  void reserve(size_t count) {  // grow only: keeps the allocation when it is already large enough
+    if (n < count || p == nullptr) alloc(count);
+  }
   void upload(const std::vector<T> &v, cudaStream_t s) {
     alloc(v.size() ? v.size() : 1);
     if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
@@ -94,6 +97,7 @@ struct cora_b200_handle {
   bool lambda_user = false;
   cora_b200::ChainChol *chol = nullptr;  // RegularizedCholesky factor of (Q + lambda I)[:-1,:-1]
   cora_b200::ChainSym *chain_sym = nullptr;  // structure of the chain factorisation (built on first use)
+  cora_b200::ChainChol *chol_spare = nullptr;  // buffers of the last released factor, recycled by the next one
   int chain_sym_state = 0;                   // 0: not built, 1: built, 2: not a chain graph
   std::string chain_sym_error;
   int precond_requested = CORA_B200_PRECON_JACOBI;  // what the caller asked for (precond: what is applied)

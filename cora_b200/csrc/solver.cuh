@@ -47,7 +47,7 @@ inline void precondition_project(H *h, const double *Y, double *R, double *Vout,
 }
 
 inline void update_preconditioner(H *h) {
-  destroy_chain_chol(h->chol);
+  release_chain_chol(h, h->chol);
   h->chol = nullptr;
   h->precond_requested = h->precond;
   if (h->precond == CORA_B200_PRECON_REG_CHOLESKY) {
