@@ -125,7 +125,7 @@ SYMBOLS = [
     "cora_b200_strip_layout_roundtrip", "cora_b200_effective_preconditioner", "cora_b200_last_cert_branch", "cora_b200_phase_profile_ctas", "cora_b200_gather_best_resident",
     "cora_b200_odometry_initialization", "cora_b200_save_solution", "cora_b200_debug_min_eigenpair", "cora_b200_psd_test",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
-    "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_phase_profile", "cora_b200_get_work_vector",
+    "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_debug_factor_stats", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
     "cora_b200_select_best", "cora_b200_nccl_unique_id", "cora_b200_nccl_init", "cora_b200_nccl_destroy",
 ]
@@ -264,6 +264,22 @@ def debug_chain_host(d, n, m, nt, Q, shift, pin_last=True, V=None):
                                              C.c_int(r), _p(V) if V is not None else None,
                                              _p(out) if out is not None else None, C.byref(pd)))
     return bool(pd.value), out
+
+
+def debug_factor_stats(d, n, m, nt, Q):
+    """Test hook: structure of the pose-system factorisation (chain levels or general sparse block Cholesky)."""
+    import scipy.sparse as sp
+    Q = sp.csr_matrix(Q)
+    rp = np.ascontiguousarray(Q.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(Q.indices, dtype=np.int32)
+    va = np.ascontiguousarray(Q.data, dtype=np.float64)
+    i32 = C.POINTER(C.c_int32)
+    st = np.zeros(8, dtype=np.int64)
+    _check(load().cora_b200_debug_factor_stats(C.c_int(d), C.c_int(n), C.c_int(m), C.c_int(nt), rp.ctypes.data_as(i32),
+                                               ci.ctypes.data_as(i32), _p(va), C.c_int64(Q.nnz),
+                                               st.ctypes.data_as(C.POINTER(C.c_int64))))
+    names = ("chain", "couplings", "l_blocks", "etree_height", "clusters", "levels", "max_column", "poses")
+    return dict(zip(names, (int(x) for x in st)))
 
 
 def parse_pyfg(path_or_text, from_text=False):

@@ -600,3 +600,35 @@ extern "C" int cora_b200_debug_chain_host(int d, int n_poses, int n_ranges, int 
   }
   API_END
 }
+
+// Test hook (CPU only): structure of the pose-system factorisation the handle would build for this matrix.
+// stats[0] = 1 if the pose graph is a chain (chain_chol.cuh levels), 0 if general (gen_chol.hpp);
+// general: [1] pose couplings, [2] blocks of L below the diagonal, [3] elimination-tree height, [4] clusters,
+// [5] cluster levels (= launches of one forward or backward solve), [6] largest column, [7] poses.
+extern "C" int cora_b200_debug_factor_stats(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
+                                            const int32_t *col, const double *val, int64_t nnz, int64_t *stats) {
+  API_BEGIN
+  require(rowptr && stats, "NULL argument");
+  HostLayout L;
+  build_layout(L, d, n_poses, n_ranges, n_trans, rowptr, col, val, nnz, 192);
+  for (int i = 0; i < 8; ++i) stats[i] = 0;
+  stats[7] = L.n;
+  ChainSym S;
+  try {
+    if (L.D1 == 3) chain_symbolic_build<3>(S, L, false); else chain_symbolic_build<4>(S, L, false);
+    stats[0] = 1;
+  } catch (const Error &e) {
+    if (e.code != CORA_B200_ENOTIMPL) throw;
+    ChainSym G;
+    if (L.D1 == 3) chain_symbolic_build<3>(G, L, true); else chain_symbolic_build<4>(G, L, true);
+    stats[1] = (int64_t)G.e_i.size();
+    stats[2] = G.gs.nnzL();
+    stats[3] = G.gs.etree_height;
+    stats[4] = (int64_t)G.gs.cl_ptr.size() - 1;
+    stats[5] = G.gs.levels();
+    int64_t mx = 0;
+    for (int v = 0; v < G.gs.n; ++v) mx = std::max<int64_t>(mx, G.gs.colptr[v + 1] - G.gs.colptr[v]);
+    stats[6] = mx;
+  }
+  API_END
+}

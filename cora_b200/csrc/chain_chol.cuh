@@ -15,11 +15,14 @@
 //      separators form a kChunk-times shorter chain that is treated the same way,
 //   3. the l landmark columns are a dense border closed with an l x l Schur complement.
 // Positive definiteness <=> every pivot block of this block elimination is positive definite.
-// Graphs whose pose coupling is not block tridiagonal (loop closures, several robots) are
-// rejected with CORA_B200_ENOTIMPL: SURVEY 8(f)-2 lists the general sparse Cholesky as "next".
+// Graphs whose pose coupling is not block tridiagonal (loop closures, several robots: TIERS, MR.CLAM) keep
+// steps 1 and 3 and replace step 2 by the general sparse block Cholesky of gen_chol.hpp (nested-dissection
+// order, level-scheduled solves).
 #pragma once
 #include <cmath>
+#include <map>
 
+#include "gen_chol_dev.cuh"
 #include "ops.cuh"
 
 #ifdef __CUDACC__
@@ -346,6 +349,10 @@ struct ChainFactorHost {
   std::vector<double> SLinv;                 // l x l
   int pinned_landmark = -1;                  // landmark index pinned to zero (or -1)
   int pinned_pose_row = -1;                  // pose-section row pinned to zero (or -1)
+  // pose graph with loop closures / several robots: general sparse block Cholesky (gen_chol.hpp) instead of levels
+  bool general = false;
+  GenSym gsym;
+  std::vector<double> gL, gDinv;
 };
 
 template <int B>
@@ -392,6 +399,10 @@ inline void chain_factor_levels(ChainFactorHost &F, std::vector<double> &A0, std
 // set-up time for W = T^-1 B and by the CPU test hook.  X: [n][B][ld], in place.
 template <int B>
 inline void chain_solve_host(const ChainFactorHost &F, double *X, int ld, int ncols) {
+  if (F.general) {
+    gen_solve_host<B>(F.gsym, F.gL.data(), F.gDinv.data(), X, ld, ncols);
+    return;
+  }
   const int nl = (int)F.levels.size();
   std::vector<std::vector<double>> sol(nl), rhs(nl), cL(nl), cR(nl);
   for (int lv = 0; lv < nl; ++lv) {
@@ -468,9 +479,14 @@ inline void chain_factor_host(ChainFactorHost &F, const HostLayout &L, const dou
   }
   auto not_chain = [](const char *why) {
     throw Error(CORA_B200_ENOTIMPL,
-                std::string("RegularizedCholesky / Cholesky certificate: the pose graph is not an odometry "
-                            "chain (") + why + "); only block-tridiagonal pose coupling + landmark border is "
-                            "implemented -- use Preconditioner::Jacobi");
+                std::string("RegularizedCholesky / Cholesky certificate: unsupported coupling (") + why + ")");
+  };
+  // couplings between non-adjacent poses (loop closures, other robots): block M_ij (rows of i, columns of j), i < j
+  std::map<std::pair<int32_t, int32_t>, std::vector<double>> extra;
+  auto extra_block = [&](int i, int j) -> double * {
+    auto &b = extra[{(int32_t)i, (int32_t)j}];
+    if (b.empty()) b.assign(BB, 0.0);
+    return b.data();
   };
   // ---- chain blocks from the block-ELL ----
   std::vector<double> A((size_t)std::max(n, 1) * BB, 0.0), U((size_t)std::max(n, 1) * BB, 0.0);
@@ -489,8 +505,9 @@ inline void chain_factor_host(ChainFactorHost &F, const HostLayout &L, const dou
         for (int e = 0; e < BB; ++e) U[(size_t)i * BB + e] = bv[(int64_t)e * L.TP];
       } else if (j == i - 1) {
         // lower block = transpose of U[i-1] (Q is symmetric); nothing to store
-      } else if (nz) {
-        not_chain("a pose is coupled to a non-adjacent pose");
+      } else if (nz && j > i) {  // (the transposed copy in row j is the same coupling)
+        double *eb = extra_block(i, j);
+        for (int e = 0; e < BB; ++e) eb[e] += bv[(int64_t)e * L.TP];
       }
     }
     for (int a = 0; a < B; ++a) A[(size_t)i * BB + a * B + a] += shift;
@@ -547,7 +564,7 @@ inline void chain_factor_host(ChainFactorHost &F, const HostLayout &L, const dou
       if (x == y) A[(size_t)x * BB + d * B + d] += v;
       else if (y == x + 1) U[(size_t)x * BB + d * B + d] += v;
       else if (y == x - 1) { /* transpose of the above */ }
-      else not_chain("a range factor joins two non-adjacent poses");
+      else if (y > x) extra_block(x, y)[d * B + d] += v;
     } else if (x < n && y >= n) {
       bents.push_back({(int32_t)(x * D1 + d), (int32_t)(y - n), v});
     } else if (x >= n && y >= n) {
@@ -568,7 +585,12 @@ inline void chain_factor_host(ChainFactorHost &F, const HostLayout &L, const dou
     for_group(i, [&](uint32_t pk, double v) {
       const int64_t ci = pk & kColMask;
       const int a = (int)(pk >> 30);
-      if (ci < L.nPoseRows) not_chain("pose-pose coupling outside the block-ELL");
+      if (ci < L.nPoseRows) {  // pose-pose coupling beyond the block-ELL slots
+        const int j = (int)(ci / D1), b = (int)(ci % D1);
+        if (j == i + 1) U[(size_t)i * BB + a * B + b] += v;
+        else if (j > i) extra_block(i, j)[a * B + b] += v;
+        return;
+      }
       if (ci < rg0) bents.push_back({(int32_t)(i * D1 + a), (int32_t)(ci - L.nPoseRows), v});
     });
   // landmark rows: landmark-landmark couplings
@@ -584,6 +606,9 @@ inline void chain_factor_host(ChainFactorHost &F, const HostLayout &L, const dou
     A[(size_t)i * BB + d * B + d] = 1.0;
     if (i > 0)
       for (int a = 0; a < B; ++a) U[(size_t)(i - 1) * BB + a * B + d] = 0.0;
+    for (auto &kv : extra)
+      if (kv.first.second == i)
+        for (int a = 0; a < B; ++a) kv.second[a * B + d] = 0.0;
   }
   if (F.pinned_landmark >= 0) {
     const int j = F.pinned_landmark;
@@ -609,8 +634,24 @@ inline void chain_factor_host(ChainFactorHost &F, const HostLayout &L, const dou
     q = e;
   }
   for (int j = 0; j < l; ++j) F.bl_ptr[j + 1] += F.bl_ptr[j];
-  // ---- factor the chain ----
-  chain_factor_levels<B>(F, A, U, n);
+  // ---- factor the pose system: chain levels, or the general sparse block Cholesky ----
+  F.general = !extra.empty();
+  if (F.general) {
+    std::vector<int32_t> ei, ej;
+    std::vector<double> E;
+    for (int i = 0; i + 1 < n; ++i) {
+      ei.push_back(i); ej.push_back(i + 1);
+      E.insert(E.end(), U.begin() + (size_t)i * BB, U.begin() + (size_t)(i + 1) * BB);
+    }
+    for (auto &kv : extra) {
+      ei.push_back(kv.first.first); ej.push_back(kv.first.second);
+      E.insert(E.end(), kv.second.begin(), kv.second.end());
+    }
+    gen_symbolic(F.gsym, n, ei, ej);
+    F.pos_def = gen_numeric<B>(F.gsym, A.data(), E.data(), F.gL, F.gDinv) && F.pos_def;
+  } else {
+    chain_factor_levels<B>(F, A, U, n);
+  }
   // ---- landmark Schur complement S_L = C - B^T T^-1 B ----
   if (l > 0) {
     std::vector<double> W((size_t)std::max(n, 1) * B * l, 0.0);
@@ -725,6 +766,10 @@ struct ChainChol {
   DevBuf<double> rdinv, rinc_e, rend_e, bl_val, W, SLinv, u, zL, Y;
   DevBuf<int> rinc_ptr, rinc_k, rend_x, bl_ptr, bl_row;
   int ws_cols = 0;
+  // pose graph with loop closures / several robots: general sparse block factor (gen_chol_dev.cuh) instead of levels
+  bool general = false;
+  GenFactorDev gen;
+  const GenSymDev *gsd = nullptr;  // owned by the handle's ChainSym
   ~ChainChol() {
     for (auto *p : levels) delete p;
   }
@@ -925,7 +970,10 @@ inline void chain_solve(H *h, ChainChol *C, const double *V, double *Z, int r, c
   const int nl = (int)C->levels.size();
   auto solp = [&](int lv) { return lv == 0 ? Y : C->levels[lv]->sol.p; };
   auto rhsp = [&](int lv) { return lv == 0 ? Y : C->levels[lv]->rhs.p; };
-  if (n > 0) {
+  if (n > 0 && C->general) {
+    if (C->B == 3) gen_solve_device<3>(h, *C->gsd, C->gen, n, Y, r, r, ctrl);
+    else gen_solve_device<4>(h, *C->gsd, C->gen, n, Y, r, r, ctrl);
+  } else if (n > 0) {
     for (int lv = 0; lv < nl; ++lv) {
       ChainLevelDev *D = C->levels[lv];
       const int threads = D->G.K * r;

@@ -53,21 +53,51 @@ struct ChainSym {
   // range incidence by translation for the solve, with the pinned translation left out: [0] no pin, [1] pinned
   std::vector<int32_t> rinc_ptr[2], rinc_k[2];
   std::vector<double> rinc_e[2];
-  ~ChainSym() { for (auto *p : lv) delete p; }
+  // ---- pose graph that is not a chain (loop closures, several robots): general sparse block Cholesky ----
+  bool general = false;
+  std::vector<int32_t> e_i, e_j;           // pose-pose couplings, i < j
+  std::vector<long long> e_off;            // offset of block (i, j) in the block values (-1: only in the spill)
+  std::vector<double> e_stat;              // static part of the block: spill entries of pose i (blocks beyond the ELL slots)
+  std::vector<int32_t> ec_ptr, ec_k;       // per coupling: ranges joining t_i and t_j
+  std::vector<double> ec_coef;
+  GenSym gs;
+  GenSymDev gsd;
+  DevBuf<int> d_e_j, d_ec_ptr, d_ec_k;
+  DevBuf<long long> d_e_off;
+  DevBuf<double> d_e_stat, d_ec_coef, d_A, d_E;
+  double *h_AE = nullptr;                  // pinned staging of the assembled pose blocks (A then E)
+  std::vector<double> h_L, h_Dinv;
+  ~ChainSym() {
+    for (auto *p : lv) delete p;
+    if (h_AE) cudaFreeHost(h_AE);
+  }
 };
 
 // ---------------------------------------------------------------- symbolic ----
+// general == false: the chain structure (throws ENOTIMPL as soon as a pose couples to a non-adjacent pose);
+// general == true: every pose-pose coupling becomes an edge of the pose graph for gen_chol.hpp.
 template <int B>
-inline void chain_symbolic_build(ChainSym &S, const HostLayout &L) {
+inline void chain_symbolic_build(ChainSym &S, const HostLayout &L, bool general) {
   constexpr int BB = B * B;
   const int n = L.n, l = L.l, m = L.m, D1 = L.D1, d = L.d;
   S.B = B; S.n = n; S.l = l; S.m = m;
+  S.general = general;
   auto not_chain = [](const char *why) {
     throw Error(CORA_B200_ENOTIMPL,
-                std::string("RegularizedCholesky / Cholesky certificate: the pose graph is not an odometry "
-                            "chain (") + why + "); only block-tridiagonal pose coupling + landmark border is "
-                            "implemented -- use Preconditioner::Jacobi");
+                std::string("RegularizedCholesky / Cholesky certificate: unsupported coupling (") + why + ")");
   };
+  std::map<std::pair<int32_t, int32_t>, int32_t> emap;
+  auto edge_id = [&](int i, int j) -> int32_t {
+    auto it = emap.find({(int32_t)i, (int32_t)j});
+    if (it != emap.end()) return it->second;
+    const int32_t id = (int32_t)S.e_i.size();
+    emap[{(int32_t)i, (int32_t)j}] = id;
+    S.e_i.push_back(i); S.e_j.push_back(j); S.e_off.push_back(-1);
+    S.e_stat.insert(S.e_stat.end(), BB, 0.0);
+    return id;
+  };
+  struct ECoup { int32_t id, k; double coef; };
+  std::vector<ECoup> ecoup;
   S.Aoff.assign((size_t)std::max(n, 1), -1); S.Uoff.assign((size_t)std::max(n, 1), -1);
   for (int i = 0; i < n; ++i) {
     const int t = i / L.TP, p = i % L.TP;
@@ -79,6 +109,7 @@ inline void chain_symbolic_build(ChainSym &S, const HostLayout &L) {
       for (int e = 0; e < BB; ++e) nz = nz || L.bval[off + (long long)e * L.TP] != 0.0;
       if (s > 0 && j == i) continue;  // padding slot
       if (j == i) S.Aoff[i] = off;
+      else if (general) { if (j > i && nz) S.e_off[edge_id(i, j)] = off; }  // (row j holds the transposed copy)
       else if (j == i + 1) S.Uoff[i] = off;
       else if (j == i - 1) { }
       else if (nz) not_chain("a pose is coupled to a non-adjacent pose");
@@ -141,7 +172,8 @@ inline void chain_symbolic_build(ChainSym &S, const HostLayout &L) {
     const double coef = S.rend_e[(size_t)k * 2] * S.rend_e[(size_t)k * 2 + 1];
     const int a = std::min(x0, x1), b = std::max(x0, x1);
     if (b < n) {
-      if (b == a + 1) uc[a].push_back({k, coef});
+      if (general) ecoup.push_back({edge_id(a, b), (int32_t)k, coef});
+      else if (b == a + 1) uc[a].push_back({k, coef});
       else not_chain("a range factor joins two non-adjacent poses");
     } else if (a < n) {
       bents.push_back({(int32_t)(a * D1 + d), (int32_t)(b - n), k, coef});
@@ -159,9 +191,24 @@ inline void chain_symbolic_build(ChainSym &S, const HostLayout &L) {
     for_group(i, [&](uint32_t pk, double v) {
       const int64_t ci = pk & kColMask;
       const int a = (int)(pk >> 30);
-      if (ci < L.nPoseRows) not_chain("pose-pose coupling outside the block-ELL");
+      if (ci < L.nPoseRows) {
+        if (!general) not_chain("pose-pose coupling outside the block-ELL");
+        const int j = (int)(ci / D1), b = (int)(ci % D1);
+        if (j > i) S.e_stat[(size_t)edge_id(i, j) * BB + a * B + b] += v;
+        return;
+      }
       if (ci < rg0) bents.push_back({(int32_t)(i * D1 + a), (int32_t)(ci - L.nPoseRows), -1, v});
     });
+  if (general) {
+    const int ne = (int)S.e_i.size();
+    S.ec_ptr.assign((size_t)ne + 1, 0);
+    for (auto &c : ecoup) ++S.ec_ptr[c.id + 1];
+    for (int e = 0; e < ne; ++e) S.ec_ptr[e + 1] += S.ec_ptr[e];
+    S.ec_k.assign(ecoup.size(), 0); S.ec_coef.assign(ecoup.size(), 0.0);
+    std::vector<int32_t> fill(S.ec_ptr.begin(), S.ec_ptr.end() - 1);
+    for (auto &c : ecoup) { S.ec_k[fill[c.id]] = c.k; S.ec_coef[fill[c.id]] = c.coef; ++fill[c.id]; }
+    gen_symbolic(S.gs, n, S.e_i, S.e_j);
+  }
   for (int j = 0; j < l; ++j)
     for_group((int64_t)n + j, [&](uint32_t pk, double v) {
       const int64_t ci = pk & kColMask;
@@ -246,6 +293,46 @@ __global__ void __launch_bounds__(kThreads) k_cf_pose_blocks(int n, int TP, cons
       for (int q = 0; q < B; ++q) u[q * B + d] = 0.0;
   }
   for (int e = 0; e < BB; ++e) { A[(size_t)i * BB + e] = a[e]; U[(size_t)i * BB + e] = u[e]; }
+}
+
+// general pose graph: thread t < n assembles the diagonal block of pose t, thread n + e the coupling block of edge e
+// (M_ij, rows of pose i, columns of pose j, i < j) = block-ELL slot + spill part - Schur terms of the ranges
+template <int B>
+__global__ void __launch_bounds__(kThreads) k_gen_pose_blocks(int n, int ne, int TP, const double *__restrict__ bval,
+                                                              const long long *__restrict__ Aoff, double shift,
+                                                              const int *__restrict__ tinc_ptr, const int *__restrict__ tinc_k,
+                                                              const double *__restrict__ tinc_e,
+                                                              const double *__restrict__ rdinv, int pinned_pose_row,
+                                                              const int *__restrict__ e_j, const long long *__restrict__ e_off,
+                                                              const double *__restrict__ e_stat,
+                                                              const int *__restrict__ ec_ptr, const int *__restrict__ ec_k,
+                                                              const double *__restrict__ ec_coef, double *A, double *E) {
+  constexpr int BB = B * B, d = B - 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    const int i = t;
+    double a[BB];
+    for (int e = 0; e < BB; ++e) a[e] = Aoff[i] >= 0 ? bval[Aoff[i] + (long long)e * TP] : 0.0;
+    for (int q = 0; q < B; ++q) a[q * B + q] += shift;
+    double s = 0.0;
+    for (int q = tinc_ptr[i]; q < tinc_ptr[i + 1]; ++q) s += tinc_e[q] * tinc_e[q] * rdinv[tinc_k[q]];
+    a[d * B + d] -= s;
+    if (pinned_pose_row >= 0 && i == n - 1) {
+      for (int q = 0; q < B; ++q) { a[d * B + q] = 0.0; a[q * B + d] = 0.0; }
+      a[d * B + d] = 1.0;
+    }
+    for (int e = 0; e < BB; ++e) A[(size_t)i * BB + e] = a[e];
+  } else if (t - n < ne) {
+    const int e = t - n;
+    double u[BB];
+    for (int q = 0; q < BB; ++q) u[q] = (e_off[e] >= 0 ? bval[e_off[e] + (long long)q * TP] : 0.0) + e_stat[(size_t)e * BB + q];
+    double su = 0.0;
+    for (int q = ec_ptr[e]; q < ec_ptr[e + 1]; ++q) su += ec_coef[q] * rdinv[ec_k[q]];
+    u[d * B + d] -= su;
+    if (pinned_pose_row >= 0 && e_j[e] == n - 1)
+      for (int q = 0; q < B; ++q) u[q * B + d] = 0.0;
+    for (int q = 0; q < BB; ++q) E[(size_t)e * BB + q] = u[q];
+  }
 }
 
 static __global__ void __launch_bounds__(kThreads) k_cf_border(int nb, const int *__restrict__ bl_ptr, int l,
@@ -365,8 +452,16 @@ inline void chain_symbolic_upload(H *h, ChainSym &S) {
   upload_as(S.d_cc_coef, S.cc_coef, s);
   upload_as(S.d_Cstat, S.Cstat, s); upload_as(S.d_Aoff, S.Aoff, s); upload_as(S.d_Uoff, S.Uoff, s);
   const int BB = S.B * S.B;
-  int cur = S.n;
-  while (true) {
+  if (S.general) {
+    const size_t ne = S.e_i.size();
+    upload_as(S.d_e_j, S.e_j, s); upload_as(S.d_e_off, S.e_off, s); upload_as(S.d_e_stat, S.e_stat, s);
+    upload_as(S.d_ec_ptr, S.ec_ptr, s); upload_as(S.d_ec_k, S.ec_k, s); upload_as(S.d_ec_coef, S.ec_coef, s);
+    S.d_A.alloc((size_t)std::max(S.n, 1) * BB); S.d_E.alloc(std::max<size_t>(ne, 1) * BB);
+    CUDA_CHECK(cudaMallocHost((void **)&S.h_AE, ((size_t)std::max(S.n, 1) + std::max<size_t>(ne, 1)) * BB * sizeof(double)));
+    gen_sym_upload(h, S.gs, S.gsd);
+  }
+  int cur = S.general ? 0 : S.n;
+  while (!S.general) {
     ChainSymLevel *Lv = new ChainSymLevel();
     Lv->G = make_geo(cur);
     Lv->A.alloc((size_t)std::max(cur, 1) * BB); Lv->U.alloc((size_t)std::max(cur, 1) * BB);
@@ -406,7 +501,15 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
     k_cf_ranges<<<(m + kThreads - 1) / kThreads, kThreads, 0, s>>>(m, l, d_sdiag, shift, C->rdinv.p, S.d_flag.p);
     check_launch(h);
   }
-  if (n > 0) {
+  C->general = S.general;
+  C->gsd = &S.gsd;
+  if (n > 0 && S.general) {
+    const int ne = (int)S.e_i.size();
+    k_gen_pose_blocks<B><<<(n + ne + kThreads - 1) / kThreads, kThreads, 0, s>>>(
+        n, ne, h->HL.TP, d_bval, S.d_Aoff.p, shift, S.d_tinc_ptr.p, S.d_tinc_k.p, S.d_tinc_e.p, C->rdinv.p,
+        F.pinned_pose_row, S.d_e_j.p, S.d_e_off.p, S.d_e_stat.p, S.d_ec_ptr.p, S.d_ec_k.p, S.d_ec_coef.p, S.d_A.p, S.d_E.p);
+    check_launch(h);
+  } else if (n > 0) {
     k_cf_pose_blocks<B><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
         n, h->HL.TP, d_bval, S.d_Aoff.p, S.d_Uoff.p, shift, S.d_tinc_ptr.p, S.d_tinc_k.p, S.d_tinc_e.p, S.d_uc_ptr.p,
         S.d_uc_k.p, S.d_uc_coef.p, C->rdinv.p, F.pinned_pose_row, S.lv[0]->A.p, S.lv[0]->U.p);
@@ -425,6 +528,20 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
                                          C->rdinv.p, (int)S.cc_j.size(), S.d_cc_j.p, S.d_cc_j2.p, S.d_cc_k.p, S.d_cc_coef.p,
                                          F.pinned_landmark, S.d_C.p);
     check_launch(h);
+  }
+  // general pose graph: the assembled blocks go to the host, the left-looking block Cholesky of gen_chol.hpp runs
+  // there on the structure built once per handle, and the factor comes back (a few MB at TIERS / MR.CLAM sizes)
+  bool gen_pd = true;
+  if (S.general && n > 0) {
+    const size_t ne = S.e_i.size();
+    CUDA_CHECK(cudaMemcpyAsync(S.h_AE, S.d_A.p, (size_t)n * BB * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (ne) CUDA_CHECK(cudaMemcpyAsync(S.h_AE + (size_t)n * BB, S.d_E.p, ne * BB * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    gen_pd = gen_numeric<B>(S.gs, S.h_AE, S.h_AE + (size_t)n * BB, S.h_L, S.h_Dinv);
+    C->gen.Lval.reserve(std::max<size_t>(S.h_L.size(), 1)); C->gen.Dinv.reserve(S.h_Dinv.size());
+    if (!S.h_L.empty()) CUDA_CHECK(cudaMemcpyAsync(C->gen.Lval.p, S.h_L.data(), S.h_L.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(C->gen.Dinv.p, S.h_Dinv.data(), S.h_Dinv.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
   }
   // levels
   F.levels.clear();
@@ -466,7 +583,9 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
                                                                              C->W.p);
       check_launch(h);
     }
-    if (n > 0) {  // W <- T^-1 W with the solve kernels (l columns, leading dimension l)
+    if (n > 0 && S.general) {
+      gen_solve_device<B>(h, S.gsd, C->gen, n, C->W.p, l, l, nullptr);
+    } else if (n > 0) {  // W <- T^-1 W with the solve kernels (l columns, leading dimension l)
       const int nl = (int)C->levels.size();
       std::vector<DevBuf<double>> &sol = S.wsol, &rhs = S.wrhs, &cL = S.wcL, &cR = S.wcR;  // kept across factorisations
       if ((int)sol.size() != nl) { sol = std::vector<DevBuf<double>>(nl); rhs = std::vector<DevBuf<double>>(nl);
@@ -506,7 +625,7 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
   std::vector<double> SLm((size_t)std::max(l, 1) * std::max(l, 1), 0.0);
   if (l > 0) CUDA_CHECK(cudaMemcpyAsync(SLm.data(), S.d_SL.p, (size_t)l * l * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
-  F.pos_def = flag != 0;
+  F.pos_def = flag != 0 && gen_pd;
   if (l > 0) {
     for (int a = 0; a < l; ++a)
       for (int b = a + 1; b < l; ++b) {
@@ -536,8 +655,19 @@ inline ChainSym &chain_symbolic(H *h) {
   if (h->chain_sym_state == 0) {
     ChainSym *S = new ChainSym();
     try {
-      if (h->HL.D1 == 3) chain_symbolic_build<3>(*S, h->HL);
-      else chain_symbolic_build<4>(*S, h->HL);
+      try {
+        if (h->HL.D1 == 3) chain_symbolic_build<3>(*S, h->HL, false);
+        else chain_symbolic_build<4>(*S, h->HL, false);
+      } catch (const Error &e) {
+        if (e.code != CORA_B200_ENOTIMPL) throw;
+        // not a chain (loop closures, several robots): the general sparse block Cholesky
+        // (CORA_B200_GENERAL_CHOLESKY=0 keeps the "no factorisation" behaviour reachable for its tests)
+        if (const char *g = getenv("CORA_B200_GENERAL_CHOLESKY")) if (atoi(g) == 0) throw;
+        delete S;
+        S = new ChainSym();
+        if (h->HL.D1 == 3) chain_symbolic_build<3>(*S, h->HL, true);
+        else chain_symbolic_build<4>(*S, h->HL, true);
+      }
     } catch (const Error &e) {
       delete S;
       if (e.code == CORA_B200_ENOTIMPL) { h->chain_sym_state = 2; h->chain_sym_error = e.what(); }

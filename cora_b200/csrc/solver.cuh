@@ -57,9 +57,10 @@ inline void update_preconditioner(H *h) {
       h->chol = build_chain_chol(h, h->d_bval.p, h->d_sdiag.p, h->lambda_reg, /*pin_last=*/true, &pd);
     } catch (const Error &e) {
       if (e.code != CORA_B200_ENOTIMPL) throw;
-      // Not an [odometry chain + landmark border] graph (loop closures, several robots): there is no device
-      // factorisation for it yet.  RegularizedCholesky is the reference's DEFAULT, so a drop-in caller must still
-      // get a working handle: apply Jacobi instead and report it (cora_b200_effective_preconditioner).
+      // A coupling neither the chain nor the general pose-graph factorisation covers (a range row tied to a
+      // rotation variable: not produced by any CORA measurement type).  RegularizedCholesky is the reference's
+      // DEFAULT, so a drop-in caller must still get a working handle: apply Jacobi instead and report it
+      // (cora_b200_effective_preconditioner).
       h->precond = CORA_B200_PRECON_JACOBI;
       return;
     }
@@ -550,7 +551,10 @@ inline void tnt_resident(H *h, int r, const cora_b200_tnt_params &p, cora_b200_t
   if (h->precond != CORA_B200_PRECON_JACOBI && h->precond != CORA_B200_PRECON_REG_CHOLESKY)
     throw Error(CORA_B200_EINVAL, "The desired preconditioner is not implemented");
   ensure_workspace(h, r);
-  if (h->use_persistent && (h->precond == CORA_B200_PRECON_JACOBI || h->precond == CORA_B200_PRECON_REG_CHOLESKY)) {
+  // the persistent kernel applies Jacobi or the CHAIN factor in its own phases; the general sparse factor of graphs
+  // with loop closures / several robots (gen_chol_dev.cuh) is applied by level-scheduled launches on the multi-launch path
+  const bool general_factor = h->precond == CORA_B200_PRECON_REG_CHOLESKY && h->chol && h->chol->general;
+  if (h->use_persistent && !general_factor) {
     tnt_persistent(h, r, p, res);
     return;
   }

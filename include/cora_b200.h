@@ -375,6 +375,13 @@ int cora_b200_debug_chain_host(int d, int n_poses, int n_ranges, int n_trans, co
                                const int32_t *col, const double *val, int64_t nnz, double shift,
                                int pin_last, int r, const double *V, double *out, int *pos_def);
 
+/* Test hook (CPU only): which factorisation the pose system of this matrix gets and its size.
+ * stats[0] = 1: odometry chain (levels of chunks); 0: general sparse block Cholesky (loop closures, several
+ * robots), then [1] pose couplings, [2] off-diagonal blocks of L, [3] elimination-tree height, [4] clusters,
+ * [5] cluster levels (launches per triangular solve), [6] largest column, [7] poses. */
+int cora_b200_debug_factor_stats(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
+                                 const int32_t *col, const double *val, int64_t nnz, int64_t *stats /* 8 */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ Outputs (committed, small):
       /root/reference/tests/data/{small_ra_slam_problem,single_rpm,single_range}
       (factor_graph.pyfg text + the 16 MatrixMarket goldens, densified) and the
       expected costs of tests/test_utils.cpp:213-217;
-  tests/golden/{plaza2,single_drone}.npz  measurement arrays of the two real
+  tests/golden/{plaza2,single_drone,tiers,mrclam2}.npz  measurement arrays of the two real
       datasets BASELINE.json names (examples/data/*.pyfg) flattened with the
       oracle's parser, so the GPU box (which has no /root/reference) can rebuild
       the exact same data matrix.
@@ -48,8 +48,14 @@ def main():
             out[k] = dense(os.path.join(src, k + ".mm"))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, {k: v.shape for k, v in out.items() if k not in ("pyfg",)})
-    for name in ("plaza2", "single_drone"):
-        p = co.parse_pyfg(os.path.join(REF, "examples", "data", name + ".pyfg"))
+    # tiers / mrclam2: several robots + inter-robot measurements (general sparse Cholesky)
+    files = {"plaza2": "plaza2.pyfg", "single_drone": "single_drone.pyfg", "tiers": "tiers.pyfg",
+             "mrclam2": os.path.join("mrclam", "range_and_rpm", "mrclam2", "mrclam2.pyfg")}
+    only = sys.argv[1:]
+    for name, rel in files.items():
+        if only and name not in only:
+            continue
+        p = co.parse_pyfg(os.path.join(REF, "examples", "data", rel))
         a = p.measurement_arrays()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), d=p.d, n=p.n, l=p.l, **a)
         print(name, p.d, p.n, p.l, p.m, len(a["rp_tau"]))

@@ -56,11 +56,3 @@ def test_psd_verdict_matches_dense_eigenvalues(lib):
     assert pd
     pd, _ = capi.debug_chain_host(p.d, p.n, p.m, p.n + p.l, p.Q, -1e-3, False)
     assert not pd
-
-
-def test_loop_closures_are_rejected(lib):
-    from cora_b200 import capi
-    p = make_synthetic(n=60, l=3, m=40, d=3, seed=5, loop_closures=[(0, 30)])
-    p.update_problem_data()
-    with pytest.raises(capi.NotImplementedInReference):
-        capi.debug_chain_host(p.d, p.n, p.m, p.n + p.l, p.Q, 1.0, True)

@@ -143,11 +143,12 @@ def test_staircase_datasets_known_answers(lib, name, r0, f_lift, f_ref):
     assert out["final_rank"] == p.d
 
 
-def test_staircase_without_factorisation_never_certifies_spuriously(lib):
-    """Loop-closure graph: there is no device factorisation of S + eta I, so positive semidefiniteness is never
-    proven.  The staircase may lift the rank only along a verified direction of negative curvature
+def test_staircase_without_factorisation_never_certifies_spuriously(lib, monkeypatch):
+    """Loop-closure graph with the general sparse Cholesky switched off: there is no factorisation of S + eta I,
+    so positive semidefiniteness is never proven.  The staircase may lift the rank only along a verified direction of negative curvature
     (x' S x < -eta/2), must stop at an inconclusive verdict, and must not report a PSD certificate."""
     from cora_b200 import capi
+    monkeypatch.setenv("CORA_B200_GENERAL_CHOLESKY", "0")
     p = make_synthetic(n=80, l=3, m=50, d=3, seed=3, loop_closures=[(0, 40), (10, 70)])
     p.update_problem_data()
     x0 = np.random.default_rng(1).uniform(-1, 1, size=(p.N, 4))

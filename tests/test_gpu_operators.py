@@ -176,10 +176,12 @@ def test_regularized_cholesky_preconditioner(lib):
             assert np.all(Z[-1] == 0.0)  # CORA_preconditioners.cpp:77-80
 
 
-def test_regularized_cholesky_falls_back_to_jacobi_on_loop_closures(lib):
+def test_regularized_cholesky_falls_back_to_jacobi_without_factorisation(lib, monkeypatch):
     """RegularizedCholesky is the reference's default (src/pyfg_text_parser.cpp:116-120): on a graph without a device
-    factorisation (a loop closure) the handle must still be created; it applies Jacobi and says so."""
+    factorisation (here: a loop closure with the general sparse Cholesky switched off) the handle must still be
+    created; it applies Jacobi and says so."""
     from cora_b200 import capi
+    monkeypatch.setenv("CORA_B200_GENERAL_CHOLESKY", "0")
     p = make_synthetic(n=60, l=3, m=40, d=3, seed=5, loop_closures=[(0, 30)])
     p.update_problem_data()
     V = np.asfortranarray(np.random.default_rng(0).standard_normal((p.N, 4)))
