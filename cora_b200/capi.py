@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CORA_B200_LIB") or os.path.join(_HERE, "lib", "libcora_b200.so")  # (override: development builds)
 
 PRECON_NONE, PRECON_JACOBI, PRECON_BLOCK_CHOLESKY, PRECON_REG_CHOLESKY = 0, 1, 2, 3
+FORMULATION_EXPLICIT, FORMULATION_IMPLICIT = 0, 1  # include/CORA/CORA_types.h:52-56
 TNT_STATUS = ["Gradient", "PreconditionedGradient", "RelativeDecrease", "Stepsize", "TrustRegion",
               "IterationLimit", "ElapsedTime", "UserFunction"]
 EINVAL, ERUNTIME, ECUDA, ENOTIMPL = 1, 2, 3, 4
@@ -125,7 +126,8 @@ SYMBOLS = [
     "cora_b200_strip_layout_roundtrip", "cora_b200_effective_preconditioner", "cora_b200_last_cert_branch", "cora_b200_phase_profile_ctas", "cora_b200_gather_best_resident",
     "cora_b200_odometry_initialization", "cora_b200_save_solution", "cora_b200_debug_min_eigenpair", "cora_b200_psd_test",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
-    "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_debug_factor_stats", "cora_b200_phase_profile", "cora_b200_get_work_vector",
+    "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_debug_factor_stats",
+    "cora_b200_set_formulation", "cora_b200_variable_rows", "cora_b200_translation_explicit_solution", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
     "cora_b200_select_best", "cora_b200_nccl_unique_id", "cora_b200_nccl_init", "cora_b200_nccl_destroy",
 ]
@@ -368,6 +370,7 @@ class Handle:
         if Q.shape != (N, N):
             raise InvalidArgument(EINVAL, "data matrix has shape %s, expected (%d, %d)" % (Q.shape, N, N))
         self.d, self.n, self.m, self.nt, self.N = int(d), int(n_poses), int(n_ranges), int(n_trans), int(N)
+        self.rows = self.N  # getExpectedVariableSize(): d n + m after set_formulation(FORMULATION_IMPLICIT)
         self.nnz = int(Q.nnz)
         rp = np.ascontiguousarray(Q.indptr, dtype=np.int32)
         ci = np.ascontiguousarray(Q.indices, dtype=np.int32)
@@ -415,6 +418,20 @@ class Handle:
         _check(self._lib.cora_b200_set_preconditioner(self._h, C.c_int(preconditioner),
                                                       C.c_double(reg_chol_max_cond)))
 
+    def set_formulation(self, formulation):
+        """Problem::setFormulation: FORMULATION_EXPLICIT / FORMULATION_IMPLICIT (translations marginalised)."""
+        _check(self._lib.cora_b200_set_formulation(self._h, C.c_int(formulation)))
+        v = C.c_int64(0)
+        _check(self._lib.cora_b200_variable_rows(self._h, C.byref(v)))
+        self.rows = int(v.value)
+
+    def translation_explicit_solution(self, Y):
+        """Problem::getTranslationExplicitSolution: (d n + m) x r -> N x r."""
+        Y = self._mat(Y)
+        out = np.empty((self.N, Y.shape[1]), order="F")
+        _check(self._lib.cora_b200_translation_explicit_solution(self._h, Y.shape[1], _p(Y), _p(out)))
+        return out
+
     @property
     def reg_lambda(self):
         v = C.c_double()
@@ -426,11 +443,12 @@ class Handle:
         _check(self._lib.cora_b200_set_reg_lambda(self._h, C.c_double(lam)))
 
     # -- tier 1 ---------------------------------------------------------------
-    def _mat(self, A, r=None):
+    def _mat(self, A, r=None, rows=None):
         A = _f64(A)
-        if A.shape[0] != self.N or (r is not None and A.shape[1] != r):
+        rows = self.rows if rows is None else rows
+        if A.shape[0] != rows or (r is not None and A.shape[1] != r):
             raise InvalidArgument(EINVAL, "expected matrix of shape (%d, %s) but got (%d, %d)"
-                                  % (self.N, r if r is not None else "r", A.shape[0], A.shape[1]))
+                                  % (rows, r if r is not None else "r", A.shape[0], A.shape[1]))
         return A
 
     def data_matrix_product(self, Y):
@@ -502,7 +520,7 @@ class Handle:
 
     def certificate_product(self, Y, x):
         Y = self._mat(Y)
-        x = self._mat(x)
+        x = self._mat(x, rows=self.N)  # S is the translation-explicit certificate matrix in either formulation
         out = np.empty_like(x, order="F")
         _check(self._lib.cora_b200_certificate_product(self._h, Y.shape[1], _p(Y), x.shape[1], _p(x), _p(out)))
         return out
@@ -552,7 +570,7 @@ class Handle:
         _check(self._lib.cora_b200_set_iterate(self._h, C.c_int(r), C.cast(host_ptr, _PD)))
 
     def get_iterate(self, r):
-        out = np.empty((self.N, r), order="F")
+        out = np.empty((self.rows, r), order="F")
         _check(self._lib.cora_b200_get_iterate(self._h, r, _p(out)))
         return out
 
@@ -602,7 +620,7 @@ class Handle:
         return {name: (float(mx[i]), float(md[i])) for i, name in enumerate(self.PHASES) if mx[i] > 0}
 
     def get_work_vector(self, which, r):
-        out = np.empty((self.N, r), order="F")
+        out = np.empty((self.rows, r), order="F")
         _check(self._lib.cora_b200_get_work_vector(self._h, C.c_int(which), C.c_int(r), _p(out)))
         return out
 
@@ -616,8 +634,8 @@ class Handle:
         r = Y.shape[1]
         B = _f64(bootstrap) if bootstrap is not None and np.size(bootstrap) else None
         cap = max(nx, r + 2)
-        ev = np.zeros((self.N, cap), order="F")
-        x = np.zeros(self.N)
+        ev = np.zeros((self.rows, cap), order="F")
+        x = np.zeros(self.rows)
         cert, ncols = C.c_int(), C.c_int()
         theta, iters = C.c_double(), C.c_int64()
         _check(self._lib.cora_b200_certify(self._h, r, _p(Y), C.c_double(eta), C.c_int(nx),
@@ -630,9 +648,9 @@ class Handle:
     def saddle_escape(self, Y, theta, v, gradient_tolerance=1e-4, preconditioned_gradient_tolerance=1e-4):
         Y = self._mat(Y)
         v = np.ascontiguousarray(v, dtype=np.float64).ravel()
-        if v.shape[0] != self.N:
+        if v.shape[0] != self.rows:
             raise InvalidArgument(EINVAL, "v must have N entries")
-        out = np.empty((self.N, Y.shape[1] + 1), order="F")
+        out = np.empty((self.rows, Y.shape[1] + 1), order="F")
         _check(self._lib.cora_b200_saddle_escape(self._h, Y.shape[1] + 1, _p(Y), C.c_double(theta), _p(v),
                                                  C.c_double(gradient_tolerance),
                                                  C.c_double(preconditioned_gradient_tolerance), _p(out)))
@@ -640,7 +658,7 @@ class Handle:
 
     def project_solution(self, Y):
         Y = self._mat(Y)
-        out = np.empty((self.N, self.d), order="F")
+        out = np.empty((self.rows, self.d), order="F")
         _check(self._lib.cora_b200_project_solution(self._h, Y.shape[1], _p(Y), _p(out)))
         return out
 
@@ -685,7 +703,7 @@ class Handle:
         res = SolveResultC()
         res.stage_capacity = cap
         res.stages = C.cast(stages, C.POINTER(StageC))
-        out = np.empty((self.N, self.d), order="F")
+        out = np.empty((self.rows, self.d), order="F")
         _check(self._lib.cora_b200_solve(self._h, X0.shape[1], _p(X0), C.c_int(max_rank), C.byref(params),
                                          C.c_int(int(verbose)), _p(out), C.byref(res)))
         st = []

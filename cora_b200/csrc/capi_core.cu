@@ -8,6 +8,7 @@
 #include "chain_factor_dev.cuh"
 #include "ops.cuh"
 #include "solver.cuh"
+#include "implicit.cuh"
 #include "lanczos.cuh"
 
 namespace cora_b200 {
@@ -202,6 +203,7 @@ extern "C" int cora_b200_destroy(cora_b200_t *h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   destroy_chain_chol(h->chol);
   destroy_chain_chol(h->chol_spare);
+  destroy_chain_chol(h->ltrans);
   destroy_chain_sym(h->chain_sym);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -220,6 +222,35 @@ extern "C" int cora_b200_size(const cora_b200_t *h, int64_t *N) {
   API_BEGIN
   require(h && N, "NULL argument");
   *N = h->HL.N;
+  API_END
+}
+
+extern "C" int cora_b200_set_formulation(cora_b200_t *h, int formulation) {
+  API_BEGIN
+  require(h != nullptr, "NULL handle");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  set_formulation(h, formulation);
+  API_END
+}
+
+extern "C" int cora_b200_variable_rows(const cora_b200_t *h, int64_t *rows) {
+  API_BEGIN
+  require(h && rows, "NULL argument");
+  *rows = h->io_rows();
+  API_END
+}
+
+// Problem::getTranslationExplicitSolution (src/CORA_problem.cpp:1168-1197): Y ((d n + m) x r) -> [Y; t*] (N x r)
+extern "C" int cora_b200_translation_explicit_solution(cora_b200_t *h, int r, const double *Y, double *Xfull) {
+  API_BEGIN
+  require(h && Y && Xfull, "NULL argument");
+  require(h->formulation == CORA_B200_FORMULATION_IMPLICIT, "the problem is not in the implicit formulation");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  ensure_workspace(h, r);
+  h->resident_r = 0;
+  import_matrix(h, Y, r, h->ws[V_X].p, r);
+  const double *F = implicit_complete(h, h->ws[V_X].p, r, nullptr);
+  export_matrix(h, F, r, Xfull, h->HL.N);
   API_END
 }
 
@@ -406,9 +437,10 @@ extern "C" int cora_b200_certificate_product(cora_b200_t *h, int r, const double
   import_matrix(h, Y, r, T.v(V_X), r);
   compute_lambda(h, T.v(V_X), r);
   DevLayout LS = build_certificate_layout(h, 0.0);
-  import_matrix(h, x, k, T.v(V_T0), k);
+  // the certificate matrix is the translation-explicit one in either formulation (src/CORA_problem.cpp:1055-1059)
+  import_matrix(h, x, k, T.v(V_T0), k, h->HL.N);
   launch_qprod(h, QM_SPMM, T.v(V_T0), nullptr, nullptr, T.v(V_T1), nullptr, k, POST_STORE, SC_TMP, nullptr, &LS);
-  export_matrix(h, T.v(V_T1), k, out);
+  export_matrix(h, T.v(V_T1), k, out, h->HL.N);
   API_END
 }
 

@@ -461,6 +461,22 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
     out.branch = accept(L.theta_S) ? CORA_B200_CERT_EIGENPAIR : CORA_B200_CERT_INCONCLUSIVE;
     if (verbose) std::printf("  certify: plain Lanczos steps=%d theta=%.6e\n", L.steps, L.theta_S);
   }
+  if (h->formulation == CORA_B200_FORMULATION_IMPLICIT && out.have_x && !out.certified) {
+    // src/CORA_problem.cpp:1085-1100: keep the rotation / range part of the direction, normalised, and report its
+    // Rayleigh quotient with the simplified certificate matrix  x' (Q_implicit x - Lambda x)
+    zero_translation_rows(h, x, 1, nullptr);
+    launch_dot2(h, x, x, x, x, N, SC_TMP);
+    read_scal(h);
+    const double nrm = std::sqrt(h->h_scal[SC_TMP]);
+    if (!(nrm > 0.0)) throw Error(CORA_B200_ERUNTIME, "NaN in theta -- result not certified and implicit form");
+    launch_axpby(h, 1.0 / nrm, x, 0.0, nullptr, x, N);
+    const double *xf = implicit_complete(h, x, 1, nullptr);
+    Sx(xf, t);  // rows of S [x; t*(x)]: the translation block of Lambda is zero
+    launch_dot2(h, x, t, x, x, N, SC_TMP);
+    read_scal(h);
+    out.theta = h->h_scal[SC_TMP];
+    if (std::isnan(out.theta)) throw Error(CORA_B200_ERUNTIME, "NaN in theta -- result not certified and implicit form");
+  }
   return out;
 }
 
@@ -487,7 +503,7 @@ inline void debug_min_eigenpair(H *h, int max_iters, double *theta, double *x_ou
   const long long N = h->DL.N;
   double *x = h->ws[V_T1].p, *w = h->ws[V_T0].p, *t = h->ws[V_Z].p;
   auto Qx = [&](const double *q, double *y) {
-    launch_qprod(h, QM_SPMM, q, nullptr, nullptr, y, nullptr, 1, POST_STORE, SC_TMP, nullptr);
+    launch_qprod_raw(h, QM_SPMM, q, nullptr, nullptr, y, nullptr, 1, POST_STORE, SC_TMP, nullptr);
   };
   auto rayleigh = [&](const double *v) -> double {
     Qx(v, t);
@@ -517,7 +533,7 @@ inline void certify_host(H *h, int r, const double *Y, double eta, int nx, const
   *is_certified = c.certified ? 1 : 0;
   *theta = c.theta;
   if (num_iters) *num_iters = c.iters;
-  const size_t N = (size_t)h->DL.N;
+  const size_t N = (size_t)h->io_rows();  // (implicit formulation: the truncated direction, :1085-1100)
   if (c.have_x) {
     export_matrix(h, h->ws[V_T1].p, 1, x);
     if (all_eigvecs && cap >= 1) std::memcpy(all_eigvecs, x, N * sizeof(double));

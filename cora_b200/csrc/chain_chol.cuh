@@ -930,8 +930,10 @@ template <typename T>
 inline void upload_vec(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t s) { b.upload(v, s); }
 
 // build_chain_chol: chain_factor_dev.cuh (the factorisation runs on the device)
+// trans_only: factor the translation Laplacian Q33 alone (rotation and range rows decoupled: identity / dropped),
+// the LtransCholRed_ of the implicit formulation (src/CORA_problem.cpp:714-741) when pin_last is set
 ChainChol *build_chain_chol(H *h, const double *d_bval, const double *d_sdiag, double shift, bool pin_last,
-                            bool *pos_def, bool want_solve = true);
+                            bool *pos_def, bool want_solve = true, bool trans_only = false);
 
 inline void chain_ensure_ws(H *h, ChainChol *C, int r) {
   if (r <= C->ws_cols) return;

@@ -251,9 +251,10 @@ inline void chain_symbolic_build(ChainSym &S, const HostLayout &L, bool general)
 
 // ----------------------------------------------------------------- kernels ----
 static __global__ void __launch_bounds__(kThreads) k_cf_ranges(int m, int l, const double *__restrict__ sdiag, double shift,
-                                                               double *rdinv, int *flag) {
+                                                               double *rdinv, int *flag, int trans_only) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m) return;
+  if (trans_only) { rdinv[k] = 0.0; return; }  // the range rows are not part of the translation Laplacian
   const double delta = sdiag[l + k] + shift;
   if (!(delta > 0.0)) { rdinv[k] = 1.0; atomicAnd(flag, 0); }
   else rdinv[k] = 1.0 / delta;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) k_cf_pose_blocks(int n, int TP, cons
                                                              const int *__restrict__ uc_ptr, const int *__restrict__ uc_k,
                                                              const double *__restrict__ uc_coef,
                                                              const double *__restrict__ rdinv, int pinned_pose_row,
-                                                             double *A, double *U) {
+                                                             double *A, double *U, int trans_only) {
   constexpr int BB = B * B, d = B - 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -292,6 +293,11 @@ __global__ void __launch_bounds__(kThreads) k_cf_pose_blocks(int n, int TP, cons
     if (i == n - 2)
       for (int q = 0; q < B; ++q) u[q * B + d] = 0.0;
   }
+  if (trans_only) {  // translation Laplacian only: identity on the rotation rows, no coupling to them
+    for (int p = 0; p < B; ++p)
+      for (int q = 0; q < B; ++q)
+        if (p != d || q != d) { a[p * B + q] = (p == q) ? 1.0 : 0.0; u[p * B + q] = 0.0; }
+  }
   for (int e = 0; e < BB; ++e) { A[(size_t)i * BB + e] = a[e]; U[(size_t)i * BB + e] = u[e]; }
 }
 
@@ -306,7 +312,8 @@ __global__ void __launch_bounds__(kThreads) k_gen_pose_blocks(int n, int ne, int
                                                               const int *__restrict__ e_j, const long long *__restrict__ e_off,
                                                               const double *__restrict__ e_stat,
                                                               const int *__restrict__ ec_ptr, const int *__restrict__ ec_k,
-                                                              const double *__restrict__ ec_coef, double *A, double *E) {
+                                                              const double *__restrict__ ec_coef, double *A, double *E,
+                                                              int trans_only) {
   constexpr int BB = B * B, d = B - 1;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) {
@@ -321,6 +328,10 @@ __global__ void __launch_bounds__(kThreads) k_gen_pose_blocks(int n, int ne, int
       for (int q = 0; q < B; ++q) { a[d * B + q] = 0.0; a[q * B + d] = 0.0; }
       a[d * B + d] = 1.0;
     }
+    if (trans_only)
+      for (int p = 0; p < B; ++p)
+        for (int q = 0; q < B; ++q)
+          if (p != d || q != d) a[p * B + q] = (p == q) ? 1.0 : 0.0;
     for (int e = 0; e < BB; ++e) A[(size_t)i * BB + e] = a[e];
   } else if (t - n < ne) {
     const int e = t - n;
@@ -331,6 +342,8 @@ __global__ void __launch_bounds__(kThreads) k_gen_pose_blocks(int n, int ne, int
     u[d * B + d] -= su;
     if (pinned_pose_row >= 0 && e_j[e] == n - 1)
       for (int q = 0; q < B; ++q) u[q * B + d] = 0.0;
+    if (trans_only)
+      for (int q = 0; q < BB; ++q) if (q != d * B + d) u[q] = 0.0;
     for (int q = 0; q < BB; ++q) E[(size_t)e * BB + q] = u[q];
   }
 }
@@ -340,9 +353,11 @@ static __global__ void __launch_bounds__(kThreads) k_cf_border(int nb, const int
                                                                const int *__restrict__ blc_ptr, const int *__restrict__ blc_k,
                                                                const double *__restrict__ blc_coef,
                                                                const double *__restrict__ rdinv, const int *__restrict__ bl_row,
-                                                               int pinned_landmark, int pinned_pose_row, double *bl_val) {
+                                                               int pinned_landmark, int pinned_pose_row, double *bl_val,
+                                                               int trans_only, int D1) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nb) return;
+  if (trans_only && bl_row[q] % D1 != D1 - 1) { bl_val[q] = 0.0; return; }  // rotation row of a pose
   double v = bl_static[q];
   for (int e = blc_ptr[q]; e < blc_ptr[q + 1]; ++e) v -= blc_coef[e] * rdinv[blc_k[e]];
   if (bl_row[q] == pinned_pose_row) v = 0.0;
@@ -480,7 +495,8 @@ inline void chain_symbolic_upload(H *h, ChainSym &S) {
 // handle's structure (Q, or S = Q - Lambda).  Throws ENOTIMPL when the graph is not a chain + landmark border.
 template <int B>
 inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d_bval, const double *d_sdiag, double shift,
-                                bool pin_last, bool want_solve) {
+                                bool pin_last, bool want_solve, bool trans_only) {
+  const int to = trans_only ? 1 : 0;  // factor the translation Laplacian Q33 only (Formulation::Implicit)
   constexpr int BB = B * B;
   const int n = S.n, l = S.l, m = S.m, d = B - 1;
   cudaStream_t s = h->stream;
@@ -498,7 +514,7 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
   CUDA_CHECK(cudaMemcpyAsync(S.d_flag.p, &one, sizeof(int), cudaMemcpyHostToDevice, s));
   C->rdinv.reserve((size_t)std::max(m, 1));
   if (m > 0) {
-    k_cf_ranges<<<(m + kThreads - 1) / kThreads, kThreads, 0, s>>>(m, l, d_sdiag, shift, C->rdinv.p, S.d_flag.p);
+    k_cf_ranges<<<(m + kThreads - 1) / kThreads, kThreads, 0, s>>>(m, l, d_sdiag, shift, C->rdinv.p, S.d_flag.p, to);
     check_launch(h);
   }
   C->general = S.general;
@@ -507,12 +523,12 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
     const int ne = (int)S.e_i.size();
     k_gen_pose_blocks<B><<<(n + ne + kThreads - 1) / kThreads, kThreads, 0, s>>>(
         n, ne, h->HL.TP, d_bval, S.d_Aoff.p, shift, S.d_tinc_ptr.p, S.d_tinc_k.p, S.d_tinc_e.p, C->rdinv.p,
-        F.pinned_pose_row, S.d_e_j.p, S.d_e_off.p, S.d_e_stat.p, S.d_ec_ptr.p, S.d_ec_k.p, S.d_ec_coef.p, S.d_A.p, S.d_E.p);
+        F.pinned_pose_row, S.d_e_j.p, S.d_e_off.p, S.d_e_stat.p, S.d_ec_ptr.p, S.d_ec_k.p, S.d_ec_coef.p, S.d_A.p, S.d_E.p, to);
     check_launch(h);
   } else if (n > 0) {
     k_cf_pose_blocks<B><<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(
         n, h->HL.TP, d_bval, S.d_Aoff.p, S.d_Uoff.p, shift, S.d_tinc_ptr.p, S.d_tinc_k.p, S.d_tinc_e.p, S.d_uc_ptr.p,
-        S.d_uc_k.p, S.d_uc_coef.p, C->rdinv.p, F.pinned_pose_row, S.lv[0]->A.p, S.lv[0]->U.p);
+        S.d_uc_k.p, S.d_uc_coef.p, C->rdinv.p, F.pinned_pose_row, S.lv[0]->A.p, S.lv[0]->U.p, to);
     check_launch(h);
   }
   const int nb = (int)S.bl_row.size();
@@ -520,7 +536,7 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
   if (nb > 0) {
     k_cf_border<<<(nb + kThreads - 1) / kThreads, kThreads, 0, s>>>(nb, S.d_bl_ptr.p, l, S.d_bl_static.p, S.d_blc_ptr.p,
                                                                    S.d_blc_k.p, S.d_blc_coef.p, C->rdinv.p, S.d_bl_row.p,
-                                                                   F.pinned_landmark, F.pinned_pose_row, C->bl_val.p);
+                                                                   F.pinned_landmark, F.pinned_pose_row, C->bl_val.p, to, B);
     check_launch(h);
   }
   if (l > 0) {
@@ -682,15 +698,16 @@ inline ChainSym &chain_symbolic(H *h) {
 }
 
 inline ChainChol *build_chain_chol(H *h, const double *d_bval, const double *d_sdiag, double shift, bool pin_last,
-                                   bool *pos_def, bool want_solve) {
+                                   bool *pos_def, bool want_solve, bool trans_only) {
   ChainSym &S = chain_symbolic(h);
-  ChainChol *C = h->chol_spare ? h->chol_spare : new ChainChol();  // recycle the buffers of the last released factor
-  h->chol_spare = nullptr;
+  // recycle the buffers of the last released factor (not for the long-lived translation factor)
+  ChainChol *C = (h->chol_spare && !trans_only) ? h->chol_spare : new ChainChol();
+  if (C == h->chol_spare) h->chol_spare = nullptr;
   C->ws_cols = C->ws_cols;  // (work vectors of the apply are sized by columns only: still valid)
   try {
     C->B = h->HL.D1;
-    if (h->HL.D1 == 3) chain_factor_device<3>(h, S, C, d_bval, d_sdiag, shift, pin_last, want_solve);
-    else chain_factor_device<4>(h, S, C, d_bval, d_sdiag, shift, pin_last, want_solve);
+    if (h->HL.D1 == 3) chain_factor_device<3>(h, S, C, d_bval, d_sdiag, shift, pin_last, want_solve, trans_only);
+    else chain_factor_device<4>(h, S, C, d_bval, d_sdiag, shift, pin_last, want_solve, trans_only);
     *pos_def = C->host.pos_def;
   } catch (...) {
     delete C;

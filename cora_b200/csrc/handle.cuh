@@ -101,6 +101,12 @@ struct cora_b200_handle {
   int chain_sym_state = 0;                   // 0: not built, 1: built, 2: not a chain graph
   std::string chain_sym_error;
   int precond_requested = CORA_B200_PRECON_JACOBI;  // what the caller asked for (precond: what is applied)
+  // Formulation::Implicit (translations marginalised, src/CORA_problem.cpp:714-757): iterates carry zero
+  // translation rows; every data-matrix product runs on the translation-completed copy (implicit.cuh)
+  int formulation = CORA_B200_FORMULATION_EXPLICIT;
+  cora_b200::ChainChol *ltrans = nullptr;    // factor of Q33 with the last translation pinned (LtransCholRed_)
+  cora_b200::DevBuf<double> d_imp[3];        // completed copy, T^T Y, L^-1 T^T Y
+  int io_rows() const { return formulation == CORA_B200_FORMULATION_IMPLICIT ? HL.d * HL.n + HL.m : HL.N; }
   int last_cert_branch = CORA_B200_CERT_NONE;
   // resident iterate rank
   int resident_r = 0;

@@ -996,21 +996,42 @@ __global__ void __launch_bounds__(kThreads) k_patch_certificate(const DevLayout 
 // ------------------------------------------------------------- layout changes ---
 // reference column-major N x r  ->  internal row-major (row permuted)
 static __global__ void __launch_bounds__(kThreads) k_import(const int *__restrict__ int2ref, const double *__restrict__ src,
-                                                     double *__restrict__ dst, int N, int r, int src_cols) {
+                                                     double *__restrict__ dst, int N, int r, int src_cols,
+                                                     int io_rows) {
+  // io_rows < N: the host matrix holds only the leading io_rows reference rows (Formulation::Implicit: rotations
+  // and ranges); the remaining internal rows (translations) are zero
   const long long nE = (long long)N * r;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nE;
        e += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(e / r), c = (int)(e - (long long)row * r);
-    dst[e] = c < src_cols ? src[(size_t)c * N + int2ref[row]] : 0.0;
+    const int ref = int2ref[row];
+    dst[e] = (c < src_cols && ref < io_rows) ? src[(size_t)c * io_rows + ref] : 0.0;
   }
 }
 static __global__ void __launch_bounds__(kThreads) k_export(const int *__restrict__ int2ref, const double *__restrict__ src,
-                                                     double *__restrict__ dst, int N, int r) {
+                                                     double *__restrict__ dst, int N, int r, int io_rows) {
   const long long nE = (long long)N * r;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nE;
        e += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(e / r), c = (int)(e - (long long)row * r);
-    dst[(size_t)c * N + int2ref[row]] = src[e];
+    const int ref = int2ref[row];
+    if (ref < io_rows) dst[(size_t)c * io_rows + ref] = src[e];
+  }
+}
+
+// Formulation::Implicit helpers.  Translation rows in the internal order: row d of every pose block, then the l
+// landmark rows.  mode 0: out = x with the translation rows zeroed; mode 1: out's translation rows = -z's
+// (out otherwise untouched); mode 2: zero the translation rows of out in place.
+static __global__ void __launch_bounds__(kThreads) k_translation_rows(int mode, int nPoseRows, int D1, int l, int r,
+                                                               const double *__restrict__ x, const double *__restrict__ z,
+                                                               double *out, long long nE, const CgCtrl *ctrl) {
+  if (ctrl != nullptr && *((volatile const int *)&ctrl->state) != 0) return;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nE;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / r;
+    const bool tr = row < nPoseRows ? (row % D1 == D1 - 1) : (row < nPoseRows + l);
+    if (mode == 0) out[e] = tr ? 0.0 : x[e];
+    else if (tr) out[e] = (mode == 1) ? -z[e] : 0.0;
   }
 }
 

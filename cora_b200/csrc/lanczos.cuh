@@ -104,7 +104,7 @@ double estimate_spectral_norm(H *h) {
   double beta = 0.0, prev = 0.0;
   const int kmax = (int)std::min<long long>(60, nE);
   for (int k = 0; k < kmax; ++k) {
-    launch_qprod(h, QM_SPMM, q, nullptr, nullptr, w, nullptr, 1, POST_STORE, SC_TMP, nullptr);
+    launch_qprod_raw(h, QM_SPMM, q, nullptr, nullptr, w, nullptr, 1, POST_STORE, SC_TMP, nullptr);
     launch_dot2(h, q, w, nullptr, nullptr, nE, SC_TMP);
     read_scal(h);
     const double alpha = h->h_scal[SC_TMP];

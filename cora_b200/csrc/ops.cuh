@@ -80,10 +80,10 @@ inline void ensure_workspace(H *h, int r) {
   });
 }
 
-// Q X (+ epilogue).  Lalt: alternative value set on the same structure (S + eta I).
-inline void launch_qprod(H *h, int mode, const double *X, const double *Y, const double *G, double *out,
-                         double *out2, int r, int post, int slot, CgCtrl *ctrl,
-                         const DevLayout *Lalt = nullptr) {
+// Q X (+ epilogue) with the explicit data matrix.  Lalt: alternative value set on the same structure (S + eta I).
+inline void launch_qprod_raw(H *h, int mode, const double *X, const double *Y, const double *G, double *out,
+                             double *out2, int r, int post, int slot, CgCtrl *ctrl,
+                             const DevLayout *Lalt = nullptr) {
   const DevLayout &L = Lalt ? *Lalt : h->DL;
   if (L.numLong > 0) {
     DISPATCH_D(h, k_long_groups<DD><<<L.numLong, kThreads, (size_t)L.D1 * kThreads * sizeof(double), h->stream>>>(
@@ -100,6 +100,27 @@ inline void launch_qprod(H *h, int mode, const double *X, const double *Y, const
   DISPATCH_D(h, k_qprod<DD><<<L.numTiles, kThreads, smem_q<DD>(h, r, mode), h->stream>>>(L, A));
   check_launch(h);
   if (prof) CUDA_CHECK(cudaEventRecord(h->prof_ev[h->prof_n++], h->stream));
+}
+
+// Formulation::Implicit (implicit.cuh): the translation-completed copy of X, and zeroing of translation rows
+inline const double *implicit_complete(H *h, const double *X, int r, CgCtrl *ctrl);
+inline void zero_translation_rows(H *h, double *V, int r, const CgCtrl *ctrl);
+
+// Problem::dataMatrixProduct (src/CORA_problem.cpp:742-757) + epilogue in the handle's formulation.  Implicit:
+// Qmain Y - T L^-1 T^T Y = rows of Q [Y; t*(Y)] -- the same fused kernel on the completed copy; the translation
+// rows of the results (zero up to rounding) are cleared.  Products with an alternative value set (the certificate
+// matrix, always the translation-explicit one: src/CORA_problem.cpp:1055-1059) are never completed.
+inline void launch_qprod(H *h, int mode, const double *X, const double *Y, const double *G, double *out,
+                         double *out2, int r, int post, int slot, CgCtrl *ctrl,
+                         const DevLayout *Lalt = nullptr) {
+  if (h->formulation != CORA_B200_FORMULATION_IMPLICIT || Lalt != nullptr) {
+    launch_qprod_raw(h, mode, X, Y, G, out, out2, r, post, slot, ctrl, Lalt);
+    return;
+  }
+  const double *Xc = implicit_complete(h, X, r, ctrl);
+  launch_qprod_raw(h, mode, Xc, Y == X ? Xc : Y, G, out, out2, r, post, slot, ctrl, nullptr);
+  if (out) zero_translation_rows(h, out, r, ctrl);
+  if (out2) zero_translation_rows(h, out2, r, ctrl);
 }
 
 inline void launch_update(H *h, const UArgs &A0) {
@@ -136,18 +157,22 @@ inline void launch_axpby(H *h, double a, const double *x, double b, const double
   check_launch(h);
 }
 
-inline void import_matrix(H *h, const double *host, int src_cols, double *dst, int r) {
-  const size_t bytes = (size_t)h->DL.N * src_cols * sizeof(double);
+// Host matrices are column-major with getExpectedVariableSize() rows (src/CORA_problem.cpp:944-954): N in the
+// explicit formulation, d n + m (rotations and ranges) in the implicit one.  rows < 0: the handle's formulation.
+inline void import_matrix(H *h, const double *host, int src_cols, double *dst, int r, int rows = -1) {
+  const int io = rows < 0 ? h->io_rows() : rows;
+  const size_t bytes = (size_t)io * src_cols * sizeof(double);
   CUDA_CHECK(cudaMemcpyAsync(h->d_stage.p, host, bytes, cudaMemcpyHostToDevice, h->stream));
   const long long nE = (long long)h->DL.N * r;
-  k_import<<<flat_grid(h, nE), kThreads, 0, h->stream>>>(h->DL.int2ref, h->d_stage.p, dst, h->DL.N, r, src_cols);
+  k_import<<<flat_grid(h, nE), kThreads, 0, h->stream>>>(h->DL.int2ref, h->d_stage.p, dst, h->DL.N, r, src_cols, io);
   check_launch(h);
 }
-inline void export_matrix(H *h, const double *src, int r, double *host) {
+inline void export_matrix(H *h, const double *src, int r, double *host, int rows = -1) {
+  const int io = rows < 0 ? h->io_rows() : rows;
   const long long nE = (long long)h->DL.N * r;
-  k_export<<<flat_grid(h, nE), kThreads, 0, h->stream>>>(h->DL.int2ref, src, h->d_stage.p, h->DL.N, r);
+  k_export<<<flat_grid(h, nE), kThreads, 0, h->stream>>>(h->DL.int2ref, src, h->d_stage.p, h->DL.N, r, io);
   check_launch(h);
-  CUDA_CHECK(cudaMemcpyAsync(host, h->d_stage.p, (size_t)nE * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaMemcpyAsync(host, h->d_stage.p, (size_t)io * r * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
 }
 

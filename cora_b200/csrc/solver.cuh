@@ -29,6 +29,10 @@ inline void apply_preconditioner(H *h, const double *V, double *Z, int r, const 
   } else {
     throw Error(CORA_B200_EINVAL, "The desired preconditioner is not implemented");  // :892-894
   }
+  // Formulation::Implicit (:878-885): V is lifted with zero translations (its translation rows ARE zero here),
+  // solved with the full factor, and only the rotation / range rows of the result are kept
+  if (h->formulation == CORA_B200_FORMULATION_IMPLICIT && h->precond != CORA_B200_PRECON_JACOBI)
+    zero_translation_rows(h, Z, r, ctrl);
 }
 
 // V = proj_Y(M^-1 R) with <R,V>, <V,V> -> scal[slot..slot+1]   (src/CORA.cpp:89-92)
@@ -554,7 +558,7 @@ inline void tnt_resident(H *h, int r, const cora_b200_tnt_params &p, cora_b200_t
   // the persistent kernel applies Jacobi or the CHAIN factor in its own phases; the general sparse factor of graphs
   // with loop closures / several robots (gen_chol_dev.cuh) is applied by level-scheduled launches on the multi-launch path
   const bool general_factor = h->precond == CORA_B200_PRECON_REG_CHOLESKY && h->chol && h->chol->general;
-  if (h->use_persistent && !general_factor) {
+  if (h->use_persistent && !general_factor && h->formulation == CORA_B200_FORMULATION_EXPLICIT) {
     tnt_persistent(h, r, p, res);
     return;
   }

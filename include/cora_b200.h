@@ -72,6 +72,22 @@ int cora_b200_create(cora_b200_t **h, int device, void *stream, int d, int n_pos
                      int preconditioner, double reg_chol_max_cond);
 int cora_b200_destroy(cora_b200_t *h);
 int cora_b200_size(const cora_b200_t *h, int64_t *N);
+/* Formulation (include/CORA/CORA_types.h:52-56, Problem::setFormulation CORA_problem.h:338).  Implicit = the
+ * translation-marginalised problem of src/CORA_problem.cpp:714-757: every dense matrix at this boundary then has
+ * getExpectedVariableSize() = d n + m rows (rotations, then ranges; src/CORA_problem.cpp:944-954) instead of N,
+ * the data-matrix product is Qmain Y - T_red chol(L_red)^-1 T_red^T Y, the preconditioner lifts with zero
+ * translations (:878-885) and a failed certificate returns the rotation/range part of the direction with its
+ * Rayleigh quotient in the implicit operator (:1085-1100).  The factor of L_red is built here (chain or general
+ * pose-graph Cholesky).  Implicit solves run on the multi-launch TNT path. */
+#define CORA_B200_FORMULATION_EXPLICIT 0
+#define CORA_B200_FORMULATION_IMPLICIT 1
+int cora_b200_set_formulation(cora_b200_t *h, int formulation);
+/* Problem::getExpectedVariableSize (src/CORA_problem.cpp:944-954) */
+int cora_b200_variable_rows(const cora_b200_t *h, int64_t *rows);
+/* Problem::getTranslationExplicitSolution (src/CORA_problem.cpp:1168-1197): Y is (d n + m) x r, Xfull is N x r
+ * = [Y; -chol(L_red)^-1 T_red^T Y; 0] (last translation pinned to zero). */
+int cora_b200_translation_explicit_solution(cora_b200_t *h, int r, const double *Y, double *Xfull);
+
 /* Problem::setPreconditioner (include/CORA/CORA_problem.h:335-337) + updatePreconditioner */
 int cora_b200_set_preconditioner(cora_b200_t *h, int preconditioner, double reg_chol_max_cond);
 /* The preconditioner actually applied.  Preconditioner::RegularizedCholesky (the reference's default,

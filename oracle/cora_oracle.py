@@ -90,11 +90,16 @@ BLOCK_CHOLESKY = 2  # broken in the reference; not implemented
 REG_CHOLESKY = 3
 
 
+EXPLICIT, IMPLICIT = 0, 1  # include/CORA/CORA_types.h:52-56
+
+
 class Problem:
-    """Restatement of CORA::Problem (explicit formulation only)."""
+    """Restatement of CORA::Problem (explicit formulation; the translation-implicit one through
+    set_formulation(IMPLICIT), src/CORA_problem.cpp:714-757)."""
 
     def __init__(self, dim: int, rank: int, preconditioner: int = REG_CHOLESKY):
         assert rank >= dim  # CORA_problem.h:203
+        self.formulation = EXPLICIT
         self.d = dim
         self.rank = rank
         self.preconditioner = preconditioner
@@ -256,7 +261,41 @@ class Problem:
         a = self.measurement_arrays()
         self.Q = assemble_Q(self.d, self.n, self.l, a)
         self._update_preconditioner()
+        if self.formulation == IMPLICIT:  # :506-508
+            self._fill_implicit()
         self.up_to_date = True
+
+    # -- implicit formulation (CORA_problem.cpp:714-741) ----------------------
+    @property
+    def rot_and_range_size(self):
+        return self.d * self.n + self.m
+
+    @property
+    def expected_variable_size(self):  # :944-954
+        return self.N if self.formulation == EXPLICIT else self.rot_and_range_size
+
+    def set_formulation(self, formulation):  # CORA_problem.h:338
+        if formulation not in (EXPLICIT, IMPLICIT):
+            raise ValueError("Unknown formulation")
+        self.formulation = formulation
+        if self.Q is not None and formulation == IMPLICIT:
+            self._fill_implicit()
+
+    def _fill_implicit(self):
+        k = self.rot_and_range_size
+        nt = self.n + self.l
+        Q = self.Q.tocsr()
+        self._Qmain = Q[:k, :k].tocsr()
+        self._Tred = Q[:k, k:k + nt - 1].tocsr()
+        self._Ltrans = spla.splu(Q[k:k + nt - 1, k:k + nt - 1].tocsc())
+
+    def translation_explicit_solution(self, Y):  # :1168-1197
+        if Y.shape[0] != self.rot_and_range_size:
+            raise ValueError("expected %d rows" % self.rot_and_range_size)
+        X = np.zeros((self.N, Y.shape[1]))
+        X[: Y.shape[0]] = Y
+        X[Y.shape[0]: self.N - 1] = -self._Ltrans.solve(np.ascontiguousarray(self._Tred.T @ Y))
+        return X
 
     # -- preconditioner (CORA_problem.cpp:512-623) ---------------------------
     def _update_preconditioner(self):
@@ -284,13 +323,16 @@ class Problem:
     def _check(self, Y):
         if not self.up_to_date:
             raise RuntimeError("The data matrix must be constructed first")
-        if Y.shape[0] != self.N:
+        if Y.shape[0] != self.expected_variable_size:
             raise ValueError("expected matrix of shape (%d, %d) but got %s"
-                             % (self.N, Y.shape[1], Y.shape))
+                             % (self.expected_variable_size, Y.shape[1], Y.shape))
 
     def data_matrix_product(self, Y):  # :742-757
         self._check(Y)
-        return self.Q @ Y
+        if self.formulation == EXPLICIT:
+            return self.Q @ Y
+        P2 = self._Ltrans.solve(np.ascontiguousarray(self._Tred.T @ Y))
+        return self._Qmain @ Y - self._Tred @ P2
 
     def evaluate_objective(self, Y):  # :759-762
         return 0.5 * float(np.sum(Y * self.data_matrix_product(Y)))
@@ -325,7 +367,13 @@ class Problem:
 
     def precondition(self, V):  # :869-903
         if self.preconditioner == JACOBI:
-            res = self._jacobi[:, None] * V
+            # (the reference multiplies the N x N diagonal with the (d n + m)-row matrix in the implicit
+            #  formulation, a size mismatch: the oracle uses the leading part of the diagonal)
+            res = self._jacobi[: V.shape[0], None] * V
+        elif self.formulation == IMPLICIT:  # :878-885: lift with zero translations, solve, keep the top rows
+            lift = np.zeros((self.N, V.shape[1]))
+            lift[: V.shape[0]] = V
+            res = self._chol.solve(np.ascontiguousarray(lift[:-1]))[: V.shape[0]]
         else:
             res = np.zeros_like(V)
             res[:-1] = self._chol.solve(np.ascontiguousarray(V[:-1]))  # CORA_preconditioners.cpp:46-83
@@ -346,7 +394,7 @@ class Problem:
         self.rank += 1
 
     def random_initial_guess(self, rng):  # :1023-1028 (reference is unseeded)
-        return self.project_to_manifold(rng.uniform(-1, 1, size=(self.N, self.rank)))
+        return self.project_to_manifold(rng.uniform(-1, 1, size=(self.expected_variable_size, self.rank)))
 
     # -- certification (CORA_problem.cpp:1030-1166) ---------------------------
     def compute_lambda_blocks(self, Y):  # :1105-1131
@@ -376,6 +424,13 @@ class Problem:
         while math.isnan(res.theta):  # :1076-1083
             eta *= 2
             res = fast_verification(S, eta, X0, max_iters)
+        if not res.is_certified and self.formulation == IMPLICIT:  # :1085-1100
+            k = self.rot_and_range_size
+            v = res.x[:k] / np.linalg.norm(res.x[:k])
+            Lam = self.lambda_from_blocks(self.compute_lambda_blocks(Y), k)
+            Sx = self.data_matrix_product(v[:, None])[:, 0] - Lam @ v
+            res.x = v
+            res.theta = float(v @ Sx)
         return res
 
 
