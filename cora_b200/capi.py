@@ -276,11 +276,12 @@ def debug_factor_stats(d, n, m, nt, Q):
     ci = np.ascontiguousarray(Q.indices, dtype=np.int32)
     va = np.ascontiguousarray(Q.data, dtype=np.float64)
     i32 = C.POINTER(C.c_int32)
-    st = np.zeros(8, dtype=np.int64)
+    st = np.zeros(12, dtype=np.int64)
     _check(load().cora_b200_debug_factor_stats(C.c_int(d), C.c_int(n), C.c_int(m), C.c_int(nt), rp.ctypes.data_as(i32),
                                                ci.ctypes.data_as(i32), _p(va), C.c_int64(Q.nnz),
                                                st.ctypes.data_as(C.POINTER(C.c_int64))))
-    names = ("chain", "couplings", "l_blocks", "etree_height", "clusters", "levels", "max_column", "poses")
+    names = ("chain", "couplings", "l_blocks", "etree_height", "clusters", "levels", "max_column", "poses",
+             "cluster_inverse_blocks", "max_cluster_row_blocks", "longest_row", "rows_over_64")
     return dict(zip(names, (int(x) for x in st)))
 
 

@@ -636,14 +636,15 @@ extern "C" int cora_b200_debug_chain_host(int d, int n_poses, int n_ranges, int 
 // Test hook (CPU only): structure of the pose-system factorisation the handle would build for this matrix.
 // stats[0] = 1 if the pose graph is a chain (chain_chol.cuh levels), 0 if general (gen_chol.hpp);
 // general: [1] pose couplings, [2] blocks of L below the diagonal, [3] elimination-tree height, [4] clusters,
-// [5] cluster levels (= launches of one forward or backward solve), [6] largest column, [7] poses.
+// [5] cluster levels (grid barriers of one forward or backward sweep), [6] largest column, [7] poses,
+// [8] blocks of the per-cluster inverses, [9] most row blocks read by one cluster, [10] longest row, [11] rows > 64.
 extern "C" int cora_b200_debug_factor_stats(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
                                             const int32_t *col, const double *val, int64_t nnz, int64_t *stats) {
   API_BEGIN
   require(rowptr && stats, "NULL argument");
   HostLayout L;
   build_layout(L, d, n_poses, n_ranges, n_trans, rowptr, col, val, nnz, 192);
-  for (int i = 0; i < 8; ++i) stats[i] = 0;
+  for (int i = 0; i < 12; ++i) stats[i] = 0;
   stats[7] = L.n;
   ChainSym S;
   try {
@@ -661,6 +662,14 @@ extern "C" int cora_b200_debug_factor_stats(int d, int n_poses, int n_ranges, in
     int64_t mx = 0;
     for (int v = 0; v < G.gs.n; ++v) mx = std::max<int64_t>(mx, G.gs.colptr[v + 1] - G.gs.colptr[v]);
     stats[6] = mx;
+    stats[8] = G.gs.linv_blocks;  // blocks of the per-cluster inverses
+    for (size_t c = 0; c + 1 < G.gs.cl_ptr.size(); ++c)  // [9] most off-diagonal blocks one cluster reads in the forward sweep
+      stats[9] = std::max<int64_t>(stats[9], G.gs.rowptr[G.gs.cl_ptr[c + 1]] - G.gs.rowptr[G.gs.cl_ptr[c]]);
+    for (int v = 0; v < G.gs.n; ++v) {  // [10] longest row, [11] rows with more than 64 blocks
+      const int64_t len = G.gs.rowptr[v + 1] - G.gs.rowptr[v];
+      stats[10] = std::max(stats[10], len);
+      stats[11] += len > 64 ? 1 : 0;
+    }
   }
   API_END
 }

@@ -769,7 +769,7 @@ struct ChainChol {
   // pose graph with loop closures / several robots: general sparse block factor (gen_chol_dev.cuh) instead of levels
   bool general = false;
   GenFactorDev gen;
-  const GenSymDev *gsd = nullptr;  // owned by the handle's ChainSym
+  GenSymDev *gsd = nullptr;  // owned by the handle's ChainSym
   ~ChainChol() {
     for (auto *p : levels) delete p;
   }

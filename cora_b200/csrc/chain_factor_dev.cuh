@@ -66,7 +66,7 @@ struct ChainSym {
   DevBuf<long long> d_e_off;
   DevBuf<double> d_e_stat, d_ec_coef, d_A, d_E;
   double *h_AE = nullptr;                  // pinned staging of the assembled pose blocks (A then E)
-  std::vector<double> h_L, h_Dinv;
+  std::vector<double> h_L, h_Dinv, h_Linv;
   ~ChainSym() {
     for (auto *p : lv) delete p;
     if (h_AE) cudaFreeHost(h_AE);
@@ -554,8 +554,12 @@ inline void chain_factor_device(H *h, ChainSym &S, ChainChol *C, const double *d
     if (ne) CUDA_CHECK(cudaMemcpyAsync(S.h_AE + (size_t)n * BB, S.d_E.p, ne * BB * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     gen_pd = gen_numeric<B>(S.gs, S.h_AE, S.h_AE + (size_t)n * BB, S.h_L, S.h_Dinv);
-    C->gen.Lval.reserve(std::max<size_t>(S.h_L.size(), 1)); C->gen.Dinv.reserve(S.h_Dinv.size());
-    if (!S.h_L.empty()) CUDA_CHECK(cudaMemcpyAsync(C->gen.Lval.p, S.h_L.data(), S.h_L.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    gen_cluster_inverses<B>(S.gs, S.h_L, S.h_Dinv, S.h_Linv);
+    C->gen.Lval.reserve(std::max<size_t>(S.h_L.size(), 1));
+    C->gen.Dinv.reserve(S.h_Dinv.size()); C->gen.Linv.reserve(S.h_Linv.size());
+    CUDA_CHECK(cudaMemcpyAsync(C->gen.Linv.p, S.h_Linv.data(), S.h_Linv.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (!S.h_L.empty())
+      CUDA_CHECK(cudaMemcpyAsync(C->gen.Lval.p, S.h_L.data(), S.h_L.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     CUDA_CHECK(cudaMemcpyAsync(C->gen.Dinv.p, S.h_Dinv.data(), S.h_Dinv.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
   }

@@ -29,6 +29,8 @@
 
 namespace cora_b200 {
 
+constexpr int kGenClusterMax = 12;  // poses per cluster
+
 struct GenSym {
   int n = 0, ne = 0;
   std::vector<int32_t> perm, iperm;              // perm[position] = pose, iperm[pose] = position
@@ -38,6 +40,13 @@ struct GenSym {
   std::vector<uint8_t> edge_tr;                  // 1: that slot holds the transpose of the input block M_ij
   std::vector<int32_t> cl_ptr;                   // clusters of consecutive positions (one warp each)
   std::vector<int32_t> lvl_ptr, lvl_cl;          // clusters grouped by dependency level
+  // schedule of the device solves (gen_chol_dev.cuh): per off-diagonal block the cluster-local pose it belongs to
+  // (row storage: its row; column storage: its column), per cluster one descriptor the warp loads at once
+  std::vector<uint8_t> erow_f, erow_b;           // (bit 7: the other pose of the block is inside the same cluster)
+  std::vector<int32_t> col2row;                  // column-storage slot -> index of the same block in row storage
+  std::vector<int32_t> desc;                     // 8 ints per cluster: {first position, poses, fwd first block, blocks,
+                                                 //  bwd first block, blocks, offset of the cluster inverse (blocks), 0}
+  int64_t linv_blocks = 0;                       // total blocks of the per-cluster inverses (sum of poses^2)
   int etree_height = 0;
   int64_t nnzL() const { return (int64_t)rowidx.size(); }
   int levels() const { return (int)lvl_ptr.size() - 1; }
@@ -221,7 +230,7 @@ inline void etree(const Graph &g, const std::vector<int32_t> &perm, const std::v
 
 // Ordering + symbolic factorisation + clustering.  Edges are pose pairs (i < j); duplicates are allowed.
 inline void gen_symbolic(GenSym &S, int n, const std::vector<int32_t> &ei, const std::vector<int32_t> &ej,
-                         int leaf_size = 12, int cluster_max = 12) {
+                         int leaf_size = 12, int cluster_max = kGenClusterMax) {
   using namespace gen_detail;
   S.n = n; S.ne = (int)ei.size();
   const Graph g = build_graph(n, ei, ej);
@@ -361,6 +370,25 @@ inline void gen_symbolic(GenSym &S, int n, const std::vector<int32_t> &ei, const
     std::vector<int32_t> fill(S.lvl_ptr.begin(), S.lvl_ptr.end() - 1);
     for (int c = 0; c < nc; ++c) S.lvl_cl[fill[clevel[c]]++] = c;
   }
+  // ---- device schedule ----
+  S.erow_f.assign(S.colidx.size(), 0); S.erow_b.assign(S.rowidx.size(), 0);
+  S.desc.clear();
+  S.linv_blocks = 0;
+  S.col2row.assign(S.rowidx.size(), 0);
+  for (size_t q = 0; q < S.rowslot.size(); ++q) S.col2row[S.rowslot[q]] = (int32_t)q;
+  for (int c = 0; c < nc; ++c) {
+    const int p0 = S.cl_ptr[c], p1 = S.cl_ptr[c + 1];
+    for (int p = p0; p < p1; ++p) {
+      for (int32_t q = S.rowptr[p]; q < S.rowptr[p + 1]; ++q)
+        S.erow_f[q] = (uint8_t)((p - p0) | (S.colidx[q] >= p0 ? 0x80 : 0));
+      for (int32_t q = S.colptr[p]; q < S.colptr[p + 1]; ++q)
+        S.erow_b[q] = (uint8_t)((p - p0) | (S.rowidx[q] < p1 ? 0x80 : 0));
+    }
+    const int32_t dsc[8] = {p0, p1 - p0, S.rowptr[p0], S.rowptr[p1] - S.rowptr[p0],
+                            S.colptr[p0], S.colptr[p1] - S.colptr[p0], (int32_t)S.linv_blocks, 0};
+    S.desc.insert(S.desc.end(), dsc, dsc + 8);
+    S.linv_blocks += ((int64_t)(p1 - p0) * (p1 - p0) + 1) & ~(int64_t)1;  // even: 16-byte aligned for any block size
+  }
 }
 
 // B x B helpers (row-major)
@@ -444,8 +472,50 @@ inline bool gen_numeric(const GenSym &S, const double *A, const double *E, std::
   return ok;
 }
 
-// X: [n][B][ld] in POSE order, solved in place (host; the device kernels of gen_chol_dev.cuh do the same sums in
-// the same order).
+// Inverse of the in-cluster part of L for every cluster K (poses p0..p1-1): Linv_K = L_KK^-1, a block lower
+// triangular (poses x poses) matrix stored dense as [j][j'][B*B].  With it a cluster is eliminated by two products
+// instead of a serial chain over its poses:  y_K = Linv_K (b_K - L_K,ext y_ext)  and  x_K = Linv_K^T (y_K - ...).
+template <int B>
+inline void gen_cluster_inverses(const GenSym &S, const std::vector<double> &Lval, const std::vector<double> &Dinv,
+                                 std::vector<double> &Linv) {
+  constexpr int BB = B * B;
+  Linv.assign((size_t)std::max<int64_t>(S.linv_blocks, 1) * BB, 0.0);
+  const int nc = (int)S.cl_ptr.size() - 1;
+  for (int c = 0; c < nc; ++c) {
+    const int p0 = S.cl_ptr[c], k = S.cl_ptr[c + 1] - p0;
+    double *X = Linv.data() + (size_t)S.desc[(size_t)c * 8 + 6] * BB;
+    auto blk = [&](int j, int jc) { return X + ((size_t)j * k + jc) * BB; };
+    for (int j = 0; j < k; ++j) {
+      const double *Dj = Dinv.data() + (size_t)(p0 + j) * BB;
+      // row j of the inverse: X[j][jc] = Dj * (delta_{j,jc} I - sum_{j'' in row j, in cluster} L[j][j''] X[j''][jc])
+      for (int jc = 0; jc <= j; ++jc) {
+        double T[BB];
+        for (int e = 0; e < BB; ++e) T[e] = 0.0;
+        if (jc == j) for (int a = 0; a < B; ++a) T[a * B + a] = 1.0;
+        for (int32_t q = S.rowptr[p0 + j]; q < S.rowptr[p0 + j + 1]; ++q) {
+          const int u = S.colidx[q] - p0;
+          if (u < jc) continue;  // outside the cluster (u < 0) or X[u][jc] = 0
+          const double *Lb = Lval.data() + (size_t)S.rowslot[q] * BB, *Xu = blk(u, jc);
+          for (int a = 0; a < B; ++a)
+            for (int b = 0; b < B; ++b) {
+              double s = 0.0;
+              for (int e = 0; e < B; ++e) s += Lb[a * B + e] * Xu[e * B + b];
+              T[a * B + b] -= s;
+            }
+        }
+        double *O = blk(j, jc);
+        for (int a = 0; a < B; ++a)
+          for (int b = 0; b < B; ++b) {
+            double s = 0.0;
+            for (int e = 0; e <= a; ++e) s += Dj[a * B + e] * T[e * B + b];
+            O[a * B + b] = s;
+          }
+      }
+    }
+  }
+}
+
+// X: [n][B][ld] in POSE order, solved in place (host reference of the device kernels of gen_chol_dev.cuh).
 template <int B>
 inline void gen_solve_host(const GenSym &S, const double *Lval, const double *Dinv, double *X, int ld, int ncols) {
   constexpr int BB = B * B;

@@ -394,9 +394,11 @@ int cora_b200_debug_chain_host(int d, int n_poses, int n_ranges, int n_trans, co
 /* Test hook (CPU only): which factorisation the pose system of this matrix gets and its size.
  * stats[0] = 1: odometry chain (levels of chunks); 0: general sparse block Cholesky (loop closures, several
  * robots), then [1] pose couplings, [2] off-diagonal blocks of L, [3] elimination-tree height, [4] clusters,
- * [5] cluster levels (launches per triangular solve), [6] largest column, [7] poses. */
+ * [5] cluster levels (grid barriers per sweep of a triangular solve), [6] largest column, [7] poses, [8] blocks
+ * of the per-cluster inverses, [9] most row blocks one cluster reads, [10] longest row of L in blocks, [11] rows
+ * longer than 64 blocks. */
 int cora_b200_debug_factor_stats(int d, int n_poses, int n_ranges, int n_trans, const int32_t *rowptr,
-                                 const int32_t *col, const double *val, int64_t nnz, int64_t *stats /* 8 */);
+                                 const int32_t *col, const double *val, int64_t nnz, int64_t *stats /* 12 */);
 
 #ifdef __cplusplus
 }

@@ -57,8 +57,8 @@ struct NotImplementedException : public std::logic_error {  // include/CORA/CORA
 enum class Preconditioner { None = CORA_B200_PRECON_NONE, Jacobi = CORA_B200_PRECON_JACOBI,
                             BlockCholesky = CORA_B200_PRECON_BLOCK_CHOLESKY,
                             RegularizedCholesky = CORA_B200_PRECON_REG_CHOLESKY };
-// enum class Formulation (include/CORA/CORA_types.h:50-55); only Explicit is on the B200 path
-enum class Formulation { Explicit, Implicit };
+// enum class Formulation (include/CORA/CORA_types.h:50-55)
+enum class Formulation { Explicit = CORA_B200_FORMULATION_EXPLICIT, Implicit = CORA_B200_FORMULATION_IMPLICIT };
 
 // CORA::CertResults (include/CORA/CORA_types.h:58-64)
 struct CertResults {
@@ -121,8 +121,20 @@ class Problem {
     check(cora_b200_set_preconditioner(h_, (int)p, 0.0));
     preconditioner_ = p;
   }
-  void setFormulation(Formulation f) {
-    if (f != Formulation::Explicit) throw NotImplementedException("the implicit formulation is not on the B200 path");
+  void setFormulation(Formulation f) {  // CORA_problem.h:338 (+ fillImplicitFormulationMatrices, :714-741)
+    check(cora_b200_set_formulation(h_, (int)f));
+    formulation_ = f;
+  }
+  Formulation getFormulation() const { return formulation_; }  // CORA_problem.h:290
+  std::ptrdiff_t rotAndRangeMatrixSize() const { return (std::ptrdiff_t)dim_ * n_ + m_; }
+  std::ptrdiff_t getExpectedVariableSize() const {  // src/CORA_problem.cpp:944-954
+    return formulation_ == Formulation::Explicit ? getDataMatrixSize() : rotAndRangeMatrixSize();
+  }
+  Matrix getTranslationExplicitSolution(const Matrix &Y) const {  // src/CORA_problem.cpp:1168-1197
+    shape(Y, "Y");
+    Matrix X(getDataMatrixSize(), Y.cols());
+    check(cora_b200_translation_explicit_solution(h_, (int)Y.cols(), Y.data(), X.data()));
+    return X;
   }
 
   Scalar evaluateObjective(const Matrix &Y) const {
@@ -193,7 +205,7 @@ class Problem {
   CertResults certify_solution(const Matrix &Y, Scalar eta, size_t nx, const Matrix &eigvec_bootstrap,
                                size_t max_LOBPCG_iters = 500, Scalar = 3, Scalar = 1e-3) const {
     shape(Y, "Y");
-    const std::ptrdiff_t N = getDataMatrixSize();
+    const std::ptrdiff_t N = getExpectedVariableSize();  // (implicit: the truncated direction, :1085-1100)
     const int cap = (int)std::max<size_t>(nx, (size_t)Y.cols() + 2);
     CertResults out;
     out.x.assign((size_t)N, 0.0);
@@ -214,9 +226,9 @@ class Problem {
 
  private:
   void shape(const Matrix &Y, const char *name) const {  // checkMatrixShape, CORA_types.h:23-39
-    if (Y.rows() != getDataMatrixSize() || Y.cols() < 1)
+    if (Y.rows() != getExpectedVariableSize() || Y.cols() < 1)
       throw std::invalid_argument(std::string(name) + " has the wrong shape: expected " +
-                                  std::to_string(getDataMatrixSize()) + " rows, got " + std::to_string(Y.rows()) +
+                                  std::to_string(getExpectedVariableSize()) + " rows, got " + std::to_string(Y.rows()) +
                                   " x " + std::to_string(Y.cols()));
   }
   static void same(const Matrix &A, const Matrix &B, const char *name) {
@@ -226,6 +238,7 @@ class Problem {
   cora_b200_t *h_ = nullptr;
   int dim_, n_, m_, nt_, rank_;
   Preconditioner preconditioner_;
+  Formulation formulation_ = Formulation::Explicit;
 };
 
 namespace detail {
@@ -268,7 +281,7 @@ inline CoraTntResult TNT(Problem &problem, const Matrix &x0, const cora_b200_tnt
 // saddleEscape, include/CORA/CORA.h:33-35 (src/CORA.cpp:245-350): Y is N x r, returns N x (r+1)
 inline Matrix saddleEscape(const Problem &problem, const Matrix &Y, Scalar theta, const Vector &v,
                            Scalar gradient_tolerance, Scalar preconditioned_gradient_tolerance) {
-  if ((std::ptrdiff_t)v.size() != problem.getDataMatrixSize()) throw std::invalid_argument("v has the wrong size");
+  if ((std::ptrdiff_t)v.size() != problem.getExpectedVariableSize()) throw std::invalid_argument("v has the wrong size");
   Matrix out(Y.rows(), Y.cols() + 1);
   check(cora_b200_saddle_escape(problem.handle(), (int)Y.cols() + 1, Y.data(), theta, v.data(), gradient_tolerance,
                                 preconditioned_gradient_tolerance, out.data()));
@@ -287,7 +300,7 @@ inline Matrix projectSolution(const Problem &problem, const Matrix &Y, bool = fa
 // final iterate only (log_iterates feeds the reference's visualiser, which is out of scope).
 inline CoraResult solveCORA(Problem &problem, const Matrix &x0, int max_relaxation_rank = 20, bool verbose = false,
                             bool /*log_iterates*/ = false, bool show_iterates = false) {
-  if (x0.rows() != problem.getDataMatrixSize())
+  if (x0.rows() != problem.getExpectedVariableSize())
     throw std::invalid_argument("x0 has the wrong number of rows");  // src/CORA.cpp:30-40
   cora_b200_tnt_params p;
   check(cora_b200_tnt_default_params(&p));

@@ -112,6 +112,24 @@ int main() {
               (long)res.first.x.cols());
   CHECK(res.first.f < 1e-6);
   CHECK(res.first.x.cols() == d);
+  // Formulation::Implicit (CORA_problem.h:338, src/CORA_problem.cpp:714-757): rotations + ranges only; the product of
+  // the marginalised problem is the top of Q [Y; t*(Y)], and the ground truth stays in the kernel
+  p.setRank(3);
+  p.setFormulation(Formulation::Implicit);
+  const int64_t K = p.getExpectedVariableSize();
+  CHECK(K == (int64_t)d * n + m);
+  Matrix Yi(K, 3);
+  for (int64_t i = 0; i < K; ++i) for (int c = 0; c < 3; ++c) Yi(i, c) = X(i, c);
+  CHECK(std::fabs(p.evaluateObjective(Yi)) < 1e-9);
+  Matrix Xf = p.getTranslationExplicitSolution(Yi);
+  CHECK(Xf.rows() == N && Xf.cols() == 3);
+  double dt = 0;  // translations are recovered up to the pinned last one (a common shift)
+  for (int64_t i = K; i < N; ++i) for (int c = 0; c < 3; ++c) dt = std::max(dt, std::fabs((Xf(i, c) - X(i, c)) - (Xf(K, c) - X(K, c))));
+  CHECK(dt < 1e-8);
+  threw = false;
+  try { p.evaluateObjective(X); } catch (const std::invalid_argument &) { threw = true; }  // N rows are rejected now
+  CHECK(threw);
+  p.setFormulation(Formulation::Explicit);
   std::printf(fails ? "FAILED\n" : "OK (gpu)\n");
   return fails ? 1 : 0;
 }
