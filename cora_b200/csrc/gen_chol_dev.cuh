@@ -56,7 +56,7 @@ struct GenSolveArgs {
   int nlevels, ld, ncols;
 };
 
-constexpr int kGenWarps = 4;  // warps (clusters in flight) per CTA
+constexpr int kGenWarps = 8;  // warps (clusters in flight) per CTA
 constexpr int kGenBatch = 8;   // off-diagonal blocks in flight per lane (gathers: index, then block + operand)
 constexpr int kGenStream = 32; // products in flight per lane when summing the contiguous forward stream
 
@@ -82,9 +82,13 @@ __device__ __forceinline__ void gen_grid_sync(unsigned long long *bar, unsigned 
   __syncthreads();
 }
 
-// one cluster, one direction, one pass of CW columns
+// one cluster, one direction, one pass of CW columns.
+// part / nparts: in the thin upper levels of the tree (fewer clusters than CTAs) the kGenWarps warps of a CTA share
+// ONE cluster: each sums a slice of the off-diagonal products into its own copy of r (a single warp keeps only
+// ~8 loads in flight: measured 4400 cycles per batch of 64), warp 0 adds the copies in a fixed order and finishes.
 template <int B, bool FWD>
-__device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0, double *own, double *linv, int lane) {
+__device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0, double *own, double *linv, int lane,
+                                            int part, int nparts) {
   constexpr int BB = B * B, CW = 32 / B;
   const int dv = lane < 8 ? A.desc[(size_t)K * 8 + lane] : 0;
   const int p0 = __shfl_sync(0xffffffffu, dv, 0), nodes = __shfl_sync(0xffffffffu, dv, 1);
@@ -110,7 +114,7 @@ __device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0
 #define GEN_FENCE() do { if (chk == 0x9E3779B97F4A7C15ull) asm volatile("nanosleep.u32 1;"); asm volatile("" ::: "memory"); } while (0)
   const int cl = min(c, ncols - 1);  // clamped column: lanes beyond the last column load valid memory, store nothing
   // ---- the cluster inverse -> shared memory (16-byte loads, all in flight) ----
-  {
+  if (part == 0) {
     const double2 *src = reinterpret_cast<const double2 *>(A.Linv + (size_t)loff * BB);  // loff even: 16-byte aligned
     double2 *dst = reinterpret_cast<double2 *>(linv);
     const int n2 = (nodes * nodes * BB + 1) / 2;
@@ -124,7 +128,11 @@ __device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0
     }
   }
   // ---- right-hand sides of the cluster's poses ----
-  {
+  if (part != 0) {
+#pragma unroll
+    for (int j = 0; j < kGenClusterMax; ++j)
+      if (j < nodes) own[j * 32 + lane] = 0.0;
+  } else {
     double v[kGenClusterMax];
     if (FWD) {
       int pp[kGenClusterMax];
@@ -143,9 +151,14 @@ __device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0
       if (j < nodes) own[j * 32 + lane] = active ? v[j] : 0.0;
   }
   // ---- minus the products with the blocks that couple the cluster to poses outside it ----
+  // (this warp's slice: whole batches, so the order of the sums does not depend on the slicing of other warps)
+  constexpr int kStep = FWD ? kGenStream : kGenBatch;
+  const int nbatch = (nent + kStep - 1) / kStep;
+  const int tbeg = (int)((long long)nbatch * part / nparts) * kStep;
+  const int tend = min(nent, (int)((long long)nbatch * (part + 1) / nparts) * kStep);
   if (FWD) {  // produced by the clusters below (push): a contiguous stream in row order
     const double *cb = A.cbuf + ((size_t)e0 * B + al) * ncols + cl;
-    for (int t0 = 0; t0 < nent; t0 += kGenStream) {
+    for (int t0 = tbeg; t0 < tend; t0 += kGenStream) {
       int fl[kGenStream];
       double v[kGenStream];
 #pragma unroll
@@ -170,7 +183,7 @@ __device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0
       if (active) own[rrow * 32 + lane] -= run;
     }
   } else {  // gather over the (short) columns
-    for (int t0 = 0; t0 < nent; t0 += kGenBatch) {
+    for (int t0 = tbeg; t0 < tend; t0 += kGenBatch) {
       int u[kGenBatch], fl[kGenBatch];
 #pragma unroll
       for (int k = 0; k < kGenBatch; ++k) {
@@ -213,6 +226,19 @@ __device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0
     }
   }
   __syncwarp();
+  if (nparts > 1) {  // (uniform over the CTA)
+    __syncthreads();
+    if (part != 0) return;
+    const int stride = gen_smem_doubles_per_warp<B>();
+#pragma unroll
+    for (int j = 0; j < kGenClusterMax; ++j)
+      if (j < nodes) {
+        double r = own[j * 32 + lane];
+        for (int w = 1; w < nparts; ++w) r += own[(size_t)w * stride + j * 32 + lane];
+        own[j * 32 + lane] = r;
+      }
+    __syncwarp();
+  }
   // ---- times the cluster inverse (transposed on the way down) ----
   double res[kGenClusterMax];
 #pragma unroll
@@ -307,13 +333,21 @@ __global__ void __launch_bounds__(kGenWarps * 32) k_gen_solve(const GenSolveArgs
   for (int c0 = 0; c0 < A.ncols; c0 += CW) {
     for (int t = 0; t < A.nlevels; ++t) {
       const int l0 = A.lvl_ptr[t], l1 = A.lvl_ptr[t + 1];
-      for (int k = l0 + gwarp; k < l1; k += nwarps) gen_cluster<B, true>(A, A.lvl_cl[k], c0, own, linv, lane);
+      if (l1 - l0 <= (int)gridDim.x) {  // thin level: one cluster per CTA, its warps share the products
+        if (l0 + (int)blockIdx.x < l1) gen_cluster<B, true>(A, A.lvl_cl[l0 + blockIdx.x], c0, own, linv, lane, warp, kGenWarps);
+      } else {
+        for (int k = l0 + gwarp; k < l1; k += nwarps) gen_cluster<B, true>(A, A.lvl_cl[k], c0, own, linv, lane, 0, 1);
+      }
       gen_grid_sync(A.bar, target, gridDim.x);
       stamp();
     }
     for (int t = A.nlevels - 1; t >= 0; --t) {
       const int l0 = A.lvl_ptr[t], l1 = A.lvl_ptr[t + 1];
-      for (int k = l0 + gwarp; k < l1; k += nwarps) gen_cluster<B, false>(A, A.lvl_cl[k], c0, own, linv, lane);
+      if (l1 - l0 <= (int)gridDim.x) {
+        if (l0 + (int)blockIdx.x < l1) gen_cluster<B, false>(A, A.lvl_cl[l0 + blockIdx.x], c0, own, linv, lane, warp, kGenWarps);
+      } else {
+        for (int k = l0 + gwarp; k < l1; k += nwarps) gen_cluster<B, false>(A, A.lvl_cl[k], c0, own, linv, lane, 0, 1);
+      }
       if (t > 0 || c0 + CW < A.ncols) gen_grid_sync(A.bar, target, gridDim.x);
       stamp();
     }
