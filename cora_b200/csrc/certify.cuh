@@ -74,6 +74,20 @@ __global__ void __launch_bounds__(kThreads) k_tall_combine(const double *__restr
   }
 }
 
+// out_c = sum_k Y[:, k] M[k, c]: nd orthonormal vectors spanning the columns of the row-major iterate Y (N x r),
+// stored back to back like the Lanczos basis (M = V diag(ev^-1/2) of the Gram matrix Y^T Y)
+__global__ void __launch_bounds__(kThreads) k_span_basis(const double *__restrict__ Y, int r, const double *__restrict__ M,
+                                                         int nd, long long n, double *out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n * nd;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e / n);
+    const long long row = e - (long long)c * n;
+    double s = 0.0;
+    for (int k = 0; k < r; ++k) s = fma(Y[row * r + k], M[(size_t)k * nd + c], s);
+    out[e] = s;
+  }
+}
+
 // G = A^T B for row-major A (N x ra), B (N x rb): partials per CTA, last CTA reduces.
 __global__ void __launch_bounds__(kThreads) k_gram(const double *__restrict__ A, int ra,
                                                    const double *__restrict__ Bm, int rb, long long N,
@@ -310,14 +324,29 @@ struct LanczosResult {
   bool accepted = false;
 };
 
+// defl / ndefl: orthonormal vectors (stored like the basis) that are projected out of the start vector and of every
+// operator product: the search runs in their orthogonal complement.  certify_resident passes an orthonormal basis of
+// span(Y): at a critical point S Y = 0, so these r zero-eigenvalue directions are the closest competitors of a
+// slightly negative lambda_min under shift-and-invert and carry no negative curvature.  (The reference seeds its
+// block eigen-solver with Y -- the bootstrap of src/CORA.cpp:155-168 -- for the same reason: to dispose of them.)
 template <typename Op, typename Rayleigh, typename Accept>
 inline LanczosResult device_lanczos(H *h, Op op, Rayleigh rayleigh, Accept accept, bool pick_largest, int kmax,
-                                    DevBuf<double> &basis, double *w, double *xout, unsigned seed) {
+                                    DevBuf<double> &basis, double *w, double *xout, unsigned seed,
+                                    const double *defl = nullptr, int ndefl = 0) {
   const long long N = h->DL.N;
   const int grid = std::max(1, std::min(h->sm_count * 4, (int)((N + 255) / 256)));
   DevBuf<double> part, coef;
-  part.alloc((size_t)grid * (kmax + 1));
-  coef.alloc(kmax + 1);
+  part.alloc((size_t)grid * (std::max(kmax, ndefl) + 1));
+  coef.alloc(std::max(kmax, ndefl) + 1);
+  auto deflate = [&](double *v) {
+    if (ndefl <= 0) return;
+    for (int pass = 0; pass < 2; ++pass) {
+      k_tall_dots<<<grid, kThreads, 0, h->stream>>>(defl, ndefl, N, v, part.p, h->d_counter.p + 2, coef.p);
+      check_launch(h);
+      k_tall_axpy<<<flat_grid(h, N), kThreads, 0, h->stream>>>(defl, ndefl, N, coef.p, v);
+      check_launch(h);
+    }
+  };
   if (basis.n < (size_t)(kmax + 1) * N) basis.alloc((size_t)(kmax + 1) * N);
   {  // random start (the reference seeds LOBPCG with Matrix::Random; any start is admissible)
     std::mt19937_64 gen(seed);
@@ -329,12 +358,20 @@ inline LanczosResult device_lanczos(H *h, Op op, Rayleigh rayleigh, Accept accep
     for (auto &v : x) v /= nrm;
     CUDA_CHECK(cudaMemcpyAsync(basis.p, x.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (ndefl > 0) {
+      deflate(basis.p);
+      launch_dot2(h, basis.p, basis.p, nullptr, nullptr, N, SC_TMP);
+      read_scal(h);
+      const double n2 = std::sqrt(std::max(h->h_scal[SC_TMP], 1e-300));
+      launch_axpby(h, 1.0 / n2, basis.p, 0.0, nullptr, basis.p, N);
+    }
   }
   std::vector<double> al, be, hc(kmax + 1);
   LanczosResult R;
   for (int k = 0; k < kmax; ++k) {
     double *q = basis.p + (size_t)k * N;
     op(q, w);
+    deflate(w);
     // two passes of classical Gram-Schmidt against the whole basis (full re-orthogonalisation)
     double alpha = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
@@ -383,6 +420,7 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
   const long long N = h->DL.N;
   double *X = h->ws[V_X].p;
   // singular-value ratio of Y (src/CORA_problem.cpp:1039-1049) from the r x r Gram matrix
+  std::vector<double> spanM;  // r x r: V diag(ev^-1/2), columns map Y to an orthonormal basis of its span
   {
     std::vector<double> G = gram_host(h, X, r, X, r), ev, V;
     sym_eig_jacobi(r, G, ev, V);
@@ -391,6 +429,9 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
       out.branch = CORA_B200_CERT_SV_RATIO;
       return out;
     }
+    spanM.assign((size_t)r * r, 0.0);
+    for (int k = 0; k < r; ++k)
+      for (int c = 0; c < r; ++c) spanM[(size_t)k * r + c] = V[(size_t)k * r + c] / std::sqrt(ev[c]);
   }
   compute_lambda(h, X, r);
   DevLayout LS = build_certificate_layout(h, 0.0);  // values of S on Q's structure
@@ -427,6 +468,16 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
     return out;
   }
   const int kmax = (int)std::min<long long>(std::max(8, max_iters), N - 1);
+  // orthonormal basis of span(Y), projected out of the eigen-search (see device_lanczos)
+  DevBuf<double> spanY, spanMd;
+  int ndefl = 0;
+  if (N > 2 * (long long)r + 2) {
+    spanMd.upload(spanM, h->stream);
+    spanY.alloc((size_t)N * r);
+    k_span_basis<<<flat_grid(h, N * r), kThreads, 0, h->stream>>>(X, r, spanMd.p, r, N, spanY.p);
+    check_launch(h);
+    ndefl = r;
+  }
   if (chain) {
     // shift-and-invert: the largest eigenvalue of (S + sigma I)^-1 is 1 / (lambda_min(S) + sigma)
     double sigma = std::max(eta, 1e-12);
@@ -440,16 +491,32 @@ inline CertOut certify_resident(H *h, int r, double eta, int max_iters, int verb
     }
     if (!C) throw Error(CORA_B200_ERUNTIME, "certification: could not shift S to positive definiteness");
     auto op = [&](const double *q, double *y) { chain_solve(h, C, q, y, 1, nullptr); };
-    LanczosResult L = device_lanczos(h, op, rayleigh, accept, /*pick_largest=*/true, std::min(kmax, 80), basis, w, x, 12345u);
+    LanczosResult L = device_lanczos(h, op, rayleigh, accept, /*pick_largest=*/true, std::min(kmax, 80), basis, w, x, 12345u,
+                                     spanY.p, ndefl);
+    if (!accept(L.theta_S) && ndefl > 0) {
+      // Y is not a critical point (TNT stopped on the relative decrease): S Y != 0 and the negative curvature may
+      // live partly in span(Y).  S + eta I failed the Cholesky test, so a direction exists: search the whole space.
+      const int64_t s0 = L.steps;
+      L = device_lanczos(h, op, rayleigh, accept, /*pick_largest=*/true, std::min(kmax, 80), basis, w, x, 12345u);
+      L.steps += (int)s0;
+    }
     release_chain_chol(h, C);
     out.iters = L.steps;
     out.theta = L.theta_S;
     out.have_x = true;
-    out.branch = CORA_B200_CERT_EIGENPAIR;
+    // (x' S x >= -eta/2 after a full search: the direction is not a verified descent direction; the caller must not
+    //  escape along it)
+    out.branch = accept(L.theta_S) ? CORA_B200_CERT_EIGENPAIR : CORA_B200_CERT_INCONCLUSIVE;
     if (verbose) std::printf("  certify: shift-invert Lanczos sigma=%.3e steps=%d theta=%.6e\n", sigma, L.steps, L.theta_S);
   } else {
     auto op = [&](const double *q, double *y) { Sx(q, y); };
-    LanczosResult L = device_lanczos(h, op, rayleigh, accept, /*pick_largest=*/false, std::min(kmax, 400), basis, w, x, 12345u);
+    LanczosResult L = device_lanczos(h, op, rayleigh, accept, /*pick_largest=*/false, std::min(kmax, 400), basis, w, x, 12345u,
+                                     spanY.p, ndefl);
+    if (!accept(L.theta_S) && ndefl > 0) {
+      const int64_t s0 = L.steps;
+      L = device_lanczos(h, op, rayleigh, accept, /*pick_largest=*/false, std::min(kmax, 400), basis, w, x, 12345u);
+      L.steps += (int)s0;
+    }
     out.iters = L.steps;
     out.theta = L.theta_S;
     out.have_x = true;
@@ -523,7 +590,11 @@ inline void debug_min_eigenpair(H *h, int max_iters, double *theta, double *x_ou
 inline void certify_host(H *h, int r, const double *Y, double eta, int nx, const double *bootstrap,
                          int bootstrap_cols, int max_iters, int *is_certified, double *theta, double *x,
                          double *all_eigvecs, int cap, int *ncols, int64_t *num_iters) {
-  (void)nx; (void)bootstrap; (void)bootstrap_cols;  // block size / bootstrap of the reference's LOBPCG
+  // nx / bootstrap: block size and initial block of the reference's LOBPCG (src/CORA.cpp:155-168: Y itself on the
+  // first loop, the last eigenvector block afterwards).  The single-vector Lanczos here has no block to seed; what the
+  // bootstrap buys the reference -- getting the zero-eigenvalue directions span(Y) out of the way -- is done by
+  // projecting span(Y) out of the search (certify_resident), for every call, from the iterate itself.
+  (void)nx; (void)bootstrap; (void)bootstrap_cols;
   ensure_workspace(h, r);
   h->resident_r = 0;
   import_matrix(h, Y, r, h->ws[V_X].p, r);

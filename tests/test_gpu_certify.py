@@ -219,3 +219,22 @@ def test_psd_test_matches_dense_eigenvalues(lib):
         assert h.psd_test(-lam_min * 1.05, Y) is True
         assert h.psd_test(-lam_min * 0.95, Y) is False
         assert h.psd_test(1e-6, Y) is False
+
+
+def test_eigen_search_runs_in_the_complement_of_span_Y(lib):
+    """The direction of negative curvature is searched in the orthogonal complement of span(Y) (the r zero-eigenvalue
+    directions of S at a critical point; what the reference's bootstrap with Y, src/CORA.cpp:155-168, disposes of):
+    the returned vector is orthogonal to every column of Y, has unit norm, and x' S x < -eta/2 on the oracle's S."""
+    p = make_synthetic(n=300, l=3, m=150, d=3, seed=9, rank=4)
+    p.update_problem_data()
+    x0 = p.random_initial_guess(np.random.default_rng(2))
+    with make_handle(p) as h:
+        Y = h.tnt(x0, _params(max_iterations=60)).x
+        eta = 1e-5
+        c = h.certify_solution(Y, eta, 10)
+    assert not c.is_certified
+    assert abs(np.linalg.norm(c.x) - 1.0) <= 1e-10
+    assert np.abs(Y.T @ c.x).max() <= 1e-9 * np.linalg.norm(Y, axis=0).max()
+    S = p.certificate_matrix(Y)
+    th = float(c.x @ (S @ c.x))
+    assert abs(th - c.theta) <= 1e-8 * max(1.0, abs(th)) and th < -eta / 2
