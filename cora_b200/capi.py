@@ -127,7 +127,8 @@ SYMBOLS = [
     "cora_b200_odometry_initialization", "cora_b200_save_solution", "cora_b200_debug_min_eigenpair", "cora_b200_psd_test",
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
     "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_debug_factor_stats",
-    "cora_b200_set_formulation", "cora_b200_variable_rows", "cora_b200_translation_explicit_solution", "cora_b200_phase_profile", "cora_b200_get_work_vector",
+    "cora_b200_set_formulation", "cora_b200_variable_rows", "cora_b200_translation_explicit_solution",
+    "cora_b200_device_vectors", "cora_b200_row_order", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
     "cora_b200_select_best", "cora_b200_nccl_unique_id", "cora_b200_nccl_init", "cora_b200_nccl_destroy",
 ]
@@ -623,6 +624,19 @@ class Handle:
     def get_work_vector(self, which, r):
         out = np.empty((self.rows, r), order="F")
         _check(self._lib.cora_b200_get_work_vector(self._h, C.c_int(which), C.c_int(r), _p(out)))
+        return out
+
+    def device_vectors(self, r):
+        """(x_ptr, qx_ptr): raw device addresses of the resident iterate and of Q*X, N x r row-major in the internal
+        row order (row_order()); marks rank r resident."""
+        x, qx = C.c_void_p(), C.c_void_p()
+        _check(self._lib.cora_b200_device_vectors(self._h, C.c_int(r), C.byref(x), C.byref(qx)))
+        return x.value, qx.value
+
+    def row_order(self):
+        """internal_to_reference[i] = reference row held by internal row i."""
+        out = np.zeros(self.N, dtype=np.int32)
+        _check(self._lib.cora_b200_row_order(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
     def spmm_resident(self, reps):

@@ -172,6 +172,27 @@ extern "C" int cora_b200_get_work_vector(cora_b200_t *h, int which, int r, doubl
   API_END
 }
 
+// Device pointers of the resident iterate X and of Q X in the INTERNAL layout (N x r row-major, rows in the order
+// cora_b200_row_order reports): lets a multi-GPU caller exchange rows GPU to GPU (row-partitioned product,
+// cora_b200/rowpart.py) without a host round trip.  Marks rank r as resident.
+extern "C" int cora_b200_device_vectors(cora_b200_t *h, int r, double **x, double **qx) {
+  API_BEGIN
+  require(h && x && qx, "NULL argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  ensure_workspace(h, r);
+  h->resident_r = r;
+  *x = h->ws[V_X].p;
+  *qx = h->ws[V_G].p;
+  API_END
+}
+
+extern "C" int cora_b200_row_order(const cora_b200_t *h, int32_t *internal_to_reference) {
+  API_BEGIN
+  require(h && internal_to_reference, "NULL argument");
+  std::copy(h->HL.int2ref.begin(), h->HL.int2ref.end(), internal_to_reference);
+  API_END
+}
+
 extern "C" int cora_b200_phase_profile_ctas(cora_b200_t *h, int capacity, double *max_us, double *median_us) {
   API_BEGIN
   require(h && max_us && median_us, "NULL argument");

@@ -221,6 +221,13 @@ int cora_b200_phase_profile(cora_b200_t *h, int capacity, double *total_us, int6
  * (every CTA's clock; the persistent kernel runs as fast as its slowest CTA allows). */
 int cora_b200_phase_profile_ctas(cora_b200_t *h, int capacity, double *max_us, double *median_us);
 
+/* Device pointers of the resident iterate X and of Q*X (as left by cora_b200_spmm_resident) in the library's
+ * internal layout: N x r row-major, row i of the buffers = reference row internal_to_reference[i]
+ * (cora_b200_row_order).  For GPU-to-GPU row exchange in the row-partitioned product (SURVEY 8f-4,
+ * cora_b200/rowpart.py); the pointers stay valid until the workspace grows (a larger rank) or the handle dies. */
+int cora_b200_device_vectors(cora_b200_t *h, int r, double **x, double **qx);
+int cora_b200_row_order(const cora_b200_t *h, int32_t *internal_to_reference /* N */);
+
 /* timed data-matrix products on the resident iterate: reps launches of Q*X, returns
  * the CUDA-event milliseconds for all of them (roofline leg of bench.py) */
 int cora_b200_spmm_resident(cora_b200_t *h, int reps, float *ms_total);

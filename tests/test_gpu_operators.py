@@ -241,3 +241,35 @@ def test_full_size_tnt_against_cpu_port(lib):
     assert np.abs(np.einsum("nir,njr->nij", B, B) - np.eye(d)).max() < 1e-10     # rotations on the Stiefel manifold
     rows = got.x[d * n: d * n + m]
     assert np.abs(np.linalg.norm(rows, axis=1) - 1).max() < 1e-12               # range rows on the sphere
+
+
+@pytest.mark.gpu
+def test_row_partition_device_buffers(lib):
+    """The device side of the row-partitioned product (cora_b200/rowpart.py) on one GPU: the raw device
+    buffers + row order the C-ABI exposes, a two-slab partition whose 'exchange' is done by hand between two handles of
+    this process, against the full product."""
+    import torch
+    from cora_b200 import capi, rowpart, synthetic
+    d, n, l, m, r = 3, 900, 4, 500, 5
+    arrays, _ = synthetic.make_arrays(n, l, m, d=d, seed=3, loop_closures=[(10, 700), (449, 451)])
+    Q = capi.assemble(d, n, l, arrays)
+    X = np.random.default_rng(0).standard_normal((Q.shape[0], r))
+    with capi.Handle(d, n, len(arrays["rg_w"]), n + l, Q, preconditioner=capi.PRECON_JACOBI) as hf:
+        Y = hf.data_matrix_product(X)
+    parts = [rowpart.LocalProblem(d, n, l, arrays, 2, g) for g in range(2)]
+    lm = 0
+    for P in parts:
+        Ql = capi.assemble(d, P.n_loc, l, P.arrays)
+        with capi.Handle(d, P.n_loc, P.m_loc, P.n_loc + l, Ql, preconditioner=capi.PRECON_JACOBI) as h:
+            h.set_iterate(np.asfortranarray(X[P.local_to_global]))   # (ghost rows filled from the global vector)
+            no_exchange = [[np.zeros(0, np.int64)] * 2] * 2
+            op, x, y, row_of = rowpart.device_product(h, P, no_exchange, r, None)
+            assert x.shape == (P.N_loc, r) and x.is_cuda
+            np.testing.assert_array_equal(x.cpu().numpy()[row_of], X[P.local_to_global])   # the buffer IS the iterate
+            op.product_fn()
+            torch.cuda.synchronize()
+            yl = y.cpu().numpy()[row_of]
+            own = P.owned
+            assert np.abs(yl[own] - Y[P.local_to_global[own]]).max() <= 1e-12 * np.abs(Y).max()
+            lm = lm + yl[P.landmark_rows]
+    assert np.abs(lm - Y[parts[0].local_to_global[parts[0].landmark_rows]]).max() <= 1e-12 * np.abs(Y).max()
