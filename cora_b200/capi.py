@@ -128,7 +128,8 @@ SYMBOLS = [
     "cora_b200_assemble", "cora_b200_snapshot_iterate", "cora_b200_restore_iterate", "cora_b200_profile_hessvec",
     "cora_b200_profile_read", "cora_b200_debug_chain_host", "cora_b200_debug_factor_stats",
     "cora_b200_set_formulation", "cora_b200_variable_rows", "cora_b200_translation_explicit_solution",
-    "cora_b200_device_vectors", "cora_b200_row_order", "cora_b200_phase_profile", "cora_b200_get_work_vector",
+    "cora_b200_device_vectors", "cora_b200_row_order",
+    "cora_b200_peer_create", "cora_b200_peer_connect", "cora_b200_peer_product", "cora_b200_peer_destroy", "cora_b200_phase_profile", "cora_b200_get_work_vector",
     "cora_b200_pyfg_parse", "cora_b200_pyfg_sizes", "cora_b200_pyfg_arrays", "cora_b200_pyfg_free",
     "cora_b200_select_best", "cora_b200_nccl_unique_id", "cora_b200_nccl_init", "cora_b200_nccl_destroy",
 ]
@@ -188,6 +189,36 @@ class NcclComm:
         if self._c:
             load().cora_b200_nccl_destroy(self._c)
             self._c = C.c_void_p()
+
+
+class PeerProduct:
+    """Row-partitioned product over peer-mapped memory (cora_b200_peer_*): create -> exchange `handles` -> connect ->
+    product(reps) -> close."""
+
+    def __init__(self, handle, r, n_landmark_rows):
+        self._lib = load()
+        self._p = C.c_void_p()
+        buf = C.create_string_buffer(192)
+        _check(self._lib.cora_b200_peer_create(handle._h, C.c_int(r), C.c_int(n_landmark_rows), C.byref(self._p), buf))
+        self.handles = buf.raw
+
+    def connect(self, world, rank, all_handles: bytes, ghost_peer, ghost_src, ghost_dst, lm_rows):
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        gp, gs, gd, lm = i32(ghost_peer), i32(ghost_src), i32(ghost_dst), i32(lm_rows)
+        P = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        assert len(all_handles) == 192 * world
+        _check(self._lib.cora_b200_peer_connect(self._p, C.c_int(world), C.c_int(rank), C.c_char_p(all_handles),
+                                                C.c_int(len(gp)), P(gp), P(gs), P(gd), P(lm)))
+
+    def product(self, reps=1):
+        ms = C.c_float()
+        _check(self._lib.cora_b200_peer_product(self._p, C.c_int(reps), C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self._p:
+            self._lib.cora_b200_peer_destroy(self._p)
+            self._p = C.c_void_p()
 
 
 def device_count() -> int:

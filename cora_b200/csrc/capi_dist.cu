@@ -172,3 +172,125 @@ extern "C" int cora_b200_gather_best_resident(void *nccl_comm, cora_b200_t *h, i
   if (winner_f) *winner_f = fs[win];
   API_END
 }
+
+// ------------------------------------------------------------ row-partitioned product over peer memory ----
+#include "peer_product.cuh"
+
+struct cora_b200_peer {
+  PeerCtx c;
+};
+
+namespace {
+constexpr size_t kIpc = sizeof(cudaIpcMemHandle_t);  // 64 bytes
+}
+
+// Create the peer context of this rank and export its three allocations: [operand X | landmark staging | flags],
+// 3 x 64 bytes into `handles`.  n_landmark_rows: landmark rows of the local problem (staging size).
+extern "C" int cora_b200_peer_create(cora_b200_t *h, int r, int n_landmark_rows, cora_b200_peer_t **out, void *handles) {
+  API_BEGIN
+  require(h && out && handles && r > 0 && n_landmark_rows >= 0, "bad argument");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  ensure_workspace(h, r);
+  h->resident_r = r;
+  auto *p = new cora_b200_peer();
+  PeerCtx &c = p->c;
+  c.h = h; c.r = r; c.n_lm = n_landmark_rows;
+  c.stage.alloc((size_t)std::max(n_landmark_rows, 1) * r);
+  c.flags.alloc(2 * kPeerMaxWorld);
+  c.err.alloc(1);
+  CUDA_CHECK(cudaMemset(c.flags.p, 0, 2 * kPeerMaxWorld * sizeof(unsigned long long)));
+  CUDA_CHECK(cudaMemset(c.err.p, 0, sizeof(int)));
+  cudaIpcMemHandle_t hx, hs, hf;
+  CUDA_CHECK(cudaIpcGetMemHandle(&hx, h->ws[V_X].p));
+  CUDA_CHECK(cudaIpcGetMemHandle(&hs, c.stage.p));
+  CUDA_CHECK(cudaIpcGetMemHandle(&hf, c.flags.p));
+  std::memcpy((char *)handles, &hx, kIpc);
+  std::memcpy((char *)handles + kIpc, &hs, kIpc);
+  std::memcpy((char *)handles + 2 * kIpc, &hf, kIpc);
+  *out = p;
+  API_END
+}
+
+// all_handles: world x 3 x 64 bytes (every rank's export, in rank order).  Plan: ghost row g of this rank's operand
+// (internal row ghost_dst[g]) is row ghost_src[g] of rank ghost_peer[g]'s operand; lm_rows: this rank's landmark rows.
+extern "C" int cora_b200_peer_connect(cora_b200_peer_t *p, int world, int rank, const void *all_handles, int n_ghost,
+                                      const int32_t *ghost_peer, const int32_t *ghost_src, const int32_t *ghost_dst,
+                                      const int32_t *lm_rows) {
+  API_BEGIN
+  require(p && all_handles && world > 0 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad argument");
+  PeerCtx &c = p->c;
+  CUDA_CHECK(cudaSetDevice(c.h->device));
+  c.world = world; c.rank = rank;
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) {
+      c.peer_x[q] = c.h->ws[V_X].p; c.peer_stage[q] = c.stage.p; c.peer_flags[q] = c.flags.p;
+      continue;
+    }
+    cudaIpcMemHandle_t hx, hs, hf;
+    const char *base = (const char *)all_handles + (size_t)q * 3 * kIpc;
+    std::memcpy(&hx, base, kIpc); std::memcpy(&hs, base + kIpc, kIpc); std::memcpy(&hf, base + 2 * kIpc, kIpc);
+    void *px = nullptr, *ps = nullptr, *pf = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&px, hx, cudaIpcMemLazyEnablePeerAccess));
+    CUDA_CHECK(cudaIpcOpenMemHandle(&ps, hs, cudaIpcMemLazyEnablePeerAccess));
+    CUDA_CHECK(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+    c.opened[3 * q] = px; c.opened[3 * q + 1] = ps; c.opened[3 * q + 2] = pf;
+    c.peer_x[q] = (const double *)px; c.peer_stage[q] = (const double *)ps; c.peer_flags[q] = (unsigned long long *)pf;
+  }
+  c.n_ghost = n_ghost;
+  auto up = [&](DevBuf<int> &b, const int32_t *src, int n) {
+    std::vector<int> t(src, src + std::max(n, 0));
+    b.upload(t, c.h->stream);
+  };
+  up(c.ghost_peer, ghost_peer, n_ghost); up(c.ghost_src, ghost_src, n_ghost); up(c.ghost_dst, ghost_dst, n_ghost);
+  up(c.lm_rows, lm_rows, c.n_lm);
+  CUDA_CHECK(cudaStreamSynchronize(c.h->stream));
+  for (int g = 0; g < n_ghost; ++g) require(ghost_peer[g] >= 0 && ghost_peer[g] < world, "ghost owner out of range");
+  API_END
+}
+
+// `reps` products Q X -> the handle's Q*X buffer, each = barrier + halo pull | local rows | barrier + landmark sum,
+// all enqueued back to back on the handle's stream; returns the CUDA-event milliseconds of the whole batch.
+extern "C" int cora_b200_peer_product(cora_b200_peer_t *p, int reps, float *ms_total) {
+  API_BEGIN
+  require(p && reps > 0, "bad argument");
+  PeerCtx &c = p->c;
+  H *h = c.h;
+  require(c.world > 0, "cora_b200_peer_connect has not been called");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  PeerPtrs P{};
+  for (int q = 0; q < c.world; ++q) { P.x[q] = c.peer_x[q]; P.stage[q] = c.peer_stage[q]; P.flags[q] = c.peer_flags[q]; }
+  cudaStream_t s = h->stream;
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+  persistent_configure(h, c.r);
+  CUDA_CHECK(cudaEventRecord(e0, s));
+  for (int i = 0; i < reps; ++i) {
+    ++c.epoch;
+    k_peer_halo<<<1, 256, 0, s>>>(P, c.world, c.rank, c.epoch, c.r, c.n_ghost, c.ghost_peer.p, c.ghost_src.p, c.ghost_dst.p,
+                                  h->ws[V_X].p, c.err.p);
+    check_launch(h);
+    spmm_persistent(h, c.r, h->ws[V_X].p, h->ws[V_G].p, 1, /*sync=*/false);
+    k_peer_reduce<<<1, 256, 0, s>>>(P, c.world, c.rank, c.epoch, c.r, c.n_lm, c.lm_rows.p, c.stage.p, h->ws[V_G].p, c.err.p);
+    check_launch(h);
+  }
+  CUDA_CHECK(cudaEventRecord(e1, s));
+  CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  int err = 0;
+  CUDA_CHECK(cudaMemcpy(&err, c.err.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) throw Error(CORA_B200_ERUNTIME, "row-partitioned product: a peer did not reach the barrier within 5 s");
+  if (ms_total) *ms_total = ms;
+  API_END
+}
+
+extern "C" int cora_b200_peer_destroy(cora_b200_peer_t *p) {
+  if (!p) return CORA_B200_OK;
+  cudaSetDevice(p->c.h->device);
+  cudaStreamSynchronize(p->c.h->stream);
+  for (void *q : p->c.opened)
+    if (q) cudaIpcCloseMemHandle(q);
+  delete p;
+  return CORA_B200_OK;
+}

@@ -522,7 +522,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
 }
 
 // reps x (out = Q X) through the tile pipeline of the persistent kernel; returns the CUDA-event milliseconds
-inline float spmm_persistent(H *h, int r, const double *X, double *out, int reps) {
+inline float spmm_persistent(H *h, int r, const double *X, double *out, int reps, bool sync = true) {
   persistent_configure(h, r);
   const int G = h->persistent_grid;
   const size_t nlp = 2 * (size_t)std::max(h->DL.numChunks, 1) * h->DL.D1 * h->ws_r;
@@ -543,6 +543,7 @@ inline float spmm_persistent(H *h, int r, const double *X, double *out, int reps
   CUDA_CHECK(cudaLaunchCooperativeKernel(h->persistent_spmm_kfn, dim3(G), dim3(h->persistent_threads), args,
                                          h->persistent_smem, h->stream));
   check_launch(h);
+  if (!sync) return 0.f;  // enqueued only (peer_product.cuh chains it between its exchange kernels)
   CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   CUDA_CHECK(cudaEventSynchronize(h->ev1));
   float ms = 0.f;

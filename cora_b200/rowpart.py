@@ -179,3 +179,41 @@ def device_product(handle, part, send_lists, r, dist, group=None):
         handle.spmm_resident(1)    # (returns after its own CUDA events: the result is complete)
 
     return RowPartitionedProduct(part, send_lists, x, y, row_of, product, dist, group), x, y, row_of
+
+
+def internal_rows_of_pose(d, local_pose_id):
+    """Rows of a pose in the library's internal (pose-major) layout: d rotation rows, then the translation row
+    (cora_b200/csrc/layout.hpp); checked against cora_b200_row_order by peer_product()."""
+    return (d + 1) * int(local_pose_id) + np.arange(d + 1)
+
+
+def peer_product(handle, parts, rank, r, dist, group=None):
+    """The same product with the library's own exchange kernels over peer-mapped memory (cora_b200_peer_*,
+    cora_b200/csrc/peer_product.cuh): no collective per product.  `dist` only ships the 192-byte IPC handles once."""
+    from . import capi
+    P = parts[rank]
+    world, d = P.world, P.d
+    int2ref = handle.row_order().astype(np.int64)
+    row_of = np.empty(P.N_loc, dtype=np.int64)
+    row_of[int2ref] = np.arange(P.N_loc)
+    # the pose-major formula every rank uses for its PEERS' buffers must hold for this rank's own buffer
+    probe = [0, P.n_own - 1, P.n_loc - 1]
+    for p in probe:
+        assert np.array_equal(row_of[P.pose_rows([p])], internal_rows_of_pose(d, p)), "unexpected internal row order"
+    assert np.array_equal(row_of[P.landmark_rows], (d + 1) * P.n_loc + np.arange(P.l)), "unexpected landmark rows"
+    ghosts = P.poses[P.n_own:]
+    gp, gs, gd = [], [], []
+    for k, g in enumerate(ghosts):
+        q = int(P.ghost_owner[k])
+        gp += [q] * (d + 1)
+        gs += list(internal_rows_of_pose(d, int(g) - int(P.bounds[q])))   # owned poses come first on their owner
+        gd += list(internal_rows_of_pose(d, P.n_own + k))
+    pp = capi.PeerProduct(handle, r, P.l)
+    if world > 1:
+        allh = [None] * world
+        dist.all_gather_object(allh, pp.handles, group=group)
+        allh = b"".join(allh)
+    else:
+        allh = pp.handles
+    pp.connect(world, rank, allh, gp, gs, gd, row_of[P.landmark_rows])
+    return pp, row_of

@@ -228,6 +228,22 @@ int cora_b200_phase_profile_ctas(cora_b200_t *h, int capacity, double *max_us, d
 int cora_b200_device_vectors(cora_b200_t *h, int r, double **x, double **qx);
 int cora_b200_row_order(const cora_b200_t *h, int32_t *internal_to_reference /* N */);
 
+/* Row-partitioned product of ONE problem across the GPUs of a node with the exchanges done by the library's own
+ * kernels over peer-mapped memory (cudaIpc*, NVLink loads) instead of collectives -- cora_b200/csrc/peer_product.cuh.
+ * Each rank: cora_b200_peer_create on its LOCAL handle (exports 3 x 64-byte IPC handles), ship the handles of all
+ * ranks to everybody over any channel, cora_b200_peer_connect with the plan (which internal row of which peer's
+ * operand each ghost row is; the rank's landmark rows), then cora_b200_peer_product: per product a cross-GPU flag
+ * barrier + pull of the ghost rows, the persistent SpMM kernel on the rank's rows, a second barrier + the sum of all
+ * ranks' partial landmark rows in rank order.  Replaces the one-core `data_matrix_ * Y` of
+ * src/CORA_problem.cpp:742-757 for a problem sharded by rows. */
+typedef struct cora_b200_peer cora_b200_peer_t;
+int cora_b200_peer_create(cora_b200_t *h, int r, int n_landmark_rows, cora_b200_peer_t **out, void *handles /* 192 B */);
+int cora_b200_peer_connect(cora_b200_peer_t *p, int world, int rank, const void *all_handles /* world x 192 B */,
+                           int n_ghost_rows, const int32_t *ghost_peer, const int32_t *ghost_src_row,
+                           const int32_t *ghost_dst_row, const int32_t *landmark_rows);
+int cora_b200_peer_product(cora_b200_peer_t *p, int reps, float *ms_total);
+int cora_b200_peer_destroy(cora_b200_peer_t *p);
+
 /* timed data-matrix products on the resident iterate: reps launches of Q*X, returns
  * the CUDA-event milliseconds for all of them (roofline leg of bench.py) */
 int cora_b200_spmm_resident(cora_b200_t *h, int reps, float *ms_total);

@@ -273,3 +273,24 @@ def test_row_partition_device_buffers(lib):
             assert np.abs(yl[own] - Y[P.local_to_global[own]]).max() <= 1e-12 * np.abs(Y).max()
             lm = lm + yl[P.landmark_rows]
     assert np.abs(lm - Y[parts[0].local_to_global[parts[0].landmark_rows]]).max() <= 1e-12 * np.abs(Y).max()
+
+
+@pytest.mark.gpu
+def test_peer_memory_product_world_size_one(lib):
+    """cora_b200_peer_* (the row-partitioned product with the library's own exchange kernels, peer_product.cuh) at
+    world size 1: flag barrier with itself, no ghosts, landmark 'sum' over one rank -- equals the plain product.
+    (N > 1 runs on 2/4/8 GPUs by scripts/rowpart_bench.py, which asserts 1e-12 against the full product.)"""
+    from cora_b200 import capi, rowpart, synthetic
+    d, n, l, m, r = 3, 700, 3, 300, 5
+    arrays, _ = synthetic.make_arrays(n, l, m, d=d, seed=4)
+    Q = capi.assemble(d, n, l, arrays)
+    X = np.random.default_rng(1).standard_normal((Q.shape[0], r))
+    parts = [rowpart.LocalProblem(d, n, l, arrays, 1, 0)]
+    with capi.Handle(d, n, len(arrays["rg_w"]), n + l, Q, preconditioner=capi.PRECON_JACOBI) as h:
+        Y = h.data_matrix_product(X)
+        h.set_iterate(np.asfortranarray(X))
+        pp, row_of = rowpart.peer_product(h, parts, 0, r, None)
+        assert pp.product(3) > 0
+        Y2 = h.get_work_vector(1, r)
+        pp.close()
+    assert np.abs(Y2 - Y).max() <= 1e-13 * np.abs(Y).max()
