@@ -257,6 +257,14 @@ def roofline_cfg5(torch, dist, world, local, stream, peak, n=1_000_000, reps=30)
     else:
         cg_all = float(cg)
     mxp, _ = ({}, {}) if not hasattr(h, "phase_profile_ctas") else (h.phase_profile_ctas(), None)
+    # N > 1: the same product with ONE problem sharded by rows over the ranks (cora_b200/rowpart.py):
+    # slabs of poses + ghost poses + replicated landmarks, exchanges by the library's kernels over peer-mapped memory
+    rowp = None
+    if world > 1:
+        try:
+            rowp = row_partitioned_cfg5(torch, dist, world, local, h, d, n, l, arrays, r, Q, reps)
+        except Exception as e:  # never lose the bench line over the extra record
+            rowp = {"error": "%s: %s" % (type(e).__name__, e)}
     h.close()
     traffic = None
     try:   # DRAM bytes per product from the committed ncu capture of this kernel on this workload (8 products per launch)
@@ -271,7 +279,7 @@ def roofline_cfg5(torch, dist, world, local, stream, peak, n=1_000_000, reps=30)
     gbs_cg = (cg * ab["cg_iter"] + outer * b_outer) / res.device_time / 1e9
     return {"workload": "synthetic %d-pose SE(3) + %d ranges, %d landmarks, rank %d (BASELINE configs[4]); one replica "
                         "per GPU" % (n, m, l, r),
-            "N": int(N), "nnz": int(Q.nnz), "replicas": world,
+            "N": int(N), "nnz": int(Q.nnz), "replicas": world, "row_partitioned": rowp,
             "spmm": {"us": 1e6 * t_spmm, "reps": reps, "algorithmic_bytes": ab["spmm"], "achieved_gbs": gbs_spmm,
                      "frac": gbs_spmm / peak, "aggregate_gbs": world * gbs_spmm, "traffic": traffic,
                      "traffic_kind": "committed ncu --set full capture (profiles/r02_spmm_1m_ncu_raw.csv), not measured in this run",
@@ -281,6 +289,45 @@ def roofline_cfg5(torch, dist, world, local, stream, peak, n=1_000_000, reps=30)
                              "cg_it_per_s_all_replicas": cg_all / t_cg,
                              "phases_us_slowest_cta": {k: v[0] for k, v in mxp.items()}},
             "peak_gbs": peak, "clocks": clocks}
+
+
+def row_partitioned_cfg5(torch, dist, world, local, h_full, d, n, l, arrays, r, Q, reps):
+    """One 1M-pose problem sharded by rows over the ranks: time per data-matrix product and error against the full
+    product of the rank's replica (h_full)."""
+    from cora_b200 import capi, rowpart
+    rank = dist.get_rank()
+    parts = [rowpart.LocalProblem(d, n, l, arrays, world, g) for g in range(world)]
+    P = parts[rank]
+    X = np.random.default_rng(1).standard_normal((P.N, r))
+    h_full.set_iterate(np.asfortranarray(X))
+    h_full.spmm_resident(1)
+    Yfull = h_full.get_work_vector(1, r)
+    Ql = capi.assemble(d, P.n_loc, l, P.arrays)
+    with capi.Handle(d, P.n_loc, P.m_loc, P.n_loc + l, Ql, preconditioner=capi.PRECON_JACOBI, device=local) as hl:
+        Xl = X[P.local_to_global].copy()
+        ghost = ~P.owned
+        ghost[P.landmark_rows] = False
+        Xl[ghost] = np.nan                      # only the exchange can make the product right
+        hl.set_iterate(np.asfortranarray(Xl))
+        pp, _ = rowpart.peer_product(hl, parts, rank, r, dist)
+        dist.barrier()
+        pp.product(1)
+        Yl = hl.get_work_vector(1, r)
+        rows = np.concatenate([np.nonzero(P.owned)[0], P.landmark_rows])
+        err = float(np.abs(Yl[rows] - Yfull[P.local_to_global[rows]]).max() / np.abs(Yfull).max())
+        pp.product(5)
+        dist.barrier()
+        us = 1e3 * pp.product(reps) / reps
+        pp.close()
+    v = torch.tensor([us, err], dtype=torch.float64, device="cuda")
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    return {"what": "ONE problem sharded by rows over the ranks (SURVEY 8f-4): slab of poses + ghost poses + replicated "
+                    "landmarks per rank; per product a cross-GPU flag barrier + pull of the ghost rows over peer-mapped "
+                    "memory, the persistent SpMM kernel on the rank's rows, barrier + rank-ordered sum of the partial "
+                    "landmark rows (cora_b200/csrc/peer_product.cuh) -- no collective",
+            "n_gpus": world, "us_per_product": float(v[0]), "max_rel_error_vs_full_product": float(v[1]),
+            "rows_per_rank": int(P.N_loc), "reps": reps,
+            "timing": "CUDA events around `reps` products enqueued back to back; max over ranks"}
 
 
 def spmv_cfg2(local, stream, reps=1000):
