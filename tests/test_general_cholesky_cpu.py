@@ -64,3 +64,36 @@ def test_general_psd_verdict_matches_dense_eigenvalues(lib):
     assert pd
     pd, _ = capi.debug_chain_host(p.d, p.n, p.m, p.n + p.l, p.Q, -1e-3, False)
     assert not pd
+
+
+def _two_robots(n=300, cut=140, loops=((5, 100), (20, 60), (150, 290), (200, 260))):
+    """Two robots: the odometry chain is cut between poses cut-1 and cut, loop closures inside each robot only, so the
+    pose graph has two connected components (coupled through the landmarks alone)."""
+    from cora_b200 import synthetic
+    arrays, gt = synthetic.make_arrays(n, 3, 150, d=3, seed=9, loop_closures=list(loops))
+    keep_rp = ~((arrays["rp_i"] == cut - 1) & (arrays["rp_j"] == cut))
+    keep_rot = ~((arrays["rot_i"] == cut - 1) & (arrays["rot_j"] == cut))
+    a = dict(arrays)
+    for k in ("rp_i", "rp_j", "rp_t", "rp_tau"):
+        a[k] = arrays[k][keep_rp]
+    for k in ("rot_i", "rot_j", "rot_R", "rot_kappa"):
+        a[k] = arrays[k][keep_rot]
+    return co.Problem.from_arrays(3, n, 3, a, preconditioner=co.REG_CHOLESKY)
+
+
+@pytest.mark.parametrize("name,p", [("two components", _two_robots()),
+                                    ("three poses, one closure", make_synthetic(n=3, l=1, m=2, d=2, seed=1, loop_closures=[(0, 2)])),
+                                    ("dense little graph", make_synthetic(n=9, l=0, m=0, d=3, seed=2,
+                                                                          loop_closures=[(i, j) for i in range(9) for j in range(i + 2, 9)]))],
+                         ids=["two components", "three poses", "dense"])
+def test_general_cholesky_edge_cases(lib, name, p):
+    from cora_b200 import capi
+    p.preconditioner = co.REG_CHOLESKY
+    p.update_problem_data()
+    st = capi.debug_factor_stats(p.d, p.n, p.m, p.n + p.l, p.Q)
+    assert st["chain"] == 0 and st["poses"] == p.n
+    V = np.random.default_rng(0).standard_normal((p.N, 3))
+    pd, Z = capi.debug_chain_host(p.d, p.n, p.m, p.n + p.l, p.Q, p.lambda_reg, True, V)
+    assert pd
+    ref = p.precondition(V)
+    assert np.abs(Z - ref).max() <= 1e-8 * np.abs(ref).max()

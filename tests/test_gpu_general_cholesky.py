@@ -8,7 +8,7 @@ import pytest
 from conftest import load_dataset, make_handle
 from oracle import cora_oracle as co
 from synth import make_synthetic
-from test_general_cholesky_cpu import _loops
+from test_general_cholesky_cpu import _loops, _two_robots
 
 pytestmark = pytest.mark.gpu
 
@@ -27,6 +27,10 @@ def _cases():
     yield "d3 near loops, no landmarks", make_synthetic(n=900, l=0, m=0, d=3, seed=4, loop_closures=_loops(900, 200, 3, near=12))
     yield "d3 hub pose (> 8 couplings)", make_synthetic(n=300, l=2, m=100, d=3, seed=6,
                                                         loop_closures=[(7, j) for j in range(20, 300, 9)])
+    yield "two robots (two components)", _two_robots()
+    yield "three poses, one closure", make_synthetic(n=3, l=1, m=2, d=2, seed=1, loop_closures=[(0, 2)])
+    yield "dense little graph", make_synthetic(n=9, l=0, m=0, d=3, seed=2,
+                                               loop_closures=[(i, j) for i in range(9) for j in range(i + 2, 9)])
     yield "tiers", load_dataset("tiers")
     yield "mrclam2", load_dataset("mrclam2")
 
