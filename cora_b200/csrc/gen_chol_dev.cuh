@@ -83,12 +83,15 @@ __device__ __forceinline__ void gen_grid_sync(unsigned long long *bar, unsigned 
 }
 
 // one cluster, one direction, one pass of CW columns.
-// part / nparts: in the thin upper levels of the tree (fewer clusters than CTAs) the kGenWarps warps of a CTA share
-// ONE cluster: each sums a slice of the off-diagonal products into its own copy of r (a single warp keeps only
-// ~8 loads in flight: measured 4400 cycles per batch of 64), warp 0 adds the copies in a fixed order and finishes.
+// part / nparts: in the thinner levels of the tree (fewer clusters than warps in the grid) groups of 2, 4 or 8
+// warps of a CTA share ONE cluster: each sums a slice of the off-diagonal products into its own copy of r (a single
+// warp keeps only ~8 loads in flight: measured 4400 cycles per batch of 64), the group leader adds the copies in a
+// fixed order, multiplies by the inverse, and all warps of the group push a slice of the column products.
 template <int B, bool FWD>
 __device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0, double *own, double *linv, int lane,
-                                            int part, int nparts) {
+                                            int part, int nparts, int bar_id) {
+  // barrier of the nparts warps that share this cluster (a named barrier: the groups of a CTA run independently)
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nparts * 32) : "memory"); };
   constexpr int BB = B * B, CW = 32 / B;
   const int dv = lane < 8 ? A.desc[(size_t)K * 8 + lane] : 0;
   const int p0 = __shfl_sync(0xffffffffu, dv, 0), nodes = __shfl_sync(0xffffffffu, dv, 1);
@@ -225,11 +228,53 @@ __device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0
       if (active) own[rrow * 32 + lane] -= run;
     }
   }
+  // push (forward sweep): c = L_wu y_u for the blocks of the cluster's columns whose row w lies outside (above) the
+  // cluster, written where the owner of row w will stream them; `res_tab`: the cluster's results in shared memory.
+  // In CTA mode every warp pushes a slice of the column blocks.
+  auto push = [&](const double *res_tab) {
+    const int e0c = __shfl_sync(0xffffffffu, dv, 4), nentc = __shfl_sync(0xffffffffu, dv, 5);
+    const unsigned char *ec = A.erow_b + e0c;
+    const int *c2r = A.col2row + e0c;
+    const double *Lc = A.Lval + (size_t)e0c * BB;
+    const int nb_c = (nentc + kGenBatch - 1) / kGenBatch;
+    const int cbeg = (int)((long long)nb_c * part / nparts) * kGenBatch;
+    const int cend = min(nentc, (int)((long long)nb_c * (part + 1) / nparts) * kGenBatch);
+    for (int t0 = cbeg; t0 < cend; t0 += kGenBatch) {
+      int fl[kGenBatch], dst[kGenBatch];
+      double Lv[kGenBatch][B];
+#pragma unroll
+      for (int k = 0; k < kGenBatch; ++k) {
+        const int t = min(t0 + k, nentc - 1);
+        fl[k] = (int)ec[t];
+        dst[k] = c2r[t];
+        GEN_KEEP(fl[k]); GEN_KEEP(dst[k]);
+#pragma unroll
+        for (int b = 0; b < B; ++b) { Lv[k][b] = Lc[(size_t)t * BB + al * B + b]; GEN_KEEPD(Lv[k][b]); }
+      }
+      GEN_FENCE();
+#pragma unroll
+      for (int k = 0; k < kGenBatch; ++k)
+        if (t0 + k < nentc && !(fl[k] & 0x80) && active) {
+          const double *y = res_tab + (fl[k] & 0x7f) * 32 + cc;
+          double s = 0.0;
+#pragma unroll
+          for (int b = 0; b < B; ++b) s += Lv[k][b] * y[b * CW];
+          A.cbuf[((size_t)dst[k] * B + a) * ncols + c] = s;
+        }
+    }
+    __syncwarp();
+  };
   __syncwarp();
-  if (nparts > 1) {  // (uniform over the CTA)
-    __syncthreads();
-    if (part != 0) return;
+  if (nparts > 1) {  // (uniform over the group)
+    group_sync();
     const int stride = gen_smem_doubles_per_warp<B>();
+    if (part != 0) {
+      if (FWD) {
+        group_sync();                  // the leader has combined, multiplied by the inverse and stored the results
+        push(own - (size_t)part * stride);
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < kGenClusterMax; ++j)
       if (j < nodes) {
@@ -274,36 +319,8 @@ __device__ __forceinline__ void gen_cluster(const GenSolveArgs &A, int K, int c0
     }
   __syncwarp();
   if (FWD) {
-    // push: c = L_wu y_u for the blocks of the cluster's columns whose row w lies outside (above) the cluster,
-    // written where the owner of row w will stream them
-    const int e0c = __shfl_sync(0xffffffffu, dv, 4), nentc = __shfl_sync(0xffffffffu, dv, 5);
-    const unsigned char *ec = A.erow_b + e0c;
-    const int *c2r = A.col2row + e0c;
-    const double *Lc = A.Lval + (size_t)e0c * BB;
-    for (int t0 = 0; t0 < nentc; t0 += kGenBatch) {
-      int fl[kGenBatch], dst[kGenBatch];
-      double Lv[kGenBatch][B];
-#pragma unroll
-      for (int k = 0; k < kGenBatch; ++k) {
-        const int t = min(t0 + k, nentc - 1);
-        fl[k] = (int)ec[t];
-        dst[k] = c2r[t];
-        GEN_KEEP(fl[k]); GEN_KEEP(dst[k]);
-#pragma unroll
-        for (int b = 0; b < B; ++b) { Lv[k][b] = Lc[(size_t)t * BB + al * B + b]; GEN_KEEPD(Lv[k][b]); }
-      }
-      GEN_FENCE();
-#pragma unroll
-      for (int k = 0; k < kGenBatch; ++k)
-        if (t0 + k < nentc && !(fl[k] & 0x80) && active) {
-          const double *y = own + (fl[k] & 0x7f) * 32 + cc;
-          double s = 0.0;
-#pragma unroll
-          for (int b = 0; b < B; ++b) s += Lv[k][b] * y[b * CW];
-          A.cbuf[((size_t)dst[k] * B + a) * ncols + c] = s;
-        }
-    }
-    __syncwarp();
+    if (nparts > 1) group_sync();  // the results are in this warp's `own`: the other warps of the group push too
+    push(own);
   }
 #undef GEN_FENCE
 #undef GEN_KEEP
@@ -320,6 +337,12 @@ __global__ void __launch_bounds__(kGenWarps * 32) k_gen_solve(const GenSolveArgs
   double *linv = own + kGenClusterMax * 32;
   const int gwarp = blockIdx.x * kGenWarps + warp, nwarps = gridDim.x * kGenWarps;
   unsigned long long target = 0;
+  // the largest group (8, 4, 2 warps of a CTA per cluster) that still handles the level in one round
+  auto group_size = [&](int nclusters) {
+    int g = kGenWarps;
+    while (g > 1 && (long long)gridDim.x * (kGenWarps / g) < nclusters) g >>= 1;
+    return g;
+  };
   int np = 0;
   auto stamp = [&]() {
     if (A.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -333,20 +356,28 @@ __global__ void __launch_bounds__(kGenWarps * 32) k_gen_solve(const GenSolveArgs
   for (int c0 = 0; c0 < A.ncols; c0 += CW) {
     for (int t = 0; t < A.nlevels; ++t) {
       const int l0 = A.lvl_ptr[t], l1 = A.lvl_ptr[t + 1];
-      if (l1 - l0 <= (int)gridDim.x) {  // thin level: one cluster per CTA, its warps share the products
-        if (l0 + (int)blockIdx.x < l1) gen_cluster<B, true>(A, A.lvl_cl[l0 + blockIdx.x], c0, own, linv, lane, warp, kGenWarps);
-      } else {
-        for (int k = l0 + gwarp; k < l1; k += nwarps) gen_cluster<B, true>(A, A.lvl_cl[k], c0, own, linv, lane, 0, 1);
+      {
+        const int g = group_size(l1 - l0);  // warps per cluster at this level: 1, 2, 4 or 8
+        if (g == 1) {
+          for (int k = l0 + gwarp; k < l1; k += nwarps) gen_cluster<B, true>(A, A.lvl_cl[k], c0, own, linv, lane, 0, 1, 0);
+        } else {
+          const int k = l0 + (int)blockIdx.x * (kGenWarps / g) + warp / g;
+          if (k < l1) gen_cluster<B, true>(A, A.lvl_cl[k], c0, own, linv, lane, warp % g, g, 1 + warp / g);
+        }
       }
       gen_grid_sync(A.bar, target, gridDim.x);
       stamp();
     }
     for (int t = A.nlevels - 1; t >= 0; --t) {
       const int l0 = A.lvl_ptr[t], l1 = A.lvl_ptr[t + 1];
-      if (l1 - l0 <= (int)gridDim.x) {
-        if (l0 + (int)blockIdx.x < l1) gen_cluster<B, false>(A, A.lvl_cl[l0 + blockIdx.x], c0, own, linv, lane, warp, kGenWarps);
-      } else {
-        for (int k = l0 + gwarp; k < l1; k += nwarps) gen_cluster<B, false>(A, A.lvl_cl[k], c0, own, linv, lane, 0, 1);
+      {
+        const int g = group_size(l1 - l0);
+        if (g == 1) {
+          for (int k = l0 + gwarp; k < l1; k += nwarps) gen_cluster<B, false>(A, A.lvl_cl[k], c0, own, linv, lane, 0, 1, 0);
+        } else {
+          const int k = l0 + (int)blockIdx.x * (kGenWarps / g) + warp / g;
+          if (k < l1) gen_cluster<B, false>(A, A.lvl_cl[k], c0, own, linv, lane, warp % g, g, 1 + warp / g);
+        }
       }
       if (t > 0 || c0 + CW < A.ncols) gen_grid_sync(A.bar, target, gridDim.x);
       stamp();
