@@ -171,7 +171,32 @@ def select_best(f, certified) -> int:
     return w.value
 
 
+_nccl_preloaded = False
+
+
+def _preload_nccl():
+    """The library resolves NCCL with dlopen("libnccl.so.2") at first use.  In a Python process that also imports
+    torch, the copy torch was built against (site-packages/nvidia/nccl) must be the one behind that SONAME: the
+    dynamic loader shares one libnccl.so.2 per process, and an older system copy loaded first breaks a later
+    `import torch` (undefined symbol ncclDevCommCreate).  Load torch's copy first when it exists."""
+    global _nccl_preloaded
+    if _nccl_preloaded or os.environ.get("CORA_B200_NCCL_LIB"):
+        return
+    _nccl_preloaded = True
+    try:
+        import glob
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            for path in sorted(glob.glob(os.path.join(base, "nccl", "lib", "libnccl.so*"))):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass  # fall back to the loader's search path
+
+
 def nccl_unique_id() -> bytes:
+    _preload_nccl()
     buf = C.create_string_buffer(128)
     _check(load().cora_b200_nccl_unique_id(buf))
     return buf.raw
@@ -181,6 +206,7 @@ class NcclComm:
     """ncclComm_t created from a unique id (cora_b200_nccl_init)."""
 
     def __init__(self, device, world_size, rank, unique_id: bytes):
+        _preload_nccl()
         self._c = C.c_void_p()
         _check(load().cora_b200_nccl_init(C.byref(self._c), C.c_int(device), C.c_int(world_size), C.c_int(rank),
                                           C.c_char_p(unique_id)))

@@ -23,8 +23,11 @@ struct NcclApi {
 NcclApi &nccl() {
   static NcclApi api;
   if (api.lib) return api;
-  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  // CORA_B200_NCCL_LIB: explicit path.  Otherwise the SONAME: a copy already loaded in the process (e.g. the one
+  // bundled with PyTorch, which cora_b200/capi.py loads first) is reused by the dynamic loader.
+  const char *names[] = {getenv("CORA_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char *nm : names) {
+    if (!nm || !*nm) continue;
     api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
     if (api.lib) break;
   }
