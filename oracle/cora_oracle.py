@@ -93,6 +93,32 @@ REG_CHOLESKY = 3
 EXPLICIT, IMPLICIT = 0, 1  # include/CORA/CORA_types.h:52-56
 
 
+def pose_major_order(d, n, l, m):
+    """A permutation of the reference rows [d n | m | n | l]: range rows, then per pose its d rotation rows and its
+    translation row, then the landmarks (the last reference row -- the pinned translation -- stays last)."""
+    dn = d * n
+    poses = np.concatenate([dn * 0 + (np.arange(n)[:, None] * d + np.arange(d)[None, :]),
+                            (dn + m + np.arange(n))[:, None]], axis=1).reshape(-1)
+    lm = dn + m + n + np.arange(l)
+    if l == 0:  # the pinned row is the last pose's translation: already last in `poses`
+        return np.concatenate([dn + np.arange(m), poses])
+    return np.concatenate([dn + np.arange(m), poses, lm])
+
+
+class _PermutedLU:
+    """splu of P M P^T in the given order without further column permutation; solve() is in the original order."""
+
+    def __init__(self, M, order):
+        self.order = np.asarray(order)
+        Mp = M[self.order][:, self.order].tocsc()
+        self.lu = spla.splu(Mp, permc_spec="NATURAL", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+
+    def solve(self, B):
+        out = np.empty_like(B)
+        out[self.order] = self.lu.solve(np.ascontiguousarray(B[self.order]))
+        return out
+
+
 class Problem:
     """Restatement of CORA::Problem (explicit formulation; the translation-implicit one through
     set_formulation(IMPLICIT), src/CORA_problem.cpp:714-757)."""
@@ -315,7 +341,13 @@ class Problem:
             N = Q.shape[0]
             M = (Q + self.lambda_reg * sp.identity(N, format="csr")).tocsc()
             # pin_last_translation_ is const true (CORA_problem.h:72, :602-609)
-            self._chol = spla.splu(M[: N - 1, : N - 1].tocsc())
+            if getattr(self, "chol_ordering", "colamd") == "pose_major":
+                # Same matrix, same solution; only the elimination order differs.  SuperLU's default column ordering
+                # takes minutes on the 100k-pose chain (dense landmark columns); ranges first, then the poses in
+                # chain order (rotation rows + translation row together), landmarks last is banded + border.
+                self._chol = _PermutedLU(M[: N - 1, : N - 1].tocsc(), pose_major_order(self.d, self.n, self.l, self.m)[:-1])
+            else:
+                self._chol = spla.splu(M[: N - 1, : N - 1].tocsc())
         else:
             raise ValueError("The desired preconditioner is not implemented")
 

@@ -294,3 +294,54 @@ def test_peer_memory_product_world_size_one(lib):
         Y2 = h.get_work_vector(1, r)
         pp.close()
     assert np.abs(Y2 - Y).max() <= 1e-13 * np.abs(Y).max()
+
+
+@pytest.mark.gpu
+def test_million_pose_spmm_against_scipy(lib):
+    """BASELINE configs[4] at full size: the persistent SpMM kernel (k_spmm_persistent, the kernel behind
+    `roofline_cfg5`) on the 1M-pose problem (N = 4.2M, nnz = 43.4M, rank 5) against SciPy's CSR product of the same
+    matrix -- Problem::dataMatrixProduct, src/CORA_problem.cpp:742-757.  fp64, only the summation order differs."""
+    from cora_b200 import capi, synthetic
+    d, n, l, m, r = 3, 1_000_000, 100, 200_000, 5
+    arrays, _ = synthetic.make_arrays(n, l, m, d=d, seed=42)
+    Q = capi.assemble(d, n, l, arrays)
+    m = len(arrays["rg_w"])
+    X = np.random.default_rng(0).standard_normal((Q.shape[0], r))
+    with capi.Handle(d, n, m, n + l, Q, preconditioner=capi.PRECON_JACOBI) as h:
+        h.set_iterate(np.asfortranarray(X))
+        assert h.spmm_resident(2) > 0
+        Y = h.get_work_vector(1, r)
+    ref = Q @ X
+    assert np.abs(Y - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_full_size_regularized_cholesky_against_sparse_lu(lib):
+    """BASELINE configs[2] at full size (100k poses) with the reference's default preconditioner: the device chain
+    factorisation + apply against the NumPy oracle's sparse LU of (Q + lambda I)[:-1, :-1]
+    (src/CORA_problem.cpp:544-614, src/CORA_preconditioners.cpp:46-83), and the leading trust-region iterations with
+    that preconditioner against the oracle's TNT (same lambda on both sides)."""
+    from cora_b200 import capi, synthetic
+    d, n, l, m, r = 3, 100_000, 10, 20_000, 5
+    arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=42)
+    p = co.Problem.from_arrays(d, n, l, arrays, rank=r, preconditioner=co.REG_CHOLESKY)
+    p.chol_ordering = "pose_major"   # same matrix and solution; SuperLU's default ordering takes minutes at this size
+    # (a wide initial trust region: with Delta0 = 5 the first outer iterations are boundary steps with no CG at all)
+    prm = dict(max_iterations=4, max_TPCG_iterations=10, Delta0=1e5)
+    V = np.random.default_rng(1).standard_normal((p.N, r))
+    Q = capi.assemble(d, n, l, arrays)
+    with capi.Handle(d, n, len(arrays["rg_w"]), n + l, Q, preconditioner=capi.PRECON_REG_CHOLESKY) as h:
+        assert h.effective_preconditioner == capi.PRECON_REG_CHOLESKY
+        p.lambda_reg = h.reg_lambda
+        p.update_problem_data()
+        assert abs(Q - p.Q).max() <= 1e-9 * abs(p.Q).max()
+        x0 = p.project_to_manifold(synthetic.perturbed_ground_truth(d, n, l, arrays, gt, r, seed=0))
+        Z = h.precondition(V)
+        got = h.tnt(x0, capi.default_tnt_params(max_computation_time=0.0, **prm))
+    ref_pre = p.precondition(V)
+    assert np.abs(Z - ref_pre).max() <= 1e-8 * np.abs(ref_pre).max()
+    assert np.all(Z[-1] == 0.0)
+    ref = co.problem_tnt(p, x0, co.cora_tnt_params(**prm))
+    assert got.inner_iterations == ref.inner_iterations and sum(ref.inner_iterations) > 0
+    np.testing.assert_allclose(got.objective_values, ref.objective_values, rtol=1e-7)
+    np.testing.assert_allclose(got.preconditioned_gradient_norms[:3], ref.preconditioned_gradient_norms[:3], rtol=1e-6)
