@@ -34,6 +34,7 @@ struct GenSymDev {  // device copy of the GenSym arrays the kernels read
   DevBuf<unsigned long long> bar, prof;
   std::vector<int> lvl_sizes;
   int nlevels = 0, max_level_clusters = 0;
+  int grid = 0;  // cooperative grid of k_gen_solve (occupancy query cached per handle)
 };
 
 struct GenFactorDev {
@@ -426,11 +427,14 @@ inline void gen_solve_device(H *h, GenSymDev &D, GenFactorDev &F, int n, double 
   A.nlevels = D.nlevels; A.ld = ld; A.ncols = ncols;
   const size_t smem = gen_smem_bytes<B>();
   void *kfn = (void *)k_gen_solve<B>;
-  CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kGenWarps * 32, smem));
-  if (per_sm < 1) throw Error(CORA_B200_ERUNTIME, "general Cholesky solve kernel does not fit on an SM");
-  const int G = std::max(1, std::min(h->sm_count * per_sm, (D.max_level_clusters + kGenWarps - 1) / kGenWarps));
+  if (D.grid == 0) {
+    CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kGenWarps * 32, smem));
+    if (per_sm < 1) throw Error(CORA_B200_ERUNTIME, "general Cholesky solve kernel does not fit on an SM");
+    D.grid = std::max(1, std::min(h->sm_count * per_sm, (D.max_level_clusters + kGenWarps - 1) / kGenWarps));
+  }
+  const int G = D.grid;
   CUDA_CHECK(cudaMemsetAsync(D.bar.p, 0, sizeof(unsigned long long), s));
   static const bool profile = getenv("CORA_B200_GEN_PROFILE") != nullptr;
   const int nstamp = 1 + 2 * D.nlevels * ((ncols + 32 / B - 1) / (32 / B));
