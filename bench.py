@@ -452,6 +452,7 @@ def run_ours(args):
     clocks = sampler.stop()
     t_kernel = dev_time[0]   # CUDA events on the launching stream around the persistent kernel of every step
     _, grid, _ = h.phase_profile()
+    mxp = h.phase_profile_ctas()   # every CTA's clock for the same (last timed) launch as `prof`
 
     # ---- e2e leg: host buffers in, host buffers out, every step ----
     lib = capi.load()
@@ -595,7 +596,6 @@ def run_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md) (of fallback)"
-    mxp = h.phase_profile_ctas()
     h.close()
     cfg5 = None if args.no_cfg5 else roofline_cfg5(torch, dist, world, local, stream, peak)
     cfg2 = None if (args.no_cfg2 or rank != 0) else spmv_cfg2(local, stream)
