@@ -13,10 +13,13 @@
 //              handful of poses and the elimination tree is O(log n) separators high instead of O(n)
 //              (minimum degree alone: ~1000 levels on TIERS, nested dissection: ~50).
 //   symbolic   elimination tree, postorder, column structures by child merging; clusters = subtrees / tree
-//              paths of a few consecutive poses that one warp eliminates serially; clusters are levelled by
-//              their dependencies, so one level = one launch (gen_chol_dev.cuh).
-//   numeric    left-looking block Cholesky, L_vv^-1 kept explicitly (the solves multiply, never divide).
-//   solve      y_v = L_vv^-1 (b_v - sum_{u<v} L_vu y_u);  x_v = L_vv^-T (y_v - sum_{w>v} L_wv^T x_w).
+//              paths of at most 12 consecutive poses that one warp (or a group of warps) eliminates at once;
+//              clusters are levelled by their dependencies: one level = one sweep between two grid barriers of the
+//              cooperative solve kernel (gen_chol_dev.cuh).
+//   numeric    left-looking block Cholesky, L_vv^-1 kept explicitly, and the inverse of the in-cluster part of L
+//              for every cluster (the device eliminates a cluster by two products, never by a serial chain).
+//   solve      y_v = L_vv^-1 (b_v - sum_{u<v} L_vu y_u);  x_v = L_vv^-T (y_v - sum_{w>v} L_wv^T x_w)
+//              (gen_solve_host: the plain recurrences, the host reference of the device kernel).
 //
 // Everything here is plain host C++ (the CPU test hook pins it against the oracle's sparse LU); the device
 // solve lives in gen_chol_dev.cuh and consumes the arrays of GenSym unchanged.

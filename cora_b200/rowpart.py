@@ -9,16 +9,19 @@ range rows attached to them, and multiplies only its rows:
     odometry chain: one pose either side of the slab), whose rows are incomplete and never used;
   * the landmark rows are replicated: every rank holds all landmark values, computes the partial sums of the landmark
     rows over ITS measurements, and the partials are all-reduced (l x r doubles);
-  * before a product the ghost rows of the operand are fetched from their owners (one all-to-all of a few pose blocks
-    per boundary), GPU to GPU over NVLink through `torch.distributed` (NCCL); the local product is the library's
-    persistent SpMM kernel on the local handle.
+  * before a product the ghost rows of the operand are fetched from their owners, GPU to GPU over NVLink; the local
+    product is the library's persistent SpMM kernel on the local handle.  Two formulations of the exchange:
+    `RowPartitionedProduct` (collectives through `torch.distributed`: one all-to-all of the ghost pose blocks, one
+    all-reduce of the landmark rows) and `peer_product` (the library's own kernels over peer-mapped memory,
+    cora_b200/csrc/peer_product.cuh: flag barrier + pull, rank-ordered sum; no collective per product).
 
 No arithmetic happens here: this module builds index sets (host) and moves rows (`index_select` / `index_copy_` on the
 device buffers the C-ABI exposes, `all_to_all_single`, `all_reduce`).  `product_fn` abstracts the local product so the
 partition and exchange logic is covered on CPU (`gloo`, tests/test_rowpart_cpu.py) with a SciPy stand-in.
 
-At the BASELINE sizes this is latency bound, as SURVEY 8(e) predicts: a 1M-pose product is 163 us on one GPU, the
-exchange is two small collectives (~20-40 us each); replicas remain the throughput mode (bench.py).
+Measured at 1M poses, rank 5 (profiles/r02_rowpart.jsonl): 161 us per product on one GPU; with collectives 211 / 174 /
+174 us on 2 / 4 / 8 GPUs (two ~35 us collectives eat the gain, as SURVEY 8(e) predicts); with the peer-memory kernels
+116 / 82 / 64 us.  Replicas remain the throughput mode at the BASELINE sizes (bench.py).
 """
 import numpy as np
 
