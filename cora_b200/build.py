@@ -39,7 +39,7 @@ def _nvcc_base():
 
 def _deps_stamp(extra):
     h = hashlib.sha1()
-    files = [os.path.join(SRC, f) for f in sorted(os.listdir(SRC))]
+    files = [os.path.join(SRC, f) for f in sorted(os.listdir(SRC)) if f.endswith((".cu", ".cuh", ".hpp", ".h"))]
     files.append(os.path.join(HERE, "..", "include", "cora_b200.h"))
     files.append(os.path.abspath(__file__))
     for f in files:

@@ -178,11 +178,14 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
   // preconditioned, projected vector: Vout = proj_Y(M^-1 Rin); sums <Rin,Vout>, <Vout,Vout>
   const bool use_chain = (A.precond == CORA_B200_PRECON_REG_CHOLESKY);
   // Rin must be complete grid-wide (a barrier lies between its producer and this call)
-  auto precond_project = [&](const double *Y, double *Rin, double *Vout, double *acc2) {
+  // HPf != nullptr (chain factor only): Rnew = Rin + alphaf HPf is formed inside the apply and takes Rin's place
+  auto precond_project = [&](const double *Y, double *Rin, double *Vout, double *acc2, const double *HPf = nullptr,
+                             double alphaf = 0.0, double *Rnew = nullptr) {
     const double *Zin = nullptr;
     int zsrc = A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1;
     if (use_chain) {
-      chain_apply_persistent<D>(A.chain, c, Rin, v[V_Z]);
+      chain_apply_persistent<D>(A.chain, c, Rin, v[V_Z], HPf, alphaf, Rnew);
+      if (HPf != nullptr) Rin = Rnew;
       Zin = v[V_Z];
       zsrc = 2;
     }
@@ -265,9 +268,9 @@ __global__ void __launch_bounds__(CORA_PERSIST_THREADS, CORA_PERSIST_MINB) k_tnt
       double a2[2] = {0.0, 0.0};
       const double alpha = cg.alpha;
       if (use_chain) {
-        axpby_flat(c, 1.0, v[V_R], alpha, v[V_HP], v[V_R]);  // r += alpha Hp  (:377)
-        grid_sync(c);
-        precond_project(v[V_X], v[V_R], v[V_V], a2);
+        // r += alpha Hp (:377) inside the factor's first phase, written to the spare vector
+        precond_project(v[V_X], v[V_R], v[V_V], a2, v[V_HP], alpha, v[V_T1]);
+        swp(V_R, V_T1);
       } else if constexpr (STREAM) {
         stream_update<D, R, true>(L, A.sd, c, rg, v[V_X], v[V_HP], v[V_R], nullptr, v[V_V], alpha,
                                   A.precond == CORA_B200_PRECON_JACOBI ? 0 : 1, a2);

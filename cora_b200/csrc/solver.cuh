@@ -398,6 +398,7 @@ inline void tnt_persistent(H *h, int r, const cora_b200_tnt_params &p, cora_b200
     cd.nl = (int)C->levels.size();
     if (cd.nl > kMaxChainLevels) throw Error(CORA_B200_ERUNTIME, "chain factor has too many levels");
     cd.n = C->host.n; cd.l = C->host.l; cd.m = C->host.m;
+    cd.smem_doubles = (int)(smem / sizeof(double));
     cd.pinned_pose_row = C->host.pinned_pose_row; cd.pinned_landmark = C->host.pinned_landmark;
     for (int lv = 0; lv < cd.nl; ++lv) {
       ChainLevelDev *Dv = C->levels[lv];
