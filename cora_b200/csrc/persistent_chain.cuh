@@ -57,6 +57,25 @@ __device__ __forceinline__ void cta_sparse_dot(PCtx &c, int q0, int q1, const in
 }
 
 
+// Two-stage TMA pipeline over the CTA's contiguous share of the pose rows.  Loads through the LSU -- plain,
+// 16-byte or cp.async, any depth -- top out at ~2.3 TB/s in this kernel (every LSU-path variant of the phases
+// below measured 29-30 us for 65 MB: the SM's outstanding-miss capacity, not the request depth, is the limit
+// at 2 CTAs x 256 threads); bulk copies are not subject to it.  Stage s uses mbarrier c.mbar[s] with the
+// CTA-wide parity bits c.mpar0 / c.mpar1 (every thread waits, every thread flips).
+__device__ __forceinline__ void chain_tile_issue(PCtx &c, int buf, double *dst0, const double *src0, unsigned bytes0,
+                                                 double *dst1, const double *src1, unsigned bytes1) {
+  if (c.tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was last touched by generic accesses
+    mbar_expect_tx(c.mbar + buf, bytes0 + bytes1);
+    bulk_g2s(dst0, src0, bytes0, c.mbar + buf);
+    if (bytes1) bulk_g2s(dst1, src1, bytes1, c.mbar + buf);
+  }
+}
+__device__ __forceinline__ void chain_tile_wait(PCtx &c, int buf) {
+  mbar_wait(c.mbar + buf, buf ? c.mpar1 : c.mpar0);
+  if (buf) c.mpar1 ^= 1u; else c.mpar0 ^= 1u;
+}
+
 // ---- chunk substitutions out of shared memory ------------------------------------------------------------
 // forward_chunk / backward_chunk (chain_chol.cuh) walk a chunk with one global round trip per block step
 // (48 / 32 coefficients + the right-hand side): 7 steps x 6 + 5 levels were 220 us of a 400 us CG iteration at
@@ -71,9 +90,33 @@ struct ChainStage {
 };
 
 // fills k0, k1 of the CTA's contiguous share of K chunks
+// (levels with an even K are split on even boundaries: their coefficient runs can then move as 16-byte aligned
+// bulk copies)
 __device__ __forceinline__ void chain_cta_chunks(const PCtx &c, int K, int &k0, int &k1) {
-  k0 = (int)((long long)K * c.b / c.G);
-  k1 = (int)((long long)K * (c.b + 1) / c.G);
+  const int sh = (K & 1) ? 0 : 1, Kh = K >> sh;
+  k0 = (int)((unsigned)Kh * (unsigned)c.b / (unsigned)c.G) << sh;
+  k1 = (int)((unsigned)Kh * (unsigned)(c.b + 1) / (unsigned)c.G) << sh;
+}
+
+// rows [0, nrows) x chunks [k0, k0 + KCb) of a [row][K] coefficient array -> dst[row * KCb + kk].  Even K, k0 and
+// KCb: one bulk copy per row on mbarrier c.mbar[0] (the LSU path tops out at ~2.3 TB/s in this kernel, see
+// chain_tile_issue below); otherwise 8-byte cp.async.  Returns whether chain_tile_wait(c, 0) must follow.
+__device__ __forceinline__ bool chain_stage_coeff(PCtx &c, double *dst, const double *src, int nrows, int K, int k0, int KCb) {
+  const bool bulk = ((K | k0 | KCb) & 1) == 0 && (unsigned)nrows * (unsigned)KCb * 8u < (1u << 20);
+  if (bulk) {
+    if (c.tid == 0) mbar_expect_tx(c.mbar, (unsigned)nrows * (unsigned)KCb * 8u);
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int row = c.tid; row < nrows; row += c.nth)
+      bulk_g2s(dst + (size_t)row * KCb, src + (size_t)row * K + k0, (unsigned)KCb * 8u, c.mbar);
+  } else {
+    const unsigned nC = (unsigned)(nrows * KCb), uk = (unsigned)KCb;
+    for (unsigned idx = c.tid; idx < nC; idx += c.nth) {
+      const unsigned row = idx / uk, kk = idx - row * uk;
+      cp_async8(dst + idx, src + (size_t)row * K + k0 + kk);
+    }
+  }
+  return bulk;
 }
 
 // Shared-memory layout of a batch: the global [j][e][K] layout restricted to the batch's chunks ([row][kk]),
@@ -112,6 +155,7 @@ __device__ __forceinline__ void chain_forward_level_staged(const ChainDev &C, PC
   }
   const int nbatch = (kb1 - kb0 + KC - 1) / KC;
   KC = (kb1 - kb0 + nbatch - 1) / nbatch;
+  if (!(K & 1) && (KC & 1) && (KC + 1) * per_chunk <= st.avail && (KC + 1) * ld <= c.nth) ++KC;  // even batches: bulk copies
   for (int k0 = kb0; k0 < kb1; k0 += KC) {
     const int KCb = min(KC, kb1 - k0);
     const int TS = KCb * ld;  // active threads, stride of the per-thread slots
@@ -122,21 +166,19 @@ __device__ __forceinline__ void chain_forward_level_staged(const ChainDev &C, PC
     double *sBw = sC + (size_t)Lb * 3 * BB * KCb;         // [Lb*2*BB][KCb]  backward coefficients (top level only)
     double *sU = sBw + (top ? (size_t)Lb * 2 * BB * KCb : 0);  // [KCb][BB]
     double *sB = sU + (size_t)KCb * BB;                   // [(j*B+a)*nslot + s][TS]
-    {
-      const unsigned nC = (unsigned)(Lb * 3 * BB * KCb), uk = (unsigned)KCb;
+    const bool bulk = !top && chain_stage_coeff(c, sC, fwd, Lb * 3 * BB, K, k0, KCb);
+    if (top) {  // one chunk: cp.async
+      const unsigned nC = (unsigned)(Lb * 3 * BB * KCb), nW = (unsigned)(Lb * 2 * BB * KCb), uk = (unsigned)KCb;
       for (unsigned idx = c.tid; idx < nC; idx += c.nth) {
         const unsigned row = idx / uk, kk = idx - row * uk;
         cp_async8(sC + idx, fwd + (size_t)row * K + k0 + kk);
       }
-      if (top) {
-        const unsigned nW = (unsigned)(Lb * 2 * BB * KCb);
-        for (unsigned idx = c.tid; idx < nW; idx += c.nth) {
-          const unsigned row = idx / uk, kk = idx - row * uk;
-          cp_async8(sBw + idx, bwd + (size_t)row * K + k0 + kk);
-        }
+      for (unsigned idx = c.tid; idx < nW; idx += c.nth) {
+        const unsigned row = idx / uk, kk = idx - row * uk;
+        cp_async8(sBw + idx, bwd + (size_t)row * K + k0 + kk);
       }
-      for (int idx = c.tid; idx < KCb * BB; idx += c.nth) cp_async8(sU + idx, UR + (size_t)k0 * BB + idx);
     }
+    for (int idx = c.tid; idx < KCb * BB; idx += c.nth) cp_async8(sU + idx, UR + (size_t)k0 * BB + idx);
     const int t = c.tid;
     const bool active = t < TS;
     const int kk = active ? t / ld : 0, col = t - kk * ld, k = k0 + kk;
@@ -172,6 +214,7 @@ __device__ __forceinline__ void chain_forward_level_staged(const ChainDev &C, PC
     }
     cp_async_commit();
     cp_async_wait<0>();
+    if (bulk) chain_tile_wait(c, 0);
     __syncthreads();
     if (active) {
       double w[B], acc[B];
@@ -270,6 +313,7 @@ __device__ __forceinline__ void chain_backward_level_staged(const ChainDev &C, P
   }
   const int nbatch = (kb1 - kb0 + KC - 1) / KC;
   KC = (kb1 - kb0 + nbatch - 1) / nbatch;
+  if (!(K & 1) && (KC & 1) && (KC + 1) * per_chunk <= st.avail && (KC + 1) * ld <= c.nth) ++KC;  // even batches: bulk copies
   for (int k0 = kb0; k0 < kb1; k0 += KC) {
     const int KCb = min(KC, kb1 - k0);
     const int TS = KCb * ld;
@@ -277,13 +321,7 @@ __device__ __forceinline__ void chain_backward_level_staged(const ChainDev &C, P
     if (k0 + KCb == K) Lb = max(Lb, G.interior(K - 1));
     double *sC = st.buf;                            // [Lb*2*BB][KCb]
     double *sB = sC + (size_t)Lb * 2 * BB * KCb;    // [j*B+a][TS]
-    {
-      const unsigned nC = (unsigned)(Lb * 2 * BB * KCb), uk = (unsigned)KCb;
-      for (unsigned idx = c.tid; idx < nC; idx += c.nth) {
-        const unsigned row = idx / uk, kk = idx - row * uk;
-        cp_async8(sC + idx, bwd + (size_t)row * K + k0 + kk);
-      }
-    }
+    const bool bulk = chain_stage_coeff(c, sC, bwd, Lb * 2 * BB, K, k0, KCb);
     const int t = c.tid;
     const bool active = t < TS;
     const int kk = active ? t / ld : 0, col = t - kk * ld, k = k0 + kk;
@@ -304,6 +342,7 @@ __device__ __forceinline__ void chain_backward_level_staged(const ChainDev &C, P
     }
     cp_async_commit();
     cp_async_wait<0>();
+    if (bulk) chain_tile_wait(c, 0);
     __syncthreads();
     if (active) {
       if (G.has_right(k))
@@ -330,25 +369,6 @@ __device__ __forceinline__ void chain_backward_level_staged(const ChainDev &C, P
     }
     __syncthreads();
   }
-}
-
-// Two-stage TMA pipeline over the CTA's contiguous share of the pose rows.  Loads through the LSU -- plain,
-// 16-byte or cp.async, any depth -- top out at ~2.3 TB/s in this kernel (every LSU-path variant of the phases
-// below measured 29-30 us for 65 MB: the SM's outstanding-miss capacity, not the request depth, is the limit
-// at 2 CTAs x 256 threads); bulk copies are not subject to it.  Stage s uses mbarrier c.mbar[s] with the
-// CTA-wide parity bits c.mpar0 / c.mpar1 (every thread waits, every thread flips).
-__device__ __forceinline__ void chain_tile_issue(PCtx &c, int buf, double *dst0, const double *src0, unsigned bytes0,
-                                                 double *dst1, const double *src1, unsigned bytes1) {
-  if (c.tid == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was last touched by generic accesses
-    mbar_expect_tx(c.mbar + buf, bytes0 + bytes1);
-    bulk_g2s(dst0, src0, bytes0, c.mbar + buf);
-    if (bytes1) bulk_g2s(dst1, src1, bytes1, c.mbar + buf);
-  }
-}
-__device__ __forceinline__ void chain_tile_wait(PCtx &c, int buf) {
-  mbar_wait(c.mbar + buf, buf ? c.mpar1 : c.mpar0);
-  if (buf) c.mpar1 ^= 1u; else c.mpar0 ^= 1u;
 }
 
 template <int D>
