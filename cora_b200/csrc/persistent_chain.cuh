@@ -392,6 +392,25 @@ __device__ __forceinline__ void chain_apply_persistent(const ChainDev &C, PCtx &
   ph_begin(c);
   // ---- pre: Y = V on pose rows minus the range elimination (k_chain_pre); the landmark rows' reductions
   // over their incident ranges are split in chunks over all CTAs and combined after the border phase ----
+  // the CTA's share of the pose rows: even boundaries (16-byte aligned tiles for any r), the last CTA to the end
+  const size_t row0c = (np * (size_t)c.b / c.G) & ~(size_t)1;
+  const size_t row1c = c.b == c.G - 1 ? np : ((np * (size_t)(c.b + 1) / c.G) & ~(size_t)1);
+  const size_t row1e = row1c & ~(size_t)1;  // tiles cover [row0c, row1e); an odd last row is handled on its own
+  const int stage_avail = C.smem_doubles - (int)(c.sW - c.smem) - 2 * c.nth;  // behind the scratch of cta_sparse_dot
+  double *const stage_base = c.sW + 2 * c.nth;
+  // pass 1 streams V (and HP) through two shared-memory tiles; the first two are requested before anything else
+  const int nin = HP != nullptr ? 2 : 1;
+  const int TRP = min((stage_avail / 2) / (nin * r), 2048) & ~1;
+  const bool pre_tiles = TRP >= 2 && row1e > row0c;
+  const int pre_tstride = TRP * nin * r;
+  const int pre_ntile = pre_tiles ? (int)((row1e - row0c + TRP - 1) / TRP) : 0;
+  auto pre_issue = [&](int t) {
+    double *sV = stage_base + (t & 1) * pre_tstride, *sH = sV + TRP * r;
+    const size_t ra = row0c + (size_t)t * TRP;
+    const unsigned by = (unsigned)(min((size_t)TRP, row1e - ra) * r * sizeof(double));
+    chain_tile_issue(c, t & 1, sV, V + ra * r, by, sH, HP != nullptr ? HP + ra * r : nullptr, HP != nullptr ? by : 0u);
+  };
+  for (int t = 0; t < min(2, pre_ntile); ++t) pre_issue(t);
   for (int item = c.b; item < l * C.max_rinc_chunks; item += c.G) {
     const int j = item / C.max_rinc_chunks, ch = item - j * C.max_rinc_chunks;
     const int q0 = C.rinc_ptr[n + j] + ch * kLmChunk, q1 = min(C.rinc_ptr[n + j + 1], q0 + kLmChunk);
@@ -400,35 +419,17 @@ __device__ __forceinline__ void chain_apply_persistent(const ChainDev &C, PCtx &
     if (c.tid < r) C.part_pre[((size_t)j * C.max_rinc_chunks + ch) * r + c.tid] = c.sW[c.nth + c.tid];
     __syncthreads();
   }
-  // the CTA's share of the pose rows: even boundaries (16-byte aligned tiles for any r), the last CTA to the end
-  const size_t row0c = (np * (size_t)c.b / c.G) & ~(size_t)1;
-  const size_t row1c = c.b == c.G - 1 ? np : ((np * (size_t)(c.b + 1) / c.G) & ~(size_t)1);
-  const size_t row1e = row1c & ~(size_t)1;  // tiles cover [row0c, row1e); an odd last row is handled on its own
-  const int stage_avail = C.smem_doubles - (int)(c.sW - c.smem) - 2 * c.nth;  // behind the scratch of cta_sparse_dot
-  double *const stage_base = c.sW + 2 * c.nth;
   {
-    // pass 1: Vnew = V + alpha HP, Y = Vnew on the pose rows, streamed through two shared-memory tiles
-    const int nin = HP != nullptr ? 2 : 1;
-    const int TRP = min((stage_avail / 2) / (nin * r), 2048) & ~1;
+    // pass 1: Vnew = V + alpha HP, Y = Vnew on the pose rows
     const long long pin0 = (long long)C.pinned_pose_row * r, pin1 = pin0 + r;  // (no pinned row: [-r, 0))
     auto emit = [&](size_t e, double vv) {
       if (HP != nullptr) Vnew[e] = vv;
       Y[e] = ((long long)e >= pin0 && (long long)e < pin1) ? 0.0 : vv;
     };
-    if (TRP >= 2 && row1e > row0c) {
-      const int tstride = TRP * nin * r;
-      const int ntile = (int)((row1e - row0c + TRP - 1) / TRP);
-      auto issue = [&](int t) {
-        double *sV = stage_base + (t & 1) * tstride, *sH = sV + TRP * r;
-        const size_t ra = row0c + (size_t)t * TRP;
-        const unsigned by = (unsigned)(min((size_t)TRP, row1e - ra) * r * sizeof(double));
-        chain_tile_issue(c, t & 1, sV, V + ra * r, by, sH, HP != nullptr ? HP + ra * r : nullptr, HP != nullptr ? by : 0u);
-      };
-      issue(0);
-      for (int t = 0; t < ntile; ++t) {
-        if (t + 1 < ntile) issue(t + 1);  // its buffer was released by the barrier that ended tile t-1
+    if (pre_tiles) {
+      for (int t = 0; t < pre_ntile; ++t) {
         chain_tile_wait(c, t & 1);
-        const double *sV = stage_base + (t & 1) * tstride, *sH = sV + TRP * r;
+        const double *sV = stage_base + (t & 1) * pre_tstride, *sH = sV + TRP * r;
         const size_t ra = row0c + (size_t)t * TRP;
         const int ne = (int)(min((size_t)TRP, row1e - ra) * r);
         for (int i = c.tid; i < ne; i += c.nth) {
@@ -437,6 +438,7 @@ __device__ __forceinline__ void chain_apply_persistent(const ChainDev &C, PCtx &
           emit(ra * r + i, vv);
         }
         __syncthreads();
+        if (t + 2 < pre_ntile) pre_issue(t + 2);  // into the buffer this barrier released
       }
     } else {
       for (size_t e = row0c * r + c.tid; e < row1e * r; e += c.nth) emit(e, veff(e));
@@ -499,6 +501,22 @@ __device__ __forceinline__ void chain_apply_persistent(const ChainDev &C, PCtx &
   }
   // ---- every CTA: u_j = (v_L[j] - range partials) - border partials ; z_L = S_L^-1 u  (l x r values each,
   // fixed summation order) ----
+  // the pose rows of the post phase (z_P = y_P - W z_L: W is np x l, 65 MB with Y at 100k poses) stream through the
+  // two-stage TMA tile pipeline; its first two tiles are requested before the landmark solve and the range rows
+  const int post_avail = C.smem_doubles - (int)(c.sW - c.smem) - ((2 * l * r + 1) & ~1);
+  const int TRW = min((post_avail / 2) / (l + r), 2048) & ~1;
+  double *const tb = c.sW + ((2 * l * r + 1) & ~1);
+  const bool post_tiles = TRW >= 2 && row1e > row0c;
+  const int post_tstride = TRW * (l + r);
+  const int post_ntile = post_tiles ? (int)((row1e - row0c + TRW - 1) / TRW) : 0;
+  auto post_issue = [&](int t) {
+    double *sWt = tb + (t & 1) * post_tstride, *sYt = sWt + TRW * l;
+    const size_t ra = row0c + (size_t)t * TRW;
+    const size_t nr = min((size_t)TRW, row1e - ra);
+    chain_tile_issue(c, t & 1, sWt, C.W + ra * l, (unsigned)(nr * l * sizeof(double)), sYt, Y + ra * r,
+                     (unsigned)(nr * r * sizeof(double)));
+  };
+  for (int t = 0; t < min(2, post_ntile); ++t) post_issue(t);
   double *uS = c.sW, *zL = c.sW + l * r;
   for (int i = c.tid; i < l * r; i += c.nth) {
     const int jj = i / r, cc = i - jj * r;
@@ -549,28 +567,10 @@ __device__ __forceinline__ void chain_apply_persistent(const ChainDev &C, PCtx &
       }
       Z[e] = out;
     }
-    // pose rows: z_P = y_P - W z_L streams W (np x l) and Y once.  A flat loop keeps ~1 KB per warp in flight
-    // (26 us for 65 MB at 100k poses); here the CTA's contiguous share of the rows moves through two shared-memory
-    // tiles filled by cp.async, tile t+1 in flight while tile t is computed
-    // pose rows: z_P = y_P - W z_L streams W (np x l) and Y once, through the two-stage TMA tile pipeline
-    const int avail = C.smem_doubles - (int)(c.sW - c.smem) - ((2 * l * r + 1) & ~1);
-    const int TRW = min((avail / 2) / (l + r), 2048) & ~1;
-    double *tb = c.sW + ((2 * l * r + 1) & ~1);
-    if (TRW >= 2 && row1e > row0c) {
-      const int tstride = TRW * (l + r);
-      const int ntile = (int)((row1e - row0c + TRW - 1) / TRW);
-      auto issue = [&](int t) {
-        double *sWt = tb + (t & 1) * tstride, *sYt = sWt + TRW * l;
-        const size_t ra = row0c + (size_t)t * TRW;
-        const size_t nr = min((size_t)TRW, row1e - ra);
-        chain_tile_issue(c, t & 1, sWt, C.W + ra * l, (unsigned)(nr * l * sizeof(double)), sYt, Y + ra * r,
-                         (unsigned)(nr * r * sizeof(double)));
-      };
-      issue(0);
-      for (int t = 0; t < ntile; ++t) {
-        if (t + 1 < ntile) issue(t + 1);
+    if (post_tiles) {
+      for (int t = 0; t < post_ntile; ++t) {
         chain_tile_wait(c, t & 1);
-        const double *sWt = tb + (t & 1) * tstride, *sYt = sWt + TRW * l;
+        const double *sWt = tb + (t & 1) * post_tstride, *sYt = sWt + TRW * l;
         const size_t ra = row0c + (size_t)t * TRW;
         const int nr = (int)min((size_t)TRW, row1e - ra);
         for (int i = c.tid; i < nr * r; i += c.nth) {
@@ -581,6 +581,7 @@ __device__ __forceinline__ void chain_apply_persistent(const ChainDev &C, PCtx &
           Z[ra * r + i] = ((int)(ra + lr) == C.pinned_pose_row) ? 0.0 : sacc;
         }
         __syncthreads();
+        if (t + 2 < post_ntile) post_issue(t + 2);
       }
     } else {
       for (size_t e = row0c * r + c.tid; e < row1e * r; e += c.nth) {
