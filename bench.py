@@ -487,6 +487,16 @@ def run_ours(args):
             comm = restarts.make_native_comm(dist, local)      # communicator created (and warmed) before the clock starts
         h.set_preconditioner(capi.PRECON_REG_CHOLESKY)
         reg_lambda = h.reg_lambda
+        # one untimed certification of a random point: CUDA loads kernels lazily, and the first use of the
+        # certification kernels (Cholesky test, shift search, Lanczos) cost 0.05-0.9 s of module loading inside the
+        # first solve (scripts/solve_leg_repeat.py: 0.30 s in the first solve of a process, 0.03 s afterwards)
+        tw = time.perf_counter()
+        for rw in (x0.shape[1], d):  # the staircase rank and the rank of the refinement stage
+            # (a full-rank random point: the sv-ratio shortcut does not fire, the eigen-search runs)
+            h.certify_solution(h.project_to_manifold(np.random.default_rng(1).uniform(-1.0, 1.0, size=(x0.shape[0], rw))),
+                               0.05, max(10, d + 2))
+        torch.cuda.synchronize()
+        t_cert_warm = time.perf_counter() - tw
         barrier()
         ts = time.perf_counter()
         out = h.solve(x0, max_rank=7, params=capi.default_tnt_params(max_computation_time=0.0))
@@ -513,7 +523,10 @@ def run_ours(args):
                       "psd_test_of_refined_solution": {"certified": bool(cert.is_certified), "branch": h.last_cert_branch,
                                                        "seconds": t_psd, "eta": eta},
                       "note": "rank 5 staircase (max rank 7) + rounding + refinement through cora_b200_solve(), host "
-                              "buffers in/out; restart seed = rank; the reference's own stopping rules (src/CORA.cpp:95-109)"}
+                              "buffers in/out; restart seed = rank; the reference's own stopping rules (src/CORA.cpp:95-109); "
+                              "one untimed certification call before the clock loads the certification kernels (CUDA lazy "
+                              "module loading)",
+                      "untimed_certification_warmup_s": t_cert_warm}
         if rank == 0:
             # the same staircase with relative_decrease_tolerance = stepsize_tolerance = 0: the rank-5 solve then runs on to
             # the optimum of the rank-5 relaxation, where the certificate is the Cholesky PSD test of S + eta I itself
