@@ -131,6 +131,31 @@ def test_regularized_cholesky_tnt(lib, name, r):
                                rtol=1e-6)
 
 
+@pytest.mark.parametrize("d,n,r", [(3, 901, 9), (2, 1203, 7), (3, 2000, 6)])
+def test_regularized_cholesky_tnt_synthetic_ranks(lib, d, n, r):
+    """The chain factor applied inside the persistent kernel (chunk batches staged in shared memory, residual
+    update folded into its first phase, TMA tile pipelines) at ranks without a rank-specialised kernel (any-rank
+    tile pipeline: d = 3 rank 9, d = 2 rank 7), with an odd number of poses, and at a streaming rank on several
+    levels; warm start, so that STPCG iterates: the leading outer iterations against the oracle's sparse LU
+    (src/CORA_preconditioners.cpp:46-83, IterativeSolvers.h:377)."""
+    from cora_b200 import capi, synthetic
+    l, m = 5, n // 3
+    p = make_synthetic(n=n, l=l, m=m, d=d, seed=7, rank=r, preconditioner=co.REG_CHOLESKY)
+    p.update_problem_data()
+    arrays, gt = synthetic.make_arrays(n, l, m, d=d, seed=7)
+    x0 = p.project_to_manifold(synthetic.perturbed_ground_truth(d, n, l, arrays, gt, r, seed=1))
+    ref = co.problem_tnt(p, x0, co.cora_tnt_params(max_iterations=8))
+    with make_handle(p, preconditioner=capi.PRECON_REG_CHOLESKY) as h:
+        h.reg_lambda = p.lambda_reg
+        got = h.tnt(x0, _params(max_iterations=8))
+    assert sum(ref.inner_iterations) > 30
+    k = 7
+    for a, b in zip(got.inner_iterations[:k], ref.inner_iterations[:k]):
+        assert a == b if b < 12 else abs(a - b) <= 1, (got.inner_iterations, ref.inner_iterations)
+    np.testing.assert_allclose(got.objective_values[:k], ref.objective_values[:k], rtol=1e-6)
+    np.testing.assert_allclose(got.preconditioned_gradient_norms[:5], ref.preconditioned_gradient_norms[:5], rtol=1e-5)
+
+
 @pytest.mark.parametrize("d,r", [(2, 2), (2, 4), (3, 3), (3, 8), (3, 9), (3, 12)])
 def test_warm_start_cg_heavy_all_ranks(lib, d, r):
     """CG-heavy regime (warm start: STPCG runs tens of iterations per call) at ranks that exercise every
