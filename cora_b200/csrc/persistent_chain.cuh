@@ -67,7 +67,7 @@ __device__ __forceinline__ void chain_tile_issue(PCtx &c, int buf, double *dst0,
   if (c.tid == 0) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was last touched by generic accesses
     mbar_expect_tx(c.mbar + buf, bytes0 + bytes1);
-    bulk_g2s(dst0, src0, bytes0, c.mbar + buf);
+    if (bytes0) bulk_g2s(dst0, src0, bytes0, c.mbar + buf);  // (no landmarks: the W tile is empty)
     if (bytes1) bulk_g2s(dst1, src1, bytes1, c.mbar + buf);
   }
 }
